@@ -1,0 +1,181 @@
+/*
+ * lccrf.h -- C ABI of liblccrf.so: the B200 (sm_100a) implementation of LC-CRF-SLAM's
+ * data-parallel hot path (fully connected CRF over permutohedral lattices + long-term unary).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the LC-CRF-SLAM tree).
+ * The C++ header mirror in lc-crf-slam_b200/densecrf/ (DenseCRF3D<M>, PottsPotential3D<M,F>,
+ * DenseCRFCPU<M>, PottsPotentialCPU<M,F>, PermutohedralLatticeCPU) forwards to these calls,
+ * so src/Tracking.cc:1919-1930 and Thirdparty/DenseCRF/examples/example_cpu.cpp:80-102
+ * compile unchanged.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - All pointers are HOST pointers unless the name says "_dev".
+ *   - Return value: 0 = LCCRF_OK, negative = error; lccrf_last_error() gives the message
+ *     (thread-local).  The reference API is all-void with no validation (SURVEY 8b "Errors");
+ *     the C++ mirror aborts with the message on a non-zero status.
+ *   - There is NO CPU fallback: every computing call fails with LCCRF_ERR_CUDA when no
+ *     sm_100 device / driver is usable.
+ *   - N == 0 is a valid no-op everywhere.
+ *   - Thread safety: one lccrf_ctx per host thread (or external locking); handles created
+ *     from a ctx share its stream.
+ */
+#ifndef LCCRF_H
+#define LCCRF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCCRF_OK 0
+#define LCCRF_ERR_ARG (-1)     /* bad argument (null pointer, unsupported d / L, ...) */
+#define LCCRF_ERR_CUDA (-2)    /* CUDA runtime / driver failure, or no device */
+#define LCCRF_ERR_STATE (-3)   /* call sequence error (e.g. step before start) */
+#define LCCRF_ERR_RANGE (-4)   /* a lattice key left the reference's `short` range (permutohedral_cpu.h:373) */
+
+#define LCCRF_MAX_D 7          /* feature dimensions supported by the lattice (reference uses 2 and 5) */
+#define LCCRF_MAX_L 64         /* labels (reference uses 2; the golden demo uses 21) */
+#define LCCRF_MAX_K 8          /* pairwise potentials per CRF */
+
+typedef struct lccrf_ctx lccrf_ctx;
+typedef struct lccrf_lattice lccrf_lattice;
+typedef struct lccrf_crf lccrf_crf;
+typedef struct lccrf_frames lccrf_frames;
+
+/* ---------------------------------------------------------------- context ---------------- */
+const char *lccrf_version(void);
+const char *lccrf_last_error(void);
+int lccrf_device_count(void);
+/* one context per GPU (and per host thread): owns a stream, memory pools, workspaces */
+int lccrf_ctx_create(int device, lccrf_ctx **out);
+void lccrf_ctx_destroy(lccrf_ctx *ctx);
+/* run on an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int lccrf_ctx_set_stream(lccrf_ctx *ctx, void *cuda_stream);
+int lccrf_ctx_sync(lccrf_ctx *ctx);
+/* number of liblccrf kernels launched on this context so far (bench.py "gpu_launches") */
+uint64_t lccrf_ctx_kernel_launches(const lccrf_ctx *ctx);
+/* option knobs: "graphs" (0/1, CUDA-graph replay of lccrf_frames_run), "fused" (0/1, per-problem
+ * fused mean-field kernel when the lattices fit shared memory) */
+int lccrf_ctx_set_option(lccrf_ctx *ctx, const char *name, int value);
+
+/* ---------------------------------------------------------------- lattice ---------------- */
+/* Replaces PermutohedralLatticeCPU::init(feature, feature_size, N)
+ *   Thirdparty/DenseCRF/include/permutohedral_cpu.h:241-424 (SSE branch, incl. the phantom
+ *   lanes k in [N, ceil4(N)) that the reference inserts into its hash table, :294-299,364-377).
+ * features: [N*d] row-major.  Vertex ids, barycentric bit patterns and the neighbour table are
+ * bit-identical to the reference. */
+int lccrf_lattice_create(lccrf_ctx *ctx, const float *features, int d, int N, lccrf_lattice **out);
+void lccrf_lattice_destroy(lccrf_lattice *lat);
+/* N_, d_, M_ of permutohedral_cpu.h:187 */
+int lccrf_lattice_sizes(const lccrf_lattice *lat, int *N, int *d, int *V);
+/* offset_[N*(d+1)], barycentric_[N*(d+1)] (permutohedral_cpu.h:375-376) and
+ * blur_neighbors_[(d+1)*V] as {n1,n2} int pairs indexed [j*V+i] (:418-419).  Any pointer may be NULL. */
+int lccrf_lattice_export(const lccrf_lattice *lat, int *offset, float *bary, int *nbr);
+/* Replaces PermutohedralLatticeCPU::compute(out, in, value_size) with default windowing
+ *   permutohedral_cpu.h:634-699.  in/out: [N*L]; out may alias in (pairwise3d.h:24). */
+int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L);
+
+/* ---------------------------------------------------------------- dense CRF -------------- */
+/* Replaces DenseCRF3D<M>(N) / DenseCRFCPU<M>(N)   densecrf3d.h:23-28, densecrf_cpu.h:22-27 */
+int lccrf_crf_create(lccrf_ctx *ctx, int N, int L, lccrf_crf **out);
+/* ~DenseCRF: also destroys the potentials it owns (densecrf_base.h:41-45) */
+void lccrf_crf_destroy(lccrf_crf *crf);
+/* setUnaryEnergy(const float*)   densecrf3d.h:41-43 ; unary: [N*L] */
+int lccrf_crf_set_unary(lccrf_crf *crf, const float *unary);
+/* setUnaryEnergyFromLabel(label, confidences)   densecrf3d.h:108-130.
+ * The three energy tables are the values the reference computes at :109-114
+ * (u = -log(1/M), n[m] = -log((1-c[m])/(M-1)), p[m] = -log(c[m])); the C++ mirror evaluates
+ * them with the same expressions in the caller's translation unit.  label: [N], -1 = unknown. */
+int lccrf_crf_set_unary_from_label(lccrf_crf *crf, const short *label, float u_energy,
+                                   const float *n_energies, const float *p_energies);
+/* SetUnaryEnergtForPositiveNode(idx, m, value)   densecrf3d.h:132-134 */
+int lccrf_crf_set_unary_entry(lccrf_crf *crf, int idx, int m, float value);
+/* addPairwiseEnergy(new PottsPotential3D<M,d>(features, N, w)) -- lattice build + norm_
+ *   pairwise3d.h:20-28 (== pairwise_cpu.h:15-23) + densecrf_base.h:54.  features: [N*d]. */
+int lccrf_crf_add_potts(lccrf_crf *crf, const float *features, int d, float w);
+/* addPairwiseEnergy(PottsPotentialCPU<M,F>::FromImage<T>(W,H,weight,posdev,features,featuredev))
+ *   pairwise_cpu.h:34-50; features assembled on the device.  img: [W*H*(F-2)] u8 or f32 (NULL if F==2). */
+int lccrf_crf_add_potts_image(lccrf_crf *crf, int W, int H, float w, float posdev, const void *img,
+                              int img_is_u8, int F, float featuredev);
+/* startInference / stepInference(relax) / inference(n, with_map, relax)   densecrf_base.h:65-91 */
+int lccrf_crf_start(lccrf_crf *crf);
+int lccrf_crf_step(lccrf_crf *crf, float relax);
+int lccrf_crf_inference(lccrf_crf *crf, int n_iterations, int with_map, float relax);
+/* buildMap()   densecrf3d.h:137-151 (for the step-by-step API) */
+int lccrf_crf_build_map(lccrf_crf *crf);
+/* getMap() / getProbability(): library-owned HOST arrays, valid until the next call that
+ * changes them or destroy (densecrf_base.h:74-75).  NULL before they exist. */
+const short *lccrf_crf_map(lccrf_crf *crf);
+const float *lccrf_crf_prob(lccrf_crf *crf);
+/* lattice sizes of potential k (tests / diagnostics) */
+int lccrf_crf_potts_vertices(const lccrf_crf *crf, int k, int *V);
+
+/* Plugin support: user-defined PairwisePotential::apply(out, in, tmp) on host pointers
+ * (densecrf_base.h:12-19).  These expose the driver's pieces on host arrays so that the C++
+ * mirror can interleave foreign potentials with built-in ones; all arithmetic still runs on
+ * the GPU.
+ *   potts_apply: PottsPotential3D::apply   pairwise3d.h:73-78   out[N*L] += w*norm*filter(in)
+ *   exp_and_normalize: DenseCRF3D<M>::expAndNormalize   densecrf3d.h:71-98 */
+int lccrf_crf_potts_apply(lccrf_crf *crf, int k, float *out, const float *in, float *tmp);
+int lccrf_exp_and_normalize(lccrf_ctx *ctx, float *out, const float *in, int N, int L, float scale,
+                            float relax);
+
+/* ---------------------------------------------------------------- long-term unary -------- */
+/* TUM3.yaml:81-101 / Tracking.cc:151-171 */
+typedef struct lccrf_slam_params {
+    float w1, w2;
+    float u_alpha, stdev_alpha; /* mRpjErrorMean, mRpjErrorStdev */
+    float u_beta, stdev_beta;   /* mObservMean, mObservStdev */
+    float u_gamma, stdev_gamma; /* mGcMean, mGcStdev (epipolar prior; not used on this path) */
+    float point3d_stdev, point2d_stdev;
+    float u_depth, pth, confidence;
+    int iters;                  /* Tracking.cc:1929 */
+} lccrf_slam_params;
+
+/* Replaces Tracking::ComputeMapPointErrAndObserv over all N map points
+ *   src/Tracking.cc:1803-1839, on a flat snapshot of the pointer graph:
+ *   xyz [N*3]; CSR obs_ptr [N+1]; obs_kf [nnz]; obs_uv [nnz*2]; kf_pose [nKF*12] rows of [Rcw|tcw];
+ *   kf_intr [nKF*4] fx fy cx cy; kf_bounds [nKF*4] mnMinX mnMaxX mnMinY mnMaxY.
+ * Out: observs [N] (as float, Tracking.cc:1867), error [N], depth [N].  Observations are
+ * accumulated in CSR order (the reference iterates a std::map in pointer order). */
+int lccrf_map_point_unary(lccrf_ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                          const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                          const float *kf_bounds, float *observs, float *error, float *depth);
+/* Replaces Tracking::RroughClassify   src/Tracking.cc:1961-2013.  p4: per-point epipolar
+ * likelihood (double, mvFeatureMatchProb[fid]) or NULL when the map is empty (:1994). */
+int lccrf_rough_classify(lccrf_ctx *ctx, int N, const float *observs, const float *error, const float *depth,
+                         const double *p4, const lccrf_slam_params *prm, short *label);
+
+/* ---------------------------------------------------------------- batched frames --------- */
+/* B independent per-frame CRF problems (the body of Tracking::DynamicDetectionWithCRF,
+ * src/Tracking.cc:1871-1930, for B frames at once): RroughClassify -> setUnaryEnergyFromLabel ->
+ * appearanceKernel + smoothKernel -> inference(iters, true).  Points are concatenated; problem b
+ * owns points [prob_ptr[b], prob_ptr[b+1]).  energies = {u, n, p} as in set_unary_from_label
+ * with one shared confidence (Tracking.cc:1921). */
+int lccrf_frames_create(lccrf_ctx *ctx, int B, const int *prob_ptr, const lccrf_slam_params *prm,
+                        const float *energies3, lccrf_frames **out);
+void lccrf_frames_destroy(lccrf_frames *fr);
+/* per-frame vectors gathered at Tracking.cc:1849-1870: observs/error/depth [NT], kp2d [NT*2] */
+int lccrf_frames_set_inputs(lccrf_frames *fr, const float *observs, const float *error, const float *depth,
+                            const float *kp2d);
+/* alternatively derive observs/error/depth on the device from a map snapshot (lccrf_map_point_unary layout);
+ * every point must have >= 1 observation (Tracking.cc:1858 drops the others before the CRF) */
+int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                                const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                                const float *kf_bounds, const float *kp2d);
+/* device-resident run of the whole batch, asynchronous on the context's stream */
+int lccrf_frames_run(lccrf_frames *fr);
+/* copy results back (synchronises): map [NT] (0 = moving, 1 = static), prob [NT*2]; either may be NULL */
+int lccrf_frames_get_outputs(lccrf_frames *fr, short *map, float *prob);
+/* diagnostics: init labels [NT], unary-derived vectors, per-problem lattice sizes [B*2] */
+int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth,
+                           int *V);
+/* algorithmic bytes of one lccrf_frames_run by the SURVEY 8(d) formulas with the actual V (valid after a run) */
+int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_iteration, double *unary);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCCRF_H */

@@ -1,0 +1,397 @@
+"""lc-crf-slam_b200 -- B200 (sm_100a) implementation of LC-CRF-SLAM's CRF hot path.
+
+The product is `liblccrf.so` (CUDA kernels behind the C ABI of include/lccrf.h) plus the C++
+header mirror of the reference's DenseCRF API in `densecrf/`.  This Python module is plumbing
+only: a ctypes binding used by tests/ and bench.py.  There is no CPU fallback -- every call
+fails loudly when the library or a B200 is missing.
+
+Import with `importlib.import_module("lc-crf-slam_b200")` (the directory name is not a valid
+identifier).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblccrf.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(HERE), "include")
+DENSECRF_INCLUDE_DIR = os.path.join(HERE, "densecrf")
+
+from . import synth  # noqa: E402,F401
+
+
+def build(verbose: bool = False) -> str:
+    """Compile liblccrf.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class LccrfError(RuntimeError):
+    pass
+
+
+class SlamParams(C.Structure):
+    """lccrf_slam_params (TUM3.yaml:81-101)."""
+    _fields_ = [(n, C.c_float) for n in (
+        "w1", "w2", "u_alpha", "stdev_alpha", "u_beta", "stdev_beta", "u_gamma", "stdev_gamma",
+        "point3d_stdev", "point2d_stdev", "u_depth", "pth", "confidence")] + [("iters", C.c_int)]
+
+    @classmethod
+    def make(cls, **kw) -> "SlamParams":
+        p = cls()
+        d = dict(synth.SLAM_PARAMS)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(p, k, v)
+        return p
+
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_sp = C.POINTER(C.c_short)
+_vp = C.c_void_p
+
+# every symbol include/lccrf.h declares: (restype, argtypes)
+SYMBOLS = {
+    "lccrf_version": (C.c_char_p, []),
+    "lccrf_last_error": (C.c_char_p, []),
+    "lccrf_device_count": (C.c_int, []),
+    "lccrf_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "lccrf_ctx_destroy": (None, [_vp]),
+    "lccrf_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "lccrf_ctx_sync": (C.c_int, [_vp]),
+    "lccrf_ctx_kernel_launches": (C.c_uint64, [_vp]),
+    "lccrf_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "lccrf_lattice_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lccrf_lattice_destroy": (None, [_vp]),
+    "lccrf_lattice_sizes": (C.c_int, [_vp, _ip, _ip, _ip]),
+    "lccrf_lattice_export": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "lccrf_lattice_filter": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "lccrf_crf_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lccrf_crf_destroy": (None, [_vp]),
+    "lccrf_crf_set_unary": (C.c_int, [_vp, _vp]),
+    "lccrf_crf_set_unary_from_label": (C.c_int, [_vp, _vp, C.c_float, _vp, _vp]),
+    "lccrf_crf_set_unary_entry": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float]),
+    "lccrf_crf_add_potts": (C.c_int, [_vp, _vp, C.c_int, C.c_float]),
+    "lccrf_crf_add_potts_image": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, C.c_int, C.c_int, C.c_float]),
+    "lccrf_crf_start": (C.c_int, [_vp]),
+    "lccrf_crf_step": (C.c_int, [_vp, C.c_float]),
+    "lccrf_crf_inference": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float]),
+    "lccrf_crf_build_map": (C.c_int, [_vp]),
+    "lccrf_crf_map": (_sp, [_vp]),
+    "lccrf_crf_prob": (_fp, [_vp]),
+    "lccrf_crf_potts_vertices": (C.c_int, [_vp, C.c_int, _ip]),
+    "lccrf_crf_potts_apply": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "lccrf_exp_and_normalize": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float]),
+    "lccrf_map_point_unary": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_rough_classify": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(SlamParams), _vp]),
+    "lccrf_frames_create": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(SlamParams), _vp, C.POINTER(_vp)]),
+    "lccrf_frames_destroy": (None, [_vp]),
+    "lccrf_frames_set_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_set_map_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_run": (C.c_int, [_vp]),
+    "lccrf_frames_get_outputs": (C.c_int, [_vp, _vp, _vp]),
+    "lccrf_frames_get_debug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen liblccrf.so and bind every declared symbol.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LccrfError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+_libm = None
+
+
+def _logf(x) -> np.float32:
+    """glibc logf -- what std::log(float) resolves to in src/Tracking.cc's translation unit."""
+    global _libm
+    if _libm is None:
+        _libm = C.CDLL("libm.so.6")
+        _libm.logf.restype = C.c_float
+        _libm.logf.argtypes = [C.c_float]
+    return np.float32(_libm.logf(C.c_float(float(x))))
+
+
+def label_energies(L: int, conf: float) -> np.ndarray:
+    """{u, n, p} of densecrf3d.h:109-114 for one shared confidence: -log(1/M), -log((1-c)/(M-1)), -log(c)."""
+    f = np.float32
+    return np.array([-_logf(f(1.0) / f(L)), -_logf((f(1.0) - f(conf)) / f(L - 1)), -_logf(f(conf))], dtype=np.float32)
+
+
+class Context:
+    """lccrf_ctx: one per GPU."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        h = _vp()
+        self._check(self.lib.lccrf_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self._check(self.lib.lccrf_ctx_set_stream(self.h, _vp(stream)))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise LccrfError(f"liblccrf error {rc}: {self.lib.lccrf_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lccrf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.lccrf_ctx_sync(self.h))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.lccrf_ctx_set_option(self.h, name.encode(), value))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.lccrf_ctx_kernel_launches(self.h))
+
+    # ---- free functions ----
+    def exp_and_normalize(self, x, scale: float, relax: float = 1.0, prev=None) -> np.ndarray:
+        x = _arr(x, np.float32)
+        N, L = x.shape
+        out = _arr(prev, np.float32).copy() if prev is not None else np.zeros_like(x)
+        self._check(self.lib.lccrf_exp_and_normalize(self.h, _ptr(out), _ptr(x), N, L, scale, relax))
+        return out
+
+    def map_point_unary(self, snap):
+        N = snap.n
+        ob, er, de = (np.empty(N, dtype=np.float32) for _ in range(3))
+        self._check(self.lib.lccrf_map_point_unary(
+            self.h, N, _ptr(snap.xyz), _ptr(snap.obs_ptr), _ptr(snap.obs_kf), _ptr(snap.obs_uv),
+            snap.kf_pose.shape[0], _ptr(snap.kf_pose), _ptr(snap.kf_intr), _ptr(snap.kf_bounds),
+            _ptr(ob), _ptr(er), _ptr(de)))
+        return ob, er, de
+
+    def rough_classify(self, observs, error, depth, prm: SlamParams, p4=None) -> np.ndarray:
+        observs, error, depth = (_arr(a, np.float32) for a in (observs, error, depth))
+        p4 = _arr(p4, np.float64)
+        lab = np.empty(observs.size, dtype=np.int16)
+        self._check(self.lib.lccrf_rough_classify(self.h, observs.size, _ptr(observs), _ptr(error), _ptr(depth),
+                                                  _ptr(p4), C.byref(prm), _ptr(lab)))
+        return lab
+
+
+class Lattice:
+    """lccrf_lattice: PermutohedralLatticeCPU replacement."""
+
+    def __init__(self, ctx: Context, features):
+        self.ctx = ctx
+        f = _arr(features, np.float32)
+        self.N, self.d = f.shape
+        h = _vp()
+        ctx._check(ctx.lib.lccrf_lattice_create(ctx.h, _ptr(f), self.d, self.N, C.byref(h)))
+        self.h = h
+        v = C.c_int()
+        ctx._check(ctx.lib.lccrf_lattice_sizes(self.h, None, None, C.byref(v)))
+        self.V = v.value
+
+    def export(self):
+        D = self.d + 1
+        off = np.empty((self.N, D), dtype=np.int32)
+        bary = np.empty((self.N, D), dtype=np.float32)
+        nbr = np.empty((D, self.V, 2), dtype=np.int32)
+        self.ctx._check(self.ctx.lib.lccrf_lattice_export(self.h, _ptr(off), _ptr(bary), _ptr(nbr)))
+        return off, bary, nbr
+
+    def filter(self, x) -> np.ndarray:
+        x = _arr(x, np.float32)
+        L = x.size // self.N if self.N else 1
+        out = np.empty_like(x)
+        self.ctx._check(self.ctx.lib.lccrf_lattice_filter(self.h, _ptr(out), _ptr(x), L))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lccrf_lattice_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DenseCRF:
+    """lccrf_crf: DenseCRF3D<M> / DenseCRFCPU<M> replacement (method names follow densecrf_base.h)."""
+
+    def __init__(self, ctx: Context, N: int, L: int):
+        self.ctx, self.N, self.L = ctx, N, L
+        h = _vp()
+        ctx._check(ctx.lib.lccrf_crf_create(ctx.h, N, L, C.byref(h)))
+        self.h = h
+
+    def setUnaryEnergy(self, unary):
+        u = _arr(unary, np.float32)
+        self.ctx._check(self.ctx.lib.lccrf_crf_set_unary(self.h, _ptr(u)))
+
+    def setUnaryEnergyFromLabel(self, label, confidence=0.5, energies=None):
+        lab = _arr(label, np.int16)
+        if energies is None:
+            energies = label_energies(self.L, confidence)
+        n_en = np.full(self.L, energies[1], dtype=np.float32)
+        p_en = np.full(self.L, energies[2], dtype=np.float32)
+        self.ctx._check(self.ctx.lib.lccrf_crf_set_unary_from_label(self.h, _ptr(lab), float(energies[0]), _ptr(n_en), _ptr(p_en)))
+
+    def SetUnaryEnergtForPositiveNode(self, idx, m, value):
+        self.ctx._check(self.ctx.lib.lccrf_crf_set_unary_entry(self.h, idx, m, value))
+
+    def addPairwiseEnergy(self, features, w: float):
+        f = _arr(features, np.float32)
+        self.ctx._check(self.ctx.lib.lccrf_crf_add_potts(self.h, _ptr(f), f.shape[1], w))
+
+    def addPairwiseFromImage(self, W, H, w, posdev, img=None, featuredev=0.0):
+        if img is None:
+            self.ctx._check(self.ctx.lib.lccrf_crf_add_potts_image(self.h, W, H, w, posdev, None, 0, 2, 0.0))
+        else:
+            is_u8 = img.dtype == np.uint8
+            a = np.ascontiguousarray(img) if is_u8 else _arr(img, np.float32)
+            F = 2 + a.size // (W * H)
+            self.ctx._check(self.ctx.lib.lccrf_crf_add_potts_image(self.h, W, H, w, posdev, _ptr(a), int(is_u8), F, featuredev))
+
+    def potts_vertices(self, k: int) -> int:
+        v = C.c_int()
+        self.ctx._check(self.ctx.lib.lccrf_crf_potts_vertices(self.h, k, C.byref(v)))
+        return v.value
+
+    def potts_apply(self, k, out, inp):
+        out = _arr(out, np.float32).copy()
+        inp = _arr(inp, np.float32)
+        tmp = np.empty_like(out)
+        self.ctx._check(self.ctx.lib.lccrf_crf_potts_apply(self.h, k, _ptr(out), _ptr(inp), _ptr(tmp)))
+        return out, tmp
+
+    def startInference(self):
+        self.ctx._check(self.ctx.lib.lccrf_crf_start(self.h))
+
+    def stepInference(self, relax=1.0):
+        self.ctx._check(self.ctx.lib.lccrf_crf_step(self.h, relax))
+
+    def inference(self, n_iterations, with_map=False, relax=1.0):
+        self.ctx._check(self.ctx.lib.lccrf_crf_inference(self.h, n_iterations, int(with_map), relax))
+
+    def buildMap(self):
+        self.ctx._check(self.ctx.lib.lccrf_crf_build_map(self.h))
+
+    def getMap(self):
+        p = self.ctx.lib.lccrf_crf_map(self.h)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(max(self.N, 1),))[:self.N].copy()
+
+    def getProbability(self):
+        p = self.ctx.lib.lccrf_crf_prob(self.h)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(max(self.N, 1) * self.L,))[:self.N * self.L].copy().reshape(self.N, self.L)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lccrf_crf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Frames:
+    """lccrf_frames: B independent per-frame CRF problems (Tracking.cc:1871-1930) in one launch sequence."""
+
+    def __init__(self, ctx: Context, n_points, prm: SlamParams | None = None, energies=None):
+        self.ctx = ctx
+        self.prm = prm or SlamParams.make()
+        n_points = np.asarray(n_points, dtype=np.int64)
+        self.B = int(n_points.size)
+        self.prob_ptr = np.zeros(self.B + 1, dtype=np.int32)
+        np.cumsum(n_points, out=self.prob_ptr[1:])
+        self.NT = int(self.prob_ptr[-1])
+        self.energies = label_energies(2, self.prm.confidence) if energies is None else _arr(energies, np.float32)
+        h = _vp()
+        ctx._check(ctx.lib.lccrf_frames_create(ctx.h, self.B, _ptr(self.prob_ptr), C.byref(self.prm), _ptr(self.energies), C.byref(h)))
+        self.h = h
+
+    def set_inputs(self, observs, error, depth, kp2d):
+        a = [_arr(x, np.float32) for x in (observs, error, depth, kp2d)]
+        self._keep = a
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_inputs(self.h, *[_ptr(x) for x in a]))
+
+    def set_map_inputs(self, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d):
+        xyz, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d = (_arr(x, np.float32) for x in (xyz, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d))
+        obs_ptr, obs_kf = _arr(obs_ptr, np.int32), _arr(obs_kf, np.int32)
+        self._keep = [xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d]
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_map_inputs(
+            self.h, _ptr(xyz), _ptr(obs_ptr), _ptr(obs_kf), _ptr(obs_uv), kf_pose.shape[0], _ptr(kf_pose),
+            _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d)))
+
+    def run(self):
+        self.ctx._check(self.ctx.lib.lccrf_frames_run(self.h))
+
+    def get_outputs(self, map_out=None, prob_out=None, want_prob=True):
+        mp = np.empty(self.NT, dtype=np.int16) if map_out is None else map_out
+        pr = (np.empty((self.NT, 2), dtype=np.float32) if prob_out is None else prob_out) if want_prob else None
+        self.ctx._check(self.ctx.lib.lccrf_frames_get_outputs(self.h, _ptr(mp), _ptr(pr)))
+        return mp, pr
+
+    def get_debug(self):
+        lab = np.empty(self.NT, dtype=np.int16)
+        ob, er, de = (np.empty(self.NT, dtype=np.float32) for _ in range(3))
+        V = np.empty((self.B, 2), dtype=np.int32)
+        self.ctx._check(self.ctx.lib.lccrf_frames_get_debug(self.h, _ptr(lab), _ptr(ob), _ptr(er), _ptr(de), _ptr(V)))
+        return dict(init_label=lab, observs=ob, error=er, depth=de, V=V)
+
+    def algorithmic_bytes(self):
+        t, i, u = C.c_double(), C.c_double(), C.c_double()
+        self.ctx._check(self.ctx.lib.lccrf_frames_algorithmic_bytes(self.h, C.byref(t), C.byref(i), C.byref(u)))
+        return dict(total=t.value, per_iteration=i.value, unary=u.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lccrf_frames_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

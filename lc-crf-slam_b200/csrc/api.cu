@@ -1,0 +1,981 @@
+// api.cu -- the extern "C" boundary (include/lccrf.h) and the host-side engine objects.
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace lccrf {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------ memory
+int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    if (zero) {
+        e = cudaMemsetAsync(*p, 0, bytes, ctx->stream);
+        if (e != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
+    }
+    return LCCRF_OK;
+}
+
+void dev_free(Ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+int ctx_scratch(Ctx *ctx, Ctx::Scratch &s, size_t bytes, bool pinned) {
+    if (bytes <= s.bytes && s.p) return LCCRF_OK;
+    size_t want = bytes + bytes / 4 + 256;
+    ctx->scratch_gen++;
+    if (pinned) {
+        if (s.p) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFreeHost(s.p);
+        }
+        s.p = nullptr;
+        s.bytes = 0;
+        LCCRF_CUDA(cudaHostAlloc(&s.p, want, cudaHostAllocDefault));
+    } else {
+        if (s.p) cudaFreeAsync(s.p, ctx->stream);
+        s.p = nullptr;
+        s.bytes = 0;
+        LCCRF_CUDA(cudaMallocAsync(&s.p, want, ctx->stream));
+    }
+    s.bytes = want;
+    return LCCRF_OK;
+}
+
+static void scratch_release(Ctx *ctx, Ctx::Scratch &s, bool pinned) {
+    if (!s.p) return;
+    if (pinned) cudaFreeHost(s.p);
+    else cudaFreeAsync(s.p, ctx->stream);
+    s.p = nullptr;
+    s.bytes = 0;
+}
+
+static int check_status(Ctx *ctx) {  // synchronises
+    LCCRF_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_status & 1) {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
+        return fail(LCCRF_ERR_RANGE, "lattice key outside the reference's short range (permutohedral_cpu.h:373)");
+    }
+    return LCCRF_OK;
+}
+
+static int batch_init(Ctx *ctx, Batch &b, int B, const int *prob_ptr, int L, bool with_state) {
+    b.ctx = ctx;
+    b.B = B;
+    b.L = L;
+    b.h_prob_ptr.assign(prob_ptr, prob_ptr + B + 1);
+    if (b.h_prob_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "prob_ptr[0] must be 0");
+    b.maxN = 0;
+    for (int i = 0; i < B; i++) {
+        int n = b.h_prob_ptr[i + 1] - b.h_prob_ptr[i];
+        if (n < 0) return fail(LCCRF_ERR_ARG, "prob_ptr must be non-decreasing");
+        if (n > b.maxN) b.maxN = n;
+    }
+    if (b.maxN > (1 << 22)) return fail(LCCRF_ERR_ARG, "more than 2^22 points in one problem (fixed-point splat range)");
+    b.NT = b.h_prob_ptr[B];
+    LCCRF_TRY(dev_alloc(ctx, (void **)&b.prob_ptr, (size_t)(B + 1) * sizeof(int)));
+    LCCRF_CUDA(cudaMemcpyAsync(b.prob_ptr, b.h_prob_ptr.data(), (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                               ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (with_state) {
+        const size_t n = (size_t)(b.NT > 0 ? b.NT : 1) * L * sizeof(float);
+        LCCRF_TRY(dev_alloc(ctx, (void **)&b.unary, n));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&b.cur, n));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&b.next, n));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&b.tmp, n));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&b.map, (size_t)(b.NT > 0 ? b.NT : 1) * sizeof(short)));
+    }
+    return LCCRF_OK;
+}
+
+static void batch_release(Ctx *ctx, Batch &b) {
+    for (auto *ls : b.lat) lattice_set_destroy(ctx, ls);
+    b.lat.clear();
+    dev_free(ctx, b.prob_ptr);
+    dev_free(ctx, b.unary);
+    dev_free(ctx, b.cur);
+    dev_free(ctx, b.next);
+    dev_free(ctx, b.tmp);
+    dev_free(ctx, b.map);
+    b.prob_ptr = nullptr;
+    b.unary = b.cur = b.next = b.tmp = nullptr;
+    b.map = nullptr;
+}
+
+}  // namespace lccrf
+
+using namespace lccrf;
+
+// ------------------------------------------------------------------ opaque handle types
+struct lccrf_ctx {
+    Ctx c;
+};
+
+struct lccrf_lattice {
+    Ctx *ctx = nullptr;
+    Batch b;
+    LatticeSet *ls = nullptr;
+    int V = 0;
+    float *io = nullptr;  // device in/out buffer for filter calls
+    size_t io_bytes = 0;
+};
+
+struct lccrf_crf {
+    Ctx *ctx = nullptr;
+    Batch b;
+    bool started = false;
+    float *h_prob = nullptr;  // pinned
+    short *h_map = nullptr;   // pinned
+    bool prob_fresh = false, map_fresh = false, map_built = false;
+    float *d_energies = nullptr;  // n_en[L], p_en[L]
+};
+
+struct lccrf_frames {
+    Ctx *ctx = nullptr;
+    Batch b;
+    lccrf_slam_params prm;
+    float energies[3];
+    float *d_en = nullptr;  // n_en[2], p_en[2]
+    float *observs = nullptr, *error = nullptr, *depth = nullptr, *kp2d = nullptr;  // device [NT], [NT*2]
+    short *label = nullptr;
+    float *feat = nullptr;  // [NT*2]
+    // map snapshot (optional)
+    bool from_map = false;
+    float *xyz = nullptr, *obs_uv = nullptr, *kf_pose = nullptr, *kf_intr = nullptr, *kf_bounds = nullptr;
+    int *obs_ptr = nullptr, *obs_kf = nullptr;
+    void *kf_packed = nullptr;
+    int nKF = 0;
+    long long nnz = 0, nnz_cap = 0;
+    int nKF_cap = 0;
+    bool have_inputs = false, ran = false;
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_launches = 0, graph_gen = 0;
+};
+
+extern "C" {
+
+const char *lccrf_version(void) { return "lccrf-b200 0.1 (sm_100a)"; }
+const char *lccrf_last_error(void) { return g_err.c_str(); }
+
+int lccrf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int lccrf_ctx_create(int device, lccrf_ctx **out) {
+    if (!out) return fail(LCCRF_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LCCRF_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(LCCRF_ERR_ARG, "device index out of range");
+    LCCRF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LCCRF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LCCRF_ERR_CUDA, std::string("liblccrf is built for sm_100a only; device is ") + prop.name);
+    auto *h = new lccrf_ctx();
+    h->c.device = device;
+    cudaError_t es = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) {
+        delete h;
+        return fail(LCCRF_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
+    }
+    h->c.own_stream = true;
+    // keep freed blocks cached in the stream-ordered pool: per-frame CRF objects allocate and free constantly
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (cudaMalloc((void **)&h->c.d_status, sizeof(int)) != cudaSuccess ||
+        cudaMemset(h->c.d_status, 0, sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->c.h_status, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+        delete h;
+        return fail(LCCRF_ERR_CUDA, "status word allocation failed");
+    }
+    *out = h;
+    return LCCRF_OK;
+}
+
+void lccrf_ctx_destroy(lccrf_ctx *h) {
+    if (!h) return;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &s : c->hash_keys) scratch_release(c, s, false);
+    scratch_release(c, c->hash_first, false);
+    scratch_release(c, c->hash_id, false);
+    scratch_release(c, c->ent_slot, false);
+    scratch_release(c, c->blk_cnt, false);
+    scratch_release(c, c->misc, false);
+    scratch_release(c, c->feat, false);
+    scratch_release(c, c->dev_io, false);
+    scratch_release(c, c->pinned_in, true);
+    scratch_release(c, c->pinned_out, true);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_status);
+    cudaFreeHost(c->h_status);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete h;
+}
+
+int lccrf_ctx_set_stream(lccrf_ctx *h, void *cuda_stream) {
+    if (!h) return fail(LCCRF_ERR_ARG, "ctx is NULL");
+    Ctx *c = &h->c;
+    LCCRF_CUDA(cudaSetDevice(c->device));
+    LCCRF_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+        c->own_stream = false;
+    } else {
+        LCCRF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return LCCRF_OK;
+}
+
+int lccrf_ctx_sync(lccrf_ctx *h) {
+    if (!h) return fail(LCCRF_ERR_ARG, "ctx is NULL");
+    LCCRF_CUDA(cudaStreamSynchronize(h->c.stream));
+    return LCCRF_OK;
+}
+
+uint64_t lccrf_ctx_kernel_launches(const lccrf_ctx *h) { return h ? h->c.launches : 0; }
+
+int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
+    if (!h || !name) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (!strcmp(name, "graphs")) h->c.opt_graphs = value;
+    else if (!strcmp(name, "fused")) h->c.opt_fused = value;
+    else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);
+    return LCCRF_OK;
+}
+
+// ------------------------------------------------------------------ lattice
+int lccrf_lattice_create(lccrf_ctx *h, const float *features, int d, int N, lccrf_lattice **out) {
+    if (!h || !out || (N > 0 && !features)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (N < 0) return fail(LCCRF_ERR_ARG, "N < 0");
+    *out = nullptr;
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    auto *lat = new lccrf_lattice();
+    lat->ctx = ctx;
+    int pp[2] = {0, N};
+    int rc = batch_init(ctx, lat->b, 1, pp, 1, false);
+    if (rc == LCCRF_OK) rc = lattice_set_create(ctx, lat->b, d, 1.0f, 0, &lat->ls);
+    if (rc == LCCRF_OK) rc = ctx_scratch(ctx, ctx->feat, (size_t)(N > 0 ? N : 1) * d * sizeof(float));
+    if (rc == LCCRF_OK && N > 0) {
+        cudaError_t e = cudaMemcpyAsync(ctx->feat.p, features, (size_t)N * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc == LCCRF_OK) rc = lattice_set_build(ctx, lat->b, lat->ls, (const float *)ctx->feat.p);
+    if (rc == LCCRF_OK) {
+        cudaError_t e = cudaMemcpyAsync(ctx->h_status, lat->ls->vbase + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+        else lat->V = *ctx->h_status;
+    }
+    if (rc == LCCRF_OK) rc = check_status(ctx);
+    if (rc != LCCRF_OK) {
+        lccrf_lattice_destroy(lat);
+        return rc;
+    }
+    *out = lat;
+    return LCCRF_OK;
+}
+
+void lccrf_lattice_destroy(lccrf_lattice *lat) {
+    if (!lat) return;
+    cudaSetDevice(lat->ctx->device);
+    if (lat->ls) lattice_set_destroy(lat->ctx, lat->ls);
+    lat->ls = nullptr;
+    batch_release(lat->ctx, lat->b);
+    dev_free(lat->ctx, lat->io);
+    delete lat;
+}
+
+int lccrf_lattice_sizes(const lccrf_lattice *lat, int *N, int *d, int *V) {
+    if (!lat) return fail(LCCRF_ERR_ARG, "lattice is NULL");
+    if (N) *N = lat->b.NT;
+    if (d) *d = lat->ls->d;
+    if (V) *V = lat->V;
+    return LCCRF_OK;
+}
+
+int lccrf_lattice_export(const lccrf_lattice *lat, int *offset, float *bary, int *nbr) {
+    if (!lat) return fail(LCCRF_ERR_ARG, "lattice is NULL");
+    Ctx *ctx = lat->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const LatticeSet *ls = lat->ls;
+    const size_t nent = (size_t)lat->b.NT * ls->D;
+    // B == 1: global ids == reference ids (vbase[0] == 0)
+    if (offset && nent) LCCRF_CUDA(cudaMemcpyAsync(offset, ls->offset, nent * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bary && nent) LCCRF_CUDA(cudaMemcpyAsync(bary, ls->bary, nent * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nbr && lat->V > 0) {
+        for (int j = 0; j < ls->D; j++)
+            LCCRF_CUDA(cudaMemcpyAsync(nbr + 2 * (size_t)j * lat->V, ls->nbr + (size_t)j * ls->Vcap,
+                                       (size_t)lat->V * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L) {
+    if (!lat || !out || !in) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (L < 1 || L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "L out of range");
+    Ctx *ctx = lat->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)lat->b.NT * L;
+    if (n == 0) return LCCRF_OK;
+    LCCRF_TRY(lattice_set_ensure_L(ctx, lat->ls, L));
+    if (lat->io_bytes < 2 * n * sizeof(float)) {
+        dev_free(ctx, lat->io);
+        lat->io = nullptr;
+        lat->io_bytes = 0;
+        LCCRF_TRY(dev_alloc(ctx, (void **)&lat->io, 2 * n * sizeof(float)));
+        lat->io_bytes = 2 * n * sizeof(float);
+    }
+    float *d_in = lat->io, *d_out = lat->io + n;
+    LCCRF_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_TRY(filter_full(ctx, lat->b, lat->ls, d_out, d_in, L, /*generic_range=*/true));
+    LCCRF_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+// ------------------------------------------------------------------ dense CRF
+int lccrf_crf_create(lccrf_ctx *h, int N, int L, lccrf_crf **out) {
+    if (!h || !out) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (N < 0 || L < 1 || L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "N or L out of range");
+    *out = nullptr;
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    auto *crf = new lccrf_crf();
+    crf->ctx = ctx;
+    int pp[2] = {0, N};
+    int rc = batch_init(ctx, crf->b, 1, pp, L, true);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&crf->d_energies, 2 * (size_t)L * sizeof(float));
+    if (rc == LCCRF_OK) {
+        const size_t n = (size_t)(N > 0 ? N : 1);
+        if (cudaHostAlloc((void **)&crf->h_prob, n * L * sizeof(float), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void **)&crf->h_map, n * sizeof(short), cudaHostAllocDefault) != cudaSuccess)
+            rc = fail(LCCRF_ERR_CUDA, "pinned result buffers: cudaHostAlloc failed");
+    }
+    if (rc != LCCRF_OK) {
+        lccrf_crf_destroy(crf);
+        return rc;
+    }
+    *out = crf;
+    return LCCRF_OK;
+}
+
+void lccrf_crf_destroy(lccrf_crf *crf) {
+    if (!crf) return;
+    cudaSetDevice(crf->ctx->device);
+    cudaStreamSynchronize(crf->ctx->stream);
+    batch_release(crf->ctx, crf->b);
+    dev_free(crf->ctx, crf->d_energies);
+    if (crf->h_prob) cudaFreeHost(crf->h_prob);
+    if (crf->h_map) cudaFreeHost(crf->h_map);
+    delete crf;
+}
+
+int lccrf_crf_set_unary(lccrf_crf *crf, const float *unary) {
+    if (!crf || (!unary && crf->b.NT > 0)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)crf->b.NT * crf->b.L;
+    if (n) LCCRF_CUDA(cudaMemcpyAsync(crf->b.unary, unary, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller may free `unary` right away (densecrf3d.h:42 copies)
+    return LCCRF_OK;
+}
+
+int lccrf_crf_set_unary_from_label(lccrf_crf *crf, const short *label, float u_energy, const float *n_energies,
+                                   const float *p_energies) {
+    if (!crf || !n_energies || !p_energies || (!label && crf->b.NT > 0)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const int NT = crf->b.NT, L = crf->b.L;
+    for (int i = 0; i < NT; i++)
+        if (label[i] < -1 || label[i] >= L) return fail(LCCRF_ERR_ARG, "label outside [-1, L)");
+    LCCRF_CUDA(cudaMemcpyAsync(crf->d_energies, n_energies, (size_t)L * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_CUDA(cudaMemcpyAsync(crf->d_energies + L, p_energies, (size_t)L * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (NT > 0) {
+        LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, (size_t)NT * sizeof(short)));
+        LCCRF_CUDA(cudaMemcpyAsync(ctx->dev_io.p, label, (size_t)NT * sizeof(short), cudaMemcpyHostToDevice, ctx->stream));
+        LCCRF_TRY(mf_unary_from_label(ctx, crf->b.unary, (const short *)ctx->dev_io.p, NT, L, u_energy, crf->d_energies,
+                                      crf->d_energies + L));
+    }
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+int lccrf_crf_set_unary_entry(lccrf_crf *crf, int idx, int m, float value) {
+    if (!crf) return fail(LCCRF_ERR_ARG, "crf is NULL");
+    if (idx < 0 || idx >= crf->b.NT || m < 0 || m >= crf->b.L) return fail(LCCRF_ERR_ARG, "index out of range");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    LCCRF_CUDA(cudaMemcpyAsync(crf->b.unary + (size_t)idx * crf->b.L + m, &value, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+static int crf_add_lattice(lccrf_crf *crf, int d, float w, const float *feat_dev) {
+    Ctx *ctx = crf->ctx;
+    if ((int)crf->b.lat.size() >= LCCRF_MAX_K) return fail(LCCRF_ERR_ARG, "too many pairwise potentials");
+    LatticeSet *ls = nullptr;
+    LCCRF_TRY(lattice_set_create(ctx, crf->b, d, w, crf->b.L, &ls));
+    int rc = lattice_set_build(ctx, crf->b, ls, feat_dev);
+    if (rc == LCCRF_OK) rc = potts_norm(ctx, crf->b, ls);
+    if (rc == LCCRF_OK) rc = check_status(ctx);
+    if (rc != LCCRF_OK) {
+        lattice_set_destroy(ctx, ls);
+        return rc;
+    }
+    crf->b.lat.push_back(ls);
+    return LCCRF_OK;
+}
+
+int lccrf_crf_add_potts(lccrf_crf *crf, const float *features, int d, float w) {
+    if (!crf || (!features && crf->b.NT > 0)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (d < 1 || d > LCCRF_MAX_D) return fail(LCCRF_ERR_ARG, "feature dimension must be in [1, LCCRF_MAX_D]");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)crf->b.NT * d;
+    LCCRF_TRY(ctx_scratch(ctx, ctx->feat, (n ? n : 1) * sizeof(float)));
+    if (n) LCCRF_CUDA(cudaMemcpyAsync(ctx->feat.p, features, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return crf_add_lattice(crf, d, w, (const float *)ctx->feat.p);
+}
+
+int lccrf_crf_add_potts_image(lccrf_crf *crf, int W, int H, float w, float posdev, const void *img, int img_is_u8,
+                              int F, float featuredev) {
+    if (!crf) return fail(LCCRF_ERR_ARG, "crf is NULL");
+    if (W < 0 || H < 0 || (long long)W * H != crf->b.NT) return fail(LCCRF_ERR_ARG, "W*H must equal N");
+    if (F < 2 || F > LCCRF_MAX_D) return fail(LCCRF_ERR_ARG, "F must be in [2, LCCRF_MAX_D]");
+    if (F > 2 && !img && crf->b.NT > 0) return fail(LCCRF_ERR_ARG, "image features required when F > 2");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)crf->b.NT;
+    LCCRF_TRY(ctx_scratch(ctx, ctx->feat, (npx ? npx : 1) * F * sizeof(float)));
+    const void *img_dev = nullptr;
+    if (F > 2 && npx) {
+        const size_t ib = npx * (F - 2) * (img_is_u8 ? 1 : sizeof(float));
+        LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, ib));
+        LCCRF_CUDA(cudaMemcpyAsync(ctx->dev_io.p, img, ib, cudaMemcpyHostToDevice, ctx->stream));
+        img_dev = ctx->dev_io.p;
+    }
+    LCCRF_TRY(feat_image(ctx, (float *)ctx->feat.p, W, H, F, posdev, img_dev, img_is_u8, featuredev));
+    return crf_add_lattice(crf, F, w, (const float *)ctx->feat.p);
+}
+
+int lccrf_crf_start(lccrf_crf *crf) {
+    if (!crf) return fail(LCCRF_ERR_ARG, "crf is NULL");
+    LCCRF_CUDA(cudaSetDevice(crf->ctx->device));
+    LCCRF_TRY(mf_start(crf->ctx, crf->b));
+    crf->started = true;
+    crf->prob_fresh = false;
+    return LCCRF_OK;
+}
+
+int lccrf_crf_step(lccrf_crf *crf, float relax) {
+    if (!crf) return fail(LCCRF_ERR_ARG, "crf is NULL");
+    if (!crf->started) return fail(LCCRF_ERR_STATE, "stepInference before startInference");
+    LCCRF_CUDA(cudaSetDevice(crf->ctx->device));
+    LCCRF_TRY(mf_step(crf->ctx, crf->b, relax));
+    crf->prob_fresh = false;
+    return LCCRF_OK;
+}
+
+int lccrf_crf_build_map(lccrf_crf *crf) {
+    if (!crf) return fail(LCCRF_ERR_ARG, "crf is NULL");
+    LCCRF_CUDA(cudaSetDevice(crf->ctx->device));
+    LCCRF_TRY(mf_build_map(crf->ctx, crf->b));
+    crf->map_built = true;
+    crf->map_fresh = false;
+    return LCCRF_OK;
+}
+
+static int crf_fetch(lccrf_crf *crf) {
+    Ctx *ctx = crf->ctx;
+    const size_t n = (size_t)crf->b.NT;
+    bool any = false;
+    if (!crf->prob_fresh && n) {
+        LCCRF_CUDA(cudaMemcpyAsync(crf->h_prob, crf->b.cur, n * crf->b.L * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        any = true;
+    }
+    if (crf->map_built && !crf->map_fresh && n) {
+        LCCRF_CUDA(cudaMemcpyAsync(crf->h_map, crf->b.map, n * sizeof(short), cudaMemcpyDeviceToHost, ctx->stream));
+        any = true;
+    }
+    if (any) LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    crf->prob_fresh = true;
+    if (crf->map_built) crf->map_fresh = true;
+    return LCCRF_OK;
+}
+
+int lccrf_crf_inference(lccrf_crf *crf, int n_iterations, int with_map, float relax) {
+    if (!crf) return fail(LCCRF_ERR_ARG, "crf is NULL");
+    LCCRF_TRY(lccrf_crf_start(crf));
+    for (int it = 0; it < n_iterations; it++) LCCRF_TRY(lccrf_crf_step(crf, relax));
+    if (with_map) LCCRF_TRY(lccrf_crf_build_map(crf));
+    // results must be host-visible when inference() returns (Tracking.cc:1930-1948 indexes them directly)
+    return crf_fetch(crf);
+}
+
+const short *lccrf_crf_map(lccrf_crf *crf) {
+    if (!crf || !crf->map_built) return nullptr;
+    cudaSetDevice(crf->ctx->device);
+    if (crf_fetch(crf) != LCCRF_OK) return nullptr;
+    return crf->h_map;
+}
+
+const float *lccrf_crf_prob(lccrf_crf *crf) {
+    if (!crf) return nullptr;
+    cudaSetDevice(crf->ctx->device);
+    if (!crf->started) {
+        // current_ exists from construction in the reference (uninitialised); hand out the buffer
+        return crf->h_prob;
+    }
+    if (crf_fetch(crf) != LCCRF_OK) return nullptr;
+    return crf->h_prob;
+}
+
+int lccrf_crf_potts_vertices(const lccrf_crf *crf, int k, int *V) {
+    if (!crf || !V) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (k < 0 || k >= (int)crf->b.lat.size()) return fail(LCCRF_ERR_ARG, "potential index out of range");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    LCCRF_CUDA(cudaMemcpyAsync(ctx->h_status, crf->b.lat[k]->vbase + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *V = *ctx->h_status;
+    return LCCRF_OK;
+}
+
+int lccrf_crf_potts_apply(lccrf_crf *crf, int k, float *out, const float *in, float *tmp) {
+    if (!crf || !out || !in || !tmp) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (k < 0 || k >= (int)crf->b.lat.size()) return fail(LCCRF_ERR_ARG, "potential index out of range");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)crf->b.NT * crf->b.L;
+    if (!n) return LCCRF_OK;
+    // device staging: next <- out, cur-like scratch <- in (b.tmp holds `in`, dev_io holds tmp)
+    LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, 3 * n * sizeof(float)));
+    float *d_out = (float *)ctx->dev_io.p, *d_in = d_out + n, *d_tmp = d_in + n;
+    LCCRF_CUDA(cudaMemcpyAsync(d_out, out, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_TRY(mf_potts_apply(ctx, crf->b, crf->b.lat[k], d_out, d_in, d_tmp, crf->b.L));
+    LCCRF_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaMemcpyAsync(tmp, d_tmp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+int lccrf_exp_and_normalize(lccrf_ctx *h, float *out, const float *in, int N, int L, float scale, float relax) {
+    if (!h || !out || !in) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (N < 0 || L < 1 || L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "N or L out of range");
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N * L;
+    if (!n) return LCCRF_OK;
+    LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, 2 * n * sizeof(float)));
+    float *d_out = (float *)ctx->dev_io.p, *d_in = d_out + n;
+    LCCRF_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (relax != 1.0f) LCCRF_CUDA(cudaMemcpyAsync(d_out, out, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_TRY(mf_exp_and_normalize(ctx, d_out, d_in, N, L, scale, relax));
+    LCCRF_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+// ------------------------------------------------------------------ long-term unary (host-pointer calls)
+int lccrf_map_point_unary(lccrf_ctx *h, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                          const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                          const float *kf_bounds, float *observs, float *error, float *depth) {
+    if (!h) return fail(LCCRF_ERR_ARG, "ctx is NULL");
+    if (N < 0 || nKF < 0) return fail(LCCRF_ERR_ARG, "negative size");
+    if (N == 0) return LCCRF_OK;
+    if (!xyz || !obs_ptr || !observs || !error || !depth) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const long long nnz = obs_ptr[N];
+    if (obs_ptr[0] != 0 || nnz < 0) return fail(LCCRF_ERR_ARG, "obs_ptr must start at 0");
+    for (int i = 0; i < N; i++)
+        if (obs_ptr[i + 1] < obs_ptr[i]) return fail(LCCRF_ERR_ARG, "obs_ptr must be non-decreasing");
+    if (nnz > 0 && (!obs_kf || !obs_uv || !kf_pose || !kf_intr || !kf_bounds)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    for (long long e = 0; e < nnz; e++)
+        if (obs_kf[e] < 0 || obs_kf[e] >= nKF) return fail(LCCRF_ERR_ARG, "obs_kf out of range");
+    // device staging
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_xyz = take((size_t)N * 12), o_ptr = take((size_t)(N + 1) * 4), o_kf = take((size_t)nnz * 4),
+                 o_uv = take((size_t)nnz * 8), o_pose = take((size_t)nKF * 48), o_intr = take((size_t)nKF * 16),
+                 o_bnd = take((size_t)nKF * 16), o_out = take((size_t)N * 12);
+    LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, off + 256));
+    char *base = (char *)ctx->dev_io.p;
+    cudaStream_t st = ctx->stream;
+    LCCRF_CUDA(cudaMemcpyAsync(base + o_xyz, xyz, (size_t)N * 12, cudaMemcpyHostToDevice, st));
+    LCCRF_CUDA(cudaMemcpyAsync(base + o_ptr, obs_ptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_kf, obs_kf, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_uv, obs_uv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (nKF) {
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_pose, kf_pose, (size_t)nKF * 48, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_intr, kf_intr, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_bnd, kf_bounds, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
+    }
+    float *d_obs = (float *)(base + o_out), *d_err = d_obs + N, *d_dep = d_err + N;
+    LCCRF_TRY(unary_map_points(ctx, N, (const float *)(base + o_xyz), (const int *)(base + o_ptr),
+                               (const int *)(base + o_kf), (const float *)(base + o_uv), nKF,
+                               (const float *)(base + o_pose), (const float *)(base + o_intr),
+                               (const float *)(base + o_bnd), d_obs, d_err, d_dep));
+    LCCRF_CUDA(cudaMemcpyAsync(observs, d_obs, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaMemcpyAsync(error, d_err, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaMemcpyAsync(depth, d_dep, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));
+    return LCCRF_OK;
+}
+
+int lccrf_rough_classify(lccrf_ctx *h, int N, const float *observs, const float *error, const float *depth,
+                         const double *p4, const lccrf_slam_params *prm, short *label) {
+    if (!h || !prm) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (N < 0) return fail(LCCRF_ERR_ARG, "N < 0");
+    if (N == 0) return LCCRF_OK;
+    if (!observs || !error || !depth || !label) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n4 = ((size_t)N * 4 + 255) / 256 * 256;
+    LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, 3 * n4 + (size_t)N * 8 + 256 + (size_t)N * 2 + 256));
+    char *base = (char *)ctx->dev_io.p;
+    float *d_o = (float *)base, *d_e = (float *)(base + n4), *d_d = (float *)(base + 2 * n4);
+    double *d_p4 = (double *)(base + 3 * n4);
+    short *d_lab = (short *)(base + 3 * n4 + ((size_t)N * 8 + 255) / 256 * 256);
+    cudaStream_t st = ctx->stream;
+    LCCRF_CUDA(cudaMemcpyAsync(d_o, observs, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    LCCRF_CUDA(cudaMemcpyAsync(d_e, error, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    LCCRF_CUDA(cudaMemcpyAsync(d_d, depth, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    if (p4) LCCRF_CUDA(cudaMemcpyAsync(d_p4, p4, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    LCCRF_TRY(unary_classify(ctx, N, d_o, d_e, d_d, p4 ? d_p4 : nullptr, *prm, d_lab));
+    LCCRF_CUDA(cudaMemcpyAsync(label, d_lab, (size_t)N * 2, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));
+    return LCCRF_OK;
+}
+
+// ------------------------------------------------------------------ batched frames
+int lccrf_frames_create(lccrf_ctx *h, int B, const int *prob_ptr, const lccrf_slam_params *prm,
+                        const float *energies3, lccrf_frames **out) {
+    if (!h || !out || !prob_ptr || !prm || !energies3) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (B < 1) return fail(LCCRF_ERR_ARG, "B must be >= 1");
+    if (prm->iters < 0) return fail(LCCRF_ERR_ARG, "iters < 0");
+    *out = nullptr;
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    auto *fr = new lccrf_frames();
+    fr->ctx = ctx;
+    fr->prm = *prm;
+    memcpy(fr->energies, energies3, sizeof(fr->energies));
+    int rc = batch_init(ctx, fr->b, B, prob_ptr, 2, true);
+    const size_t n = (size_t)(fr->b.NT > 0 ? fr->b.NT : 1);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->observs, n * 4);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->error, n * 4);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->depth, n * 4);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->kp2d, n * 8);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->feat, n * 8);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->label, n * 2);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->d_en, 4 * sizeof(float));
+    if (rc == LCCRF_OK) {
+        float en[4] = {energies3[1], energies3[1], energies3[2], energies3[2]};  // n_en[2], p_en[2]
+        cudaError_t e = cudaMemcpyAsync(fr->d_en, en, sizeof(en), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    for (int k = 0; k < 2 && rc == LCCRF_OK; k++) {
+        LatticeSet *ls = nullptr;
+        rc = lattice_set_create(ctx, fr->b, 2, k == 0 ? prm->w1 : prm->w2, 2, &ls);
+        if (rc == LCCRF_OK) fr->b.lat.push_back(ls);
+    }
+    if (rc != LCCRF_OK) {
+        lccrf_frames_destroy(fr);
+        return rc;
+    }
+    *out = fr;
+    return LCCRF_OK;
+}
+
+void lccrf_frames_destroy(lccrf_frames *fr) {
+    if (!fr) return;
+    Ctx *ctx = fr->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (fr->graph) cudaGraphExecDestroy(fr->graph);
+    batch_release(ctx, fr->b);
+    dev_free(ctx, fr->observs);
+    dev_free(ctx, fr->error);
+    dev_free(ctx, fr->depth);
+    dev_free(ctx, fr->kp2d);
+    dev_free(ctx, fr->feat);
+    dev_free(ctx, fr->label);
+    dev_free(ctx, fr->d_en);
+    dev_free(ctx, fr->xyz);
+    dev_free(ctx, fr->obs_uv);
+    dev_free(ctx, fr->kf_pose);
+    dev_free(ctx, fr->kf_intr);
+    dev_free(ctx, fr->kf_bounds);
+    dev_free(ctx, fr->obs_ptr);
+    dev_free(ctx, fr->obs_kf);
+    dev_free(ctx, fr->kf_packed);
+    delete fr;
+}
+
+int lccrf_frames_set_inputs(lccrf_frames *fr, const float *observs, const float *error, const float *depth,
+                            const float *kp2d) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)fr->b.NT;
+    if (n) {
+        if (!observs || !error || !depth || !kp2d) return fail(LCCRF_ERR_ARG, "NULL argument");
+        cudaStream_t st = ctx->stream;
+        LCCRF_CUDA(cudaMemcpyAsync(fr->observs, observs, n * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->error, error, n * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->depth, depth, n * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kp2d, kp2d, n * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (fr->from_map && fr->graph) {
+        cudaGraphExecDestroy(fr->graph);
+        fr->graph = nullptr;
+    }
+    fr->from_map = false;
+    fr->have_inputs = true;
+    return LCCRF_OK;
+}
+
+int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                                const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                                const float *kf_bounds, const float *kp2d) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const int NT = fr->b.NT;
+    if (NT > 0 && (!xyz || !obs_ptr || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    const long long nnz = NT > 0 ? obs_ptr[NT] : 0;
+    if (NT > 0 && obs_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "obs_ptr must start at 0");
+    if (nnz > 0 && (!obs_kf || !obs_uv || !kf_pose || !kf_intr || !kf_bounds || nKF <= 0))
+        return fail(LCCRF_ERR_ARG, "NULL argument");
+    // Tracking.cc:1858: points without observations never reach the CRF -- the caller drops them
+    // (obs_ptr is host data, so this is a host-side structural check, not device work)
+    for (int i = 0; i < NT; i++)
+        if (obs_ptr[i + 1] <= obs_ptr[i]) return fail(LCCRF_ERR_ARG, "every point needs >= 1 observation (Tracking.cc:1858)");
+    bool realloc_graph = false;
+    if (nnz > fr->nnz_cap || !fr->obs_kf) {
+        dev_free(ctx, fr->obs_kf);
+        dev_free(ctx, fr->obs_uv);
+        fr->obs_kf = nullptr;
+        fr->obs_uv = nullptr;
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->obs_kf, (size_t)(nnz ? nnz : 1) * 4));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->obs_uv, (size_t)(nnz ? nnz : 1) * 8));
+        fr->nnz_cap = nnz;
+        realloc_graph = true;
+    }
+    if (nKF > fr->nKF_cap || !fr->kf_pose) {
+        dev_free(ctx, fr->kf_pose);
+        dev_free(ctx, fr->kf_intr);
+        dev_free(ctx, fr->kf_bounds);
+        dev_free(ctx, fr->kf_packed);
+        const size_t k = (size_t)(nKF ? nKF : 1);
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_pose, k * 48));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_intr, k * 16));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_bounds, k * 16));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_packed, k * 80));
+        fr->nKF_cap = nKF;
+        realloc_graph = true;
+    }
+    if (!fr->xyz) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->xyz, (size_t)(NT ? NT : 1) * 12));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->obs_ptr, (size_t)(NT + 1) * 4));
+        realloc_graph = true;
+    }
+    if (fr->nKF != nKF || fr->nnz != nnz || !fr->from_map) realloc_graph = true;
+    if (realloc_graph && fr->graph) {
+        cudaGraphExecDestroy(fr->graph);
+        fr->graph = nullptr;
+    }
+    fr->nKF = nKF;
+    fr->nnz = nnz;
+    cudaStream_t st = ctx->stream;
+    if (NT > 0) {
+        LCCRF_CUDA(cudaMemcpyAsync(fr->xyz, xyz, (size_t)NT * 12, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->obs_ptr, obs_ptr, (size_t)(NT + 1) * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kp2d, kp2d, (size_t)NT * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (nnz > 0) {
+        LCCRF_CUDA(cudaMemcpyAsync(fr->obs_kf, obs_kf, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->obs_uv, obs_uv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_pose, kf_pose, (size_t)nKF * 48, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_intr, kf_intr, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_bounds, kf_bounds, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
+    }
+    fr->from_map = true;
+    fr->have_inputs = true;
+    return LCCRF_OK;
+}
+
+static int frames_enqueue(lccrf_frames *fr) {
+    Ctx *ctx = fr->ctx;
+    Batch &b = fr->b;
+    const int NT = b.NT;
+    const lccrf_slam_params &prm = fr->prm;
+    if (fr->from_map) {
+        LCCRF_TRY(unary_pack_kf(ctx, fr->kf_packed, fr->kf_pose, fr->kf_intr, fr->kf_bounds, fr->nKF));
+        LCCRF_TRY(unary_map_points_packed(ctx, NT, fr->xyz, fr->obs_ptr, fr->obs_kf, fr->obs_uv, fr->kf_packed,
+                                          fr->observs, fr->error, fr->depth));
+    }
+    // RroughClassify -> setUnaryEnergyFromLabel   (Tracking.cc:1871,1921)
+    LCCRF_TRY(unary_classify(ctx, NT, fr->observs, fr->error, fr->depth, nullptr, prm, fr->label));
+    LCCRF_TRY(mf_unary_from_label(ctx, b.unary, fr->label, NT, 2, fr->energies[0], fr->d_en, fr->d_en + 2));
+    // appearanceKernel(N, w1, vobservs, verrors, mObservStdev, mRpjErrorStdev)   (Tracking.cc:1923)
+    LCCRF_TRY(feat_div2(ctx, fr->feat, fr->observs, 1, prm.stdev_beta, fr->error, 1, prm.stdev_alpha, NT));
+    LCCRF_TRY(lattice_set_build(ctx, b, b.lat[0], fr->feat));
+    LCCRF_TRY(potts_norm(ctx, b, b.lat[0]));
+    // smoothKernel(N, w2, vpoints, vcorrd2d, mPoint3dStdev, mPoint2dStdev): 2-D branch   (Tracking.cc:1926)
+    LCCRF_TRY(feat_div2(ctx, fr->feat, fr->kp2d, 2, prm.point2d_stdev, fr->kp2d + 1, 2, prm.point2d_stdev, NT));
+    LCCRF_TRY(lattice_set_build(ctx, b, b.lat[1], fr->feat));
+    LCCRF_TRY(potts_norm(ctx, b, b.lat[1]));
+    // inference(iters, true)   (Tracking.cc:1929)
+    LCCRF_TRY(mf_start(ctx, b));
+    for (int it = 0; it < prm.iters; it++) LCCRF_TRY(mf_step(ctx, b, 1.0f));
+    LCCRF_TRY(mf_build_map(ctx, b));
+    return LCCRF_OK;
+}
+
+int lccrf_frames_run(lccrf_frames *fr) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (!fr->have_inputs) return fail(LCCRF_ERR_STATE, "frames_run before set_inputs");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->opt_graphs) {
+        LCCRF_TRY(frames_enqueue(fr));
+        fr->ran = true;
+        return LCCRF_OK;
+    }
+    if (fr->graph && fr->graph_gen != ctx->scratch_gen) {  // a scratch buffer moved since capture
+        cudaGraphExecDestroy(fr->graph);
+        fr->graph = nullptr;
+    }
+    if (!fr->graph) {
+        // make sure every scratch buffer has its final size before capture (no allocation inside the graph)
+        const uint64_t l0 = ctx->launches;
+        LCCRF_TRY(frames_enqueue(fr));
+        LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+        const uint64_t per_run = ctx->launches - l0;
+        cudaGraph_t g = nullptr;
+        LCCRF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = frames_enqueue(fr);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        ctx->launches -= per_run;  // the capture pass launched nothing
+        if (rc != LCCRF_OK) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&fr->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+        fr->graph_launches = per_run;
+        fr->graph_gen = ctx->scratch_gen;
+        fr->ran = true;
+        return LCCRF_OK;  // the warm-up pass above already produced this call's results
+    }
+    LCCRF_CUDA(cudaGraphLaunch(fr->graph, ctx->stream));
+    ctx->launches += fr->graph_launches;
+    fr->ran = true;
+    return LCCRF_OK;
+}
+
+int lccrf_frames_get_outputs(lccrf_frames *fr, short *map, float *prob) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_get_outputs before frames_run");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)fr->b.NT;
+    if (n && map) LCCRF_CUDA(cudaMemcpyAsync(map, fr->b.map, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && prob) LCCRF_CUDA(cudaMemcpyAsync(prob, fr->b.cur, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return check_status(ctx);
+}
+
+int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth, int *V) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_get_debug before frames_run");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)fr->b.NT;
+    cudaStream_t st = ctx->stream;
+    if (n && init_label) LCCRF_CUDA(cudaMemcpyAsync(init_label, fr->label, n * 2, cudaMemcpyDeviceToHost, st));
+    if (n && observs) LCCRF_CUDA(cudaMemcpyAsync(observs, fr->observs, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n && error) LCCRF_CUDA(cudaMemcpyAsync(error, fr->error, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n && depth) LCCRF_CUDA(cudaMemcpyAsync(depth, fr->depth, n * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<int> vb[2];
+    if (V) {
+        for (int k = 0; k < 2; k++) {
+            vb[k].resize(fr->b.B + 1);
+            LCCRF_CUDA(cudaMemcpyAsync(vb[k].data(), fr->b.lat[k]->vbase, (size_t)(fr->b.B + 1) * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    LCCRF_CUDA(cudaStreamSynchronize(st));
+    if (V)
+        for (int i = 0; i < fr->b.B; i++)
+            for (int k = 0; k < 2; k++) V[2 * i + k] = vb[k][i + 1] - vb[k][i];
+    return LCCRF_OK;
+}
+
+// SURVEY.md 8(d) formulas with the actual V of every problem
+int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_iteration, double *unary) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    std::vector<int> V((size_t)fr->b.B * 2);
+    LCCRF_TRY(lccrf_frames_get_debug(fr, nullptr, nullptr, nullptr, nullptr, V.data()));
+    const double d = 2, D = 3, L = 2, K = 2, T = fr->prm.iters;
+    double tot = 0, it_tot = 0;
+    for (int i = 0; i < fr->b.B; i++) {
+        const double N = fr->b.h_prob_ptr[i + 1] - fr->b.h_prob_ptr[i];
+        double Bit = K * N * 4 + 2 * N * L * 4, Bb = 0;
+        for (int k = 0; k < 2; k++) {
+            const double Vk = V[2 * i + k];
+            auto Bf = [&](double l) { return 2 * N * D * 8 + 2 * N * l * 4 + D * Vk * (2 * l * 4 + 8); };
+            Bit += Bf(L);
+            Bb += N * d * 4 + N * D * 8 + Vk * (2 * d + 8 * D) + Bf(1) + N * 4;
+        }
+        tot += N * 2 + N * L * 4 + 2 * N * L * 4 + Bb + T * Bit + N * L * 4 + N * 2;
+        it_tot += Bit;
+    }
+    double u = 0;
+    if (fr->from_map) u = (double)fr->nnz * 12 + (double)fr->b.NT * 24 + (double)fr->nKF * 80;
+    if (total) *total = tot + u;
+    if (per_iteration) *per_iteration = it_tot;
+    if (unary) *unary = u;
+    return LCCRF_OK;
+}
+
+}  // extern "C"

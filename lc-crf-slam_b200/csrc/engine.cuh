@@ -1,0 +1,114 @@
+// engine.cuh -- internal data model of liblccrf: a *batch* of B independent CRF problems whose
+// points are concatenated (problem b owns points [prob_ptr[b], prob_ptr[b+1])).  A single
+// DenseCRF object is a batch with B == 1.  Everything lives in HBM; the layouts are chosen for
+// coalesced streaming (see DESIGN.md "Data layout").
+#pragma once
+
+#include <cstddef>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lccrf {
+
+struct Ctx;
+
+// One pairwise kernel (one permutohedral lattice per problem) across the whole batch.
+struct LatticeSet {
+    int d = 0, D = 0;
+    float w = 0.f;      // Potts weight w_ (pairwise3d.h:17)
+    float alpha = 0.f;  // 1/(1+2^-d) (permutohedral_cpu.h:681)
+    int NT = 0, B = 0;
+    int Vcap = 0;       // capacity of the per-vertex arrays: (NT + B) * D worst case
+    // per (point, remainder), tight point-major [NT*D]: GLOBAL vertex id (= vbase[b] + reference id)
+    int *offset = nullptr;
+    float *bary = nullptr;
+    // per vertex
+    int2 *nbr = nullptr;        // [D][Vcap] {n1,n2} global ids, -1 = absent   (permutohedral_cpu.h:418-419)
+    int *vert_slot = nullptr;   // [Vcap] hash slot of each vertex (build only)
+    int *vert_prob = nullptr;   // [Vcap] owning problem
+    int *vbase = nullptr;       // [B+1] first global vertex id of each problem; vbase[B] = V_total
+    int *tab_base = nullptr;    // [B+1] first hash slot of each problem's open-addressing region (build only)
+    long long tab_slots = 0;
+    float *norm = nullptr;      // [NT] 1/(filter(1)+1e-20)   (pairwise3d.h:22-27)
+    // filter workspace
+    long long *acc = nullptr;   // [Vcap*Lmax] fixed-point splat accumulators (kept zero between calls)
+    float *valA = nullptr, *valB = nullptr;  // [Vcap*Lmax] blur ping-pong
+    int Lmax = 0;
+};
+
+struct Batch {
+    Ctx *ctx = nullptr;
+    int B = 0, NT = 0, L = 0;
+    std::vector<int> h_prob_ptr;  // host copy
+    int *prob_ptr = nullptr;      // [B+1] device
+    int maxN = 0;
+    std::vector<LatticeSet *> lat;  // K potentials
+    float *unary = nullptr, *cur = nullptr, *next = nullptr, *tmp = nullptr;  // [NT*L]
+    short *map = nullptr;                                                      // [NT]
+};
+
+// ------------------------------------------------------------------ context
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    uint64_t scratch_gen = 0;  // bumped whenever a scratch buffer moves (captured graphs hold raw pointers)
+    int opt_graphs = 1;
+    int opt_fused = 1;
+    // scratch for the lattice build (grown on demand, reused)
+    struct Scratch {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    Scratch hash_keys[3], hash_first, hash_id, ent_slot, blk_cnt, misc, feat, pinned_in, pinned_out, dev_io;
+    int *d_status = nullptr;   // device status word (key range overflow etc.)
+    int *h_status = nullptr;   // pinned
+};
+
+int ctx_scratch(Ctx *ctx, Ctx::Scratch &s, size_t bytes, bool pinned = false);
+int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero = false);
+void dev_free(Ctx *ctx, void *p);
+
+// ------------------------------------------------------------------ stages (each enqueues kernels on ctx->stream)
+// lattice build: features [NT*d] on device -> offset/bary/nbr/vbase (lattice_build.cu)
+int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, LatticeSet **out);
+void lattice_set_destroy(Ctx *ctx, LatticeSet *ls);
+int lattice_set_build(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *feat_dev);
+int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L);  // (re)allocate the filter workspace for L labels
+// filter (filter.cu): out/in device [NT*L]; in_max = upper bound of |in| (power-of-two scaling of the accumulator)
+// scale2_dev: optional device pair {2^-e, 2^e} bringing |in| <= 1 (nullptr: inputs already in [-1, 1])
+int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_dev, int L,
+                      const float *scale2_dev, const float **values_out);
+int filter_full(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out_dev, const float *in_dev, int L,
+                bool generic_range);
+int potts_norm(Ctx *ctx, const Batch &b, LatticeSet *ls);
+// mean field (meanfield.cu)
+int mf_unary_from_label(Ctx *ctx, float *unary, const short *label_dev, int NT, int L, float u_energy,
+                        const float *n_en, const float *p_en);
+int mf_exp_and_normalize(Ctx *ctx, float *out, const float *in, int NT, int L, float scale, float relax);
+int mf_start(Ctx *ctx, Batch &b);
+int mf_step(Ctx *ctx, Batch &b, float relax);
+int mf_build_map(Ctx *ctx, Batch &b);
+// potts apply on arbitrary device arrays (plugin path): tmp = filter(in); out += (w*norm)*tmp
+int mf_potts_apply(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out, const float *in, float *tmp, int L);
+// one potential of a mean-field step: next = (first ? -unary : next) + (w*norm)*filter(cur)
+int mf_apply_fused(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *cur, float *next, const float *unary,
+                   bool first);
+int launch_axpy_norm(Ctx *ctx, float *out, const float *tmp, const float *norm, float w, int NT, int L);
+// features (unary.cu)
+int feat_div2(Ctx *ctx, float *feat, const float *a, int stride_a, float sa, const float *b, int stride_b,
+              float sb, int N);
+int feat_image(Ctx *ctx, float *feat, int W, int H, int F, float posdev, const void *img_dev, int is_u8,
+               float featuredev);
+int unary_pack_kf(Ctx *ctx, void *kf_packed /*nKF*80 B*/, const float *pose, const float *intr, const float *bnd, int nKF);
+int unary_map_points_packed(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                            const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth);
+int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                     const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                     const float *kf_bounds, float *observs, float *error, float *depth);
+int unary_classify(Ctx *ctx, int N, const float *observs, const float *error, const float *depth,
+                   const double *p4, const lccrf_slam_params &prm, short *label);
+
+}  // namespace lccrf

@@ -1,0 +1,186 @@
+// meanfield.cu -- the DenseCRF driver on the device.
+// Replaces DenseCRF::startInference/stepInference (Thirdparty/DenseCRF/include/densecrf_base.h:78-91),
+// DenseCRF3D<M>::expAndNormalize + fast_exp (densecrf3d.h:51-98), stepInit (:155-158),
+// buildMap (:137-151) and setUnaryEnergyFromLabel (:108-130).
+#include "engine.cuh"
+
+namespace lccrf {
+
+namespace {
+
+// very_fast_exp / fast_exp, densecrf3d.h:51-67 -- operation for operation (a polynomial on a
+// range-reduced argument followed by repeated squaring), NOT __expf: MAP near-ties follow the
+// reference only if every rounding does.  The range-reduction thresholds are double constants.
+__device__ __forceinline__ float very_fast_exp(float x) {
+    float p = 0.0001413161f;
+    p = __fsub_rn(0.0013298820f, __fmul_rn(x, p));
+    p = __fsub_rn(0.0083013598f, __fmul_rn(x, p));
+    p = __fsub_rn(0.0416573475f, __fmul_rn(x, p));
+    p = __fsub_rn(0.1666653019f, __fmul_rn(x, p));
+    p = __fsub_rn(0.4999999206f, __fmul_rn(x, p));
+    p = __fsub_rn(0.9999999995f, __fmul_rn(x, p));
+    return __fsub_rn(1.0f, __fmul_rn(x, p));
+}
+
+__device__ __forceinline__ float fast_exp(float x) {
+    bool lessZero = true;
+    if (x < 0) {
+        lessZero = false;
+        x = -x;
+    }
+    if (x > 20) return 0;
+    int mult = 0;
+    while ((double)x > 0.69 * 2 * 2 * 2) {
+        mult += 3;
+        x = __fdiv_rn(x, 8.0f);
+    }
+    while ((double)x > 0.69 * 2 * 2) {
+        mult += 2;
+        x = __fdiv_rn(x, 4.0f);
+    }
+    while ((double)x > 0.69) {
+        mult++;
+        x = __fdiv_rn(x, 2.0f);
+    }
+    x = very_fast_exp(x);
+    while (mult) {
+        mult--;
+        x = __fmul_rn(x, x);
+    }
+    return lessZero ? __fdiv_rn(1.0f, x) : x;
+}
+
+// expAndNormalize, densecrf3d.h:71-98; one thread per point.  fast_exp is recomputed instead of
+// buffered for run-time L (it is deterministic), kept in registers for L == 2.
+template <int LT>
+__global__ void __launch_bounds__(kThreads)
+k_exp_normalize(float *__restrict__ out, const float *__restrict__ in, int NT, int L_rt, float scale, float relax) {
+    const int L = LT > 0 ? LT : L_rt;
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= NT) return;
+    const float *b = in + (size_t)i * L;
+    float *a = out + (size_t)i * L;
+    float mx = __fmul_rn(scale, b[0]);
+    for (int j = 1; j < L; j++) {
+        float s = __fmul_rn(scale, b[j]);
+        if (mx < s) mx = s;
+    }
+    float tt = 0.f;
+    if (LT == 2) {
+        float v0 = fast_exp(__fsub_rn(__fmul_rn(scale, b[0]), mx));
+        float v1 = fast_exp(__fsub_rn(__fmul_rn(scale, b[1]), mx));
+        tt = __fadd_rn(__fadd_rn(tt, v0), v1);
+        v0 = __fdiv_rn(v0, tt);
+        v1 = __fdiv_rn(v1, tt);
+        if (relax == 1.0f) {
+            a[0] = v0;
+            a[1] = v1;
+        } else {
+            const float om = __fsub_rn(1.0f, relax);
+            a[0] = __fadd_rn(__fmul_rn(om, a[0]), __fmul_rn(relax, v0));
+            a[1] = __fadd_rn(__fmul_rn(om, a[1]), __fmul_rn(relax, v1));
+        }
+        return;
+    }
+    for (int j = 0; j < L; j++) tt = __fadd_rn(tt, fast_exp(__fsub_rn(__fmul_rn(scale, b[j]), mx)));
+    const float om = __fsub_rn(1.0f, relax);
+    for (int j = 0; j < L; j++) {
+        float v = __fdiv_rn(fast_exp(__fsub_rn(__fmul_rn(scale, b[j]), mx)), tt);
+        a[j] = relax == 1.0f ? v : __fadd_rn(__fmul_rn(om, a[j]), __fmul_rn(relax, v));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_unary_from_label(float *__restrict__ unary, const short *__restrict__ label, int NT, int L, float u_energy,
+                   const float *__restrict__ n_en, const float *__restrict__ p_en) {
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= (long long)NT * L) return;
+    const int i = (int)(t / L), m = (int)(t - (long long)i * L);
+    const int lab = label[i];
+    float v;
+    if (lab == -1) v = u_energy;                       // densecrf3d.h:118-121
+    else v = (m == lab) ? p_en[lab] : n_en[lab];      // :123-126
+    unary[t] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_negate(float *__restrict__ out, const float *__restrict__ in, long long n) {
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (t < n) out[t] = -in[t];  // stepInit, densecrf3d.h:155-158
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_build_map(short *__restrict__ map, const float *__restrict__ Q, int NT, int L) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= NT) return;
+    const float *p = Q + (size_t)i * L;
+    float mx = p[0];
+    short imx = 0;
+    for (int m = 1; m < L; m++)
+        if (mx < p[m]) {  // strict: first maximum wins, densecrf3d.h:144-147
+            mx = p[m];
+            imx = (short)m;
+        }
+    map[i] = imx;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_axpy_norm(float *__restrict__ out, const float *__restrict__ tmp, const float *__restrict__ norm, float w, int NT, int L) {
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= (long long)NT * L) return;
+    const int i = (int)(t / L);
+    out[t] = __fadd_rn(out[t], __fmul_rn(__fmul_rn(w, norm[i]), tmp[t]));  // pairwise3d.h:75-77
+}
+
+}  // namespace
+
+int launch_axpy_norm(Ctx *ctx, float *out, const float *tmp, const float *norm, float w, int NT, int L) {
+    if (NT == 0) return LCCRF_OK;
+    k_axpy_norm<<<cdiv((long long)NT * L, kThreads), kThreads, 0, ctx->stream>>>(out, tmp, norm, w, NT, L);
+    ctx->launches++;
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
+
+int mf_unary_from_label(Ctx *ctx, float *unary, const short *label_dev, int NT, int L, float u_energy,
+                        const float *n_en_dev, const float *p_en_dev) {
+    if (NT == 0) return LCCRF_OK;
+    k_unary_from_label<<<cdiv((long long)NT * L, kThreads), kThreads, 0, ctx->stream>>>(unary, label_dev, NT, L, u_energy,
+                                                                                       n_en_dev, p_en_dev);
+    ctx->launches++;
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
+
+int mf_exp_and_normalize(Ctx *ctx, float *out, const float *in, int NT, int L, float scale, float relax) {
+    if (NT == 0) return LCCRF_OK;
+    const int grid = cdiv(NT, kThreads);
+    if (L == 2) k_exp_normalize<2><<<grid, kThreads, 0, ctx->stream>>>(out, in, NT, L, scale, relax);
+    else k_exp_normalize<0><<<grid, kThreads, 0, ctx->stream>>>(out, in, NT, L, scale, relax);
+    ctx->launches++;
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
+
+// startInference: Q = softmax(-U)   densecrf_base.h:78-80
+int mf_start(Ctx *ctx, Batch &b) { return mf_exp_and_normalize(ctx, b.cur, b.unary, b.NT, b.L, -1.0f, 1.0f); }
+
+// stepInference   densecrf_base.h:82-91
+int mf_step(Ctx *ctx, Batch &b, float relax) {
+    if (b.NT == 0) return LCCRF_OK;
+    if (b.lat.empty()) {
+        k_negate<<<cdiv((long long)b.NT * b.L, kThreads), kThreads, 0, ctx->stream>>>(b.next, b.unary, (long long)b.NT * b.L);
+        ctx->launches++;
+    }
+    for (size_t k = 0; k < b.lat.size(); k++) LCCRF_TRY(mf_apply_fused(ctx, b, b.lat[k], b.cur, b.next, b.unary, k == 0));
+    return mf_exp_and_normalize(ctx, b.cur, b.next, b.NT, b.L, 1.0f, relax);
+}
+
+int mf_build_map(Ctx *ctx, Batch &b) {
+    if (b.NT == 0) return LCCRF_OK;
+    k_build_map<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(b.map, b.cur, b.NT, b.L);
+    ctx->launches++;
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
+
+}  // namespace lccrf
