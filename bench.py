@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- CRF problems/s of the LC-CRF hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[2] "C3" -- long-term unary + CRF, N = 100 000 map points
+x 64 keyframe observations each, 2 labels, 2 pairwise kernels (d = 2, 2), 5 mean-field iterations.
+One *step* = one pass of the whole hot path (unary from the map snapshot -> RroughClassify ->
+label->unary -> 2 lattice builds + norms -> 5 iterations -> MAP) over one batch of `--batch`
+independent problems per GPU.  Independent problems shard across GPUs with no collective (weak
+scaling: the per-GPU batch is fixed); torch.distributed only provides the barrier and the
+max-over-ranks of the device-timed region.
+
+  value   whole-job problems/s with the inputs resident in HBM (CUDA events, max over ranks)
+  e2e     the same metric through the C ABI with HOST buffers: pinned host -> device copies of every
+          input of the step and the device -> host read of MAP labels + marginals inside the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
+  cpu_baseline   the reference's CPU path on this box's host cores (bounded sample), rank 0 at N=1
+
+`--impl reference` times the reference's own CPU implementation instead (reference DenseCRF headers
+compiled in place when oracle/_ref exists, the oracle port otherwise; the unary is always the oracle
+port because Tracking.cc cannot be compiled), with all host threads.
+Other workloads for exploration: --workload c1 | c4 (not the headline).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "crf_problems_per_s"
+UNIT = "problems/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lccrf", choices=["lccrf", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4"])
+    ap.add_argument("--batch", type=int, default=0, help="problems per step per GPU (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: (description, default batch, points, observations per point)
+    "c3": ("C3: long-term unary + CRF, N=100k map points x 64 keyframe observations, L=2, K=2 (d=2,2), T=5", 8, 100000, 64),
+    "c1": ("C1: per-frame CRF, N=3000 points, L=2, K=2 (d=2,2), T=5 (reference's own CPU-runnable case)", 1, 3000, 0),
+    "c4": ("C4: 1024 independent per-frame CRFs of N~U[4000,6000] points in one launch sequence", 1024, 5000, 0),
+}
+
+
+def make_problems(workload: str, batch: int, seed0: int):
+    """Seeded synthetic problems.  Returns a list of MapSnapshot (c3) or SlamFrame (c1/c4)."""
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    _, _, n, obs = WORKLOADS[workload]
+    if workload == "c3":
+        return [synth.map_snapshot(n, obs, seed=seed0 + i) for i in range(batch)]
+    if workload == "c1":
+        return [synth.slam_frame(n, seed=seed0 + i) for i in range(batch)]
+    rng = np.random.default_rng(seed0)
+    sizes = rng.integers(4000, 6001, batch)
+    return [synth.slam_frame(int(s), seed=seed0 + 1 + i, dyn_frac=float(rng.uniform(0.15, 0.3))) for i, s in enumerate(sizes)]
+
+
+def concat_snapshots(snaps):
+    """Concatenate map snapshots into one batch: CSR pointers and keyframe ids are rebased."""
+    xyz = np.concatenate([s.xyz for s in snaps])
+    kp2d = np.concatenate([s.kp2d for s in snaps])
+    obs_uv = np.concatenate([s.obs_uv for s in snaps])
+    kf_pose = np.concatenate([s.kf_pose for s in snaps])
+    kf_intr = np.concatenate([s.kf_intr for s in snaps])
+    kf_bounds = np.concatenate([s.kf_bounds for s in snaps])
+    ptr, kf, eo, ko = [np.zeros(1, np.int64)], [], 0, 0
+    for s in snaps:
+        ptr.append(s.obs_ptr[1:].astype(np.int64) + eo)
+        kf.append(s.obs_kf + ko)
+        eo += s.nnz
+        ko += s.kf_pose.shape[0]
+    return dict(xyz=xyz, obs_ptr=np.concatenate(ptr).astype(np.int32), obs_kf=np.concatenate(kf).astype(np.int32),
+                obs_uv=obs_uv, kf_pose=kf_pose, kf_intr=kf_intr, kf_bounds=kf_bounds, kp2d=kp2d)
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- CPU reference arm
+def cpu_problem_runner(workload):
+    """Returns f(problem) -> None running the reference's CPU path on one problem (one host thread)."""
+    from oracle.pyoracle import Oracle, Ref, slam_params
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    pkg = importlib.import_module("lc-crf-slam_b200")
+    o = Oracle()
+    r = Ref() if Ref.available() else None
+    prm = slam_params(**synth.SLAM_PARAMS)
+    en = pkg.label_energies(2, prm.confidence)
+
+    def run(p):
+        if workload == "c3":
+            ob, er, de = o.map_point_unary(p)
+            kp = p.kp2d
+        else:
+            ob, er, de, kp = p.observs, p.error, p.depth, p.kp2d
+        lab = o.rough_classify(ob, er, de, prm)
+        if r is not None:
+            r.slam_crf(ob, er, kp, lab, prm)
+        else:
+            o.slam_crf(ob, er, kp, lab, en, prm)
+
+    kind = "reference" if r is not None else "port"
+    return run, kind
+
+
+def time_cpu(workload, problems, threads, repeats=1):
+    """`threads` host threads, each running whole problems (the reference has no intra-problem threading).
+    Returns problems/s over `repeats` passes of len(problems) problems."""
+    run, kind = cpu_problem_runner(workload)
+    run(problems[0])  # warm-up (page in, build tables)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            list(ex.map(run, problems))
+        dt = time.perf_counter() - t0
+    return repeats * len(problems) / dt, kind, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs and prints the reference arm
+    cores = os.cpu_count() or 1
+    desc, dbatch, n, obs = WORKLOADS[args.workload]
+    # bounded sample: one problem per host thread per step (c3: ~0.1-0.2 s of CPU work per problem)
+    per_step = cores if args.workload != "c4" else 4 * cores
+    base = make_problems(args.workload, min(per_step, 4), seed0=1000)
+    problems = [base[i % len(base)] for i in range(per_step)]
+    for _ in range(args.warmup):
+        time_cpu(args.workload, problems[:cores], cores)
+    t0 = time.perf_counter()
+    kind = "port"
+    for _ in range(args.steps):
+        _, kind, _ = time_cpu(args.workload, problems, cores)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    sample = "%d problems per step on %d host threads; CRF = %s, unary = oracle port (Tracking.cc is not compilable)" % (
+        per_step, cores, "reference headers compiled in place (oracle/_ref)" if kind == "reference" else "oracle port")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "problems_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, L=2, D=3):
+    """Algorithmic bytes of ONE launch of a kernel over the whole batch (DESIGN.md 'Kernels'): the
+    SURVEY 8(d) per-unit figures x the units one launch processes.  V_tot: vertices of the lattice set
+    the launch works on (mean over the two sets where a kernel serves both)."""
+    return {
+        "k_map_point_unary": nnz * 12 + N_tot * 24 + nKF * 80,       # B_u
+        "k_splat": N_tot * D * 8 + N_tot * L * 4 + V_tot * L * 8,    # offset+bary, in, accumulators
+        "k_blur": V_tot * (2 * L * 4 + 8),                           # read+write values, neighbour pair
+        "k_slice": N_tot * D * 8 + N_tot * L * 4 * 2 + N_tot * 4 + V_tot * L * 4,
+        "k_embed": N_tot * (2 * 4 + D * 8),                          # features in, slot + bary out
+        "k_exp_normalize": 2 * N_tot * L * 4,
+    }.get(name)
+
+
+def run_gpu_arm(args):
+    import torch
+    pkg = importlib.import_module("lc-crf-slam_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    desc, dbatch, n, obs = WORKLOADS[args.workload]
+    batch = args.batch or dbatch
+
+    # ---- problems of this rank (independent units: no collective on the data path)
+    problems = make_problems(args.workload, batch, seed0=1000 + 100000 * rank)
+    stream = torch.cuda.Stream()
+    ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
+    prm = pkg.SlamParams.make()
+    sizes = [p.n for p in problems]
+    F = pkg.Frames(ctx, sizes, prm)
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+
+    keep = []
+    if args.workload == "c3":
+        cat = concat_snapshots(problems)
+        host = {}
+        for k, v in cat.items():
+            host[k], t = pinned(v)
+            keep.append(t)
+        nnz, nKF = int(host["obs_kf"].size), int(host["kf_pose"].shape[0])
+
+        def upload():
+            F.set_map_inputs(host["xyz"], host["obs_ptr"], host["obs_kf"], host["obs_uv"], host["kf_pose"],
+                             host["kf_intr"], host["kf_bounds"], host["kp2d"])
+        h2d = sum(int(v.nbytes) for v in host.values())
+    else:
+        host = {}
+        for k in ("observs", "error", "depth", "kp2d"):
+            host[k], t = pinned(np.concatenate([getattr(p, k) for p in problems]))
+            keep.append(t)
+        nnz, nKF = 0, 0
+
+        def upload():
+            F.set_inputs(host["observs"], host["error"], host["depth"], host["kp2d"])
+        h2d = sum(int(v.nbytes) for v in host.values())
+    NT = int(sum(sizes))
+    out_map_t = torch.empty(NT, dtype=torch.int16).pin_memory()
+    out_prob_t = torch.empty((NT, 2), dtype=torch.float32).pin_memory()
+    out_map, out_prob = out_map_t.numpy(), out_prob_t.numpy()
+    d2h = int(out_map.nbytes + out_prob.nbytes)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident metric ("value")
+    upload()
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            F.run()
+        ctx.sync()
+        l0 = ctx.kernel_launches
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            F.run()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = ctx.kernel_launches - l0
+        clocks = sampler.stop() if sampler else None
+        # ---- end-to-end metric: host buffers in, host results out, every step
+        for _ in range(2):
+            upload(); F.run(); F.get_outputs(out_map, out_prob)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            upload()
+            F.run()
+            F.get_outputs(out_map, out_prob)
+        e1.record(stream)
+        barrier()
+        ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    t_dev = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)  # max over ranks
+    ms, ms_e2e = (float(x) for x in t_dev.tolist())
+    total_problems = world * batch * args.steps
+    value = total_problems / (ms * 1e-3)
+    e2e_value = total_problems / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0): per-kernel CUDA events on the launching stream
+    roofline, shares = None, None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if not args.no_profile:
+        with torch.cuda.stream(stream):
+            ctx.set_option("profile", 1)
+            ctx.profile_report()
+            nprof = 3
+            for _ in range(nprof):
+                F.run()
+            rep = ctx.profile_report()
+            ctx.set_option("profile", 0)
+        tot = sum(v[1] for v in rep.values()) or 1.0
+        shares = {k: round(v[1] / tot, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+        dbg = F.get_debug()
+        Vtot = float(dbg["V"].sum()) / 2.0  # mean over the two lattice sets
+        top = next(iter(shares))
+        cnt, tms = rep[top]
+        ab = algorithmic_kernel_bytes(top, NT, Vtot, nnz, nKF)
+        if ab is not None:
+            per_launch_ms = tms / cnt
+            ach = ab / (per_launch_ms * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                        "avg_launch_ms": per_launch_ms, "share_of_step": shares[top]}
+        else:
+            roofline = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                        "traffic": None, "peak_source": peak_src, "share_of_step": shares[top]}
+    abytes = F.algorithmic_bytes()
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        sample = [problems[i % len(problems)] for i in range(cores if args.workload != "c4" else 4 * cores)]
+        v, kind, dt = time_cpu(args.workload, sample, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d problems on %d host threads in %.1f s; CRF = %s, unary = oracle port" % (
+                   len(sample), cores, dt, "reference headers compiled in place" if kind == "reference" else "oracle port")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "problems_per_step_per_gpu": batch, "points_per_step_per_gpu": NT,
+                   "l2_policy": "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (abytes["total"] / 1e6),
+                   "sharding": "independent problems per rank, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernel_shares": shares,
+        "algorithmic_bytes_per_step": abytes,
+        "step_hbm_frac": (abytes["total"] / (ms / args.steps * 1e-3) / 1e9) / peak,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,11 @@ uint64_t lccrf_ctx_kernel_launches(const lccrf_ctx *ctx);
 /* option knobs: "graphs" (0/1, CUDA-graph replay of lccrf_frames_run), "fused" (0/1, per-problem
  * fused mean-field kernel when the lattices fit shared memory) */
 int lccrf_ctx_set_option(lccrf_ctx *ctx, const char *name, int value);
+/* Per-kernel timing.  With option "profile" = 1 every kernel launch is bracketed by two CUDA events on
+ * the launching stream (graphs are bypassed while profiling).  The report synchronises, writes one line
+ * per kernel name -- "name launches total_ms" -- into buf (NUL-terminated, truncated to cap) and
+ * clears the records.  Returns the number of distinct kernels, negative on error. */
+int lccrf_ctx_profile_report(lccrf_ctx *ctx, char *buf, int cap);
 
 /* ---------------------------------------------------------------- lattice ---------------- */
 /* Replaces PermutohedralLatticeCPU::init(feature, feature_size, N)
@@ -109,8 +114,9 @@ int lccrf_crf_build_map(lccrf_crf *crf);
  * changes them or destroy (densecrf_base.h:74-75).  NULL before they exist. */
 const short *lccrf_crf_map(lccrf_crf *crf);
 const float *lccrf_crf_prob(lccrf_crf *crf);
-/* lattice sizes of potential k (tests / diagnostics) */
+/* lattice sizes of potential k (tests / diagnostics); number of potentials added so far */
 int lccrf_crf_potts_vertices(const lccrf_crf *crf, int k, int *V);
+int lccrf_crf_num_potts(const lccrf_crf *crf);
 
 /* Plugin support: user-defined PairwisePotential::apply(out, in, tmp) on host pointers
  * (densecrf_base.h:12-19).  These expose the driver's pieces on host arrays so that the C++
@@ -119,6 +125,10 @@ int lccrf_crf_potts_vertices(const lccrf_crf *crf, int k, int *V);
  *   potts_apply: PottsPotential3D::apply   pairwise3d.h:73-78   out[N*L] += w*norm*filter(in)
  *   exp_and_normalize: DenseCRF3D<M>::expAndNormalize   densecrf3d.h:71-98 */
 int lccrf_crf_potts_apply(lccrf_crf *crf, int k, float *out, const float *in, float *tmp);
+/*   step_init: DenseCRF3D<M>::stepInit   densecrf3d.h:155-158   next[N*L] = -unary
+ *   set_prob:  overwrite current_ (the marginals) with host values after a host-driven step */
+int lccrf_crf_step_init(lccrf_crf *crf, float *next);
+int lccrf_crf_set_prob(lccrf_crf *crf, const float *prob);
 int lccrf_exp_and_normalize(lccrf_ctx *ctx, float *out, const float *in, int N, int L, float scale,
                             float relax);
 

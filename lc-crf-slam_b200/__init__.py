@@ -67,6 +67,7 @@ SYMBOLS = {
     "lccrf_ctx_sync": (C.c_int, [_vp]),
     "lccrf_ctx_kernel_launches": (C.c_uint64, [_vp]),
     "lccrf_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "lccrf_ctx_profile_report": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lccrf_lattice_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lccrf_lattice_destroy": (None, [_vp]),
     "lccrf_lattice_sizes": (C.c_int, [_vp, _ip, _ip, _ip]),
@@ -86,6 +87,9 @@ SYMBOLS = {
     "lccrf_crf_map": (_sp, [_vp]),
     "lccrf_crf_prob": (_fp, [_vp]),
     "lccrf_crf_potts_vertices": (C.c_int, [_vp, C.c_int, _ip]),
+    "lccrf_crf_num_potts": (C.c_int, [_vp]),
+    "lccrf_crf_step_init": (C.c_int, [_vp, _vp]),
+    "lccrf_crf_set_prob": (C.c_int, [_vp, _vp]),
     "lccrf_crf_potts_apply": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "lccrf_exp_and_normalize": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float]),
     "lccrf_map_point_unary": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -178,6 +182,18 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.lccrf_ctx_set_option(self.h, name.encode(), value))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total_ms)} since profiling was switched on; clears the records."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.lccrf_ctx_profile_report(self.h, buf, len(buf))
+        if n < 0:
+            self._check(n)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     @property
     def kernel_launches(self) -> int:

@@ -265,8 +265,45 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
     if (!h || !name) return fail(LCCRF_ERR_ARG, "NULL argument");
     if (!strcmp(name, "graphs")) h->c.opt_graphs = value;
     else if (!strcmp(name, "fused")) h->c.opt_fused = value;
+    else if (!strcmp(name, "profile")) h->c.opt_profile = value;
     else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);
     return LCCRF_OK;
+}
+
+int lccrf_ctx_profile_report(lccrf_ctx *h, char *buf, int cap) {
+    if (!h || !buf || cap < 1) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *c = &h->c;
+    LCCRF_CUDA(cudaSetDevice(c->device));
+    LCCRF_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<long long> cnt;
+    for (auto &r : c->prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        size_t k = 0;
+        for (; k < names.size(); k++)
+            if (names[k] == r.name) break;
+        if (k == names.size()) {
+            names.push_back(r.name);
+            ms.push_back(0);
+            cnt.push_back(0);
+        }
+        ms[k] += t;
+        cnt[k]++;
+    }
+    c->prof.clear();
+    std::string out;
+    char line[256];
+    for (size_t k = 0; k < names.size(); k++) {
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", names[k].c_str(), cnt[k], ms[k]);
+        out += line;
+    }
+    strncpy(buf, out.c_str(), (size_t)cap - 1);
+    buf[cap - 1] = 0;
+    return (int)names.size();
 }
 
 // ------------------------------------------------------------------ lattice
@@ -566,6 +603,32 @@ int lccrf_crf_potts_vertices(const lccrf_crf *crf, int k, int *V) {
     LCCRF_CUDA(cudaMemcpyAsync(ctx->h_status, crf->b.lat[k]->vbase + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
     *V = *ctx->h_status;
+    return LCCRF_OK;
+}
+
+int lccrf_crf_num_potts(const lccrf_crf *crf) { return crf ? (int)crf->b.lat.size() : 0; }
+
+int lccrf_crf_step_init(lccrf_crf *crf, float *next) {
+    if (!crf || !next) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)crf->b.NT * crf->b.L;
+    if (!n) return LCCRF_OK;
+    LCCRF_TRY(mf_negate(ctx, crf->b.next, crf->b.unary, (long long)n));
+    LCCRF_CUDA(cudaMemcpyAsync(next, crf->b.next, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+int lccrf_crf_set_prob(lccrf_crf *crf, const float *prob) {
+    if (!crf || !prob) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = crf->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)crf->b.NT * crf->b.L;
+    if (n) LCCRF_CUDA(cudaMemcpyAsync(crf->b.cur, prob, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    crf->started = true;
+    crf->prob_fresh = false;
     return LCCRF_OK;
 }
 
@@ -875,7 +938,7 @@ int lccrf_frames_run(lccrf_frames *fr) {
     if (!fr->have_inputs) return fail(LCCRF_ERR_STATE, "frames_run before set_inputs");
     Ctx *ctx = fr->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
-    if (!ctx->opt_graphs) {
+    if (!ctx->opt_graphs || ctx->opt_profile) {
         LCCRF_TRY(frames_enqueue(fr));
         fr->ran = true;
         return LCCRF_OK;

@@ -57,6 +57,13 @@ struct Ctx {
     uint64_t scratch_gen = 0;  // bumped whenever a scratch buffer moves (captured graphs hold raw pointers)
     int opt_graphs = 1;
     int opt_fused = 1;
+    // per-kernel CUDA-event timing (option "profile"): every launch site is bracketed by two events
+    int opt_profile = 0;
+    struct ProfRec {
+        const char *name;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> prof;
     // scratch for the lattice build (grown on demand, reused)
     struct Scratch {
         void *p = nullptr;
@@ -68,6 +75,29 @@ struct Ctx {
 };
 
 int ctx_scratch(Ctx *ctx, Ctx::Scratch &s, size_t bytes, bool pinned = false);
+
+// RAII bracket around one kernel launch: counts it and, in profile mode, times it with CUDA events
+// recorded on the launching stream.
+struct KernelScope {
+    Ctx *c;
+    int idx = -1;
+    KernelScope(Ctx *ctx, const char *name) : c(ctx) {
+        c->launches++;
+        if (c->opt_profile) {
+            Ctx::ProfRec r;
+            r.name = name;
+            if (cudaEventCreate(&r.a) == cudaSuccess && cudaEventCreate(&r.b) == cudaSuccess) {
+                cudaEventRecord(r.a, c->stream);
+                c->prof.push_back(r);
+                idx = (int)c->prof.size() - 1;
+            }
+        }
+    }
+    ~KernelScope() {
+        if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
+    }
+};
+#define LCCRF_KERNEL(ctx, name) ::lccrf::KernelScope _kscope_##__LINE__(ctx, name)
 int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero = false);
 void dev_free(Ctx *ctx, void *p);
 
@@ -91,6 +121,7 @@ int mf_exp_and_normalize(Ctx *ctx, float *out, const float *in, int NT, int L, f
 int mf_start(Ctx *ctx, Batch &b);
 int mf_step(Ctx *ctx, Batch &b, float relax);
 int mf_build_map(Ctx *ctx, Batch &b);
+int mf_negate(Ctx *ctx, float *out, const float *in, long long n);
 // potts apply on arbitrary device arrays (plugin path): tmp = filter(in); out += (w*norm)*tmp
 int mf_potts_apply(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out, const float *in, float *tmp, int L);
 // one potential of a mean-field step: next = (first ? -unary : next) + (w*norm)*filter(cur)

@@ -152,20 +152,18 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     const int NT = b.NT, D = ls->D;
     if (NT > 0) {
         const int grid = cdiv(NT, kThreads);
-        if (L == 1) k_splat<1><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, in_dev, ls->acc, NT, D, L, scale2_dev);
-        else if (L == 2) k_splat<2><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, in_dev, ls->acc, NT, D, L, scale2_dev);
-        else k_splat<0><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, in_dev, ls->acc, NT, D, L, scale2_dev);
-        ctx->launches++;
+        if (L == 1) { LCCRF_KERNEL(ctx, "k_splat"); k_splat<1><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, in_dev, ls->acc, NT, D, L, scale2_dev); }
+        else if (L == 2) { LCCRF_KERNEL(ctx, "k_splat"); k_splat<2><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, in_dev, ls->acc, NT, D, L, scale2_dev); }
+        else { LCCRF_KERNEL(ctx, "k_splat"); k_splat<0><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, in_dev, ls->acc, NT, D, L, scale2_dev); }
     }
     const int bgrid = persistent_grid((long long)ls->Vcap * L, kThreads, 8);
     const int *vt = ls->vbase + ls->B;
     float *src = ls->valA, *dst = ls->valB;
     for (int j = 0; j < D; j++) {
         const int2 *nb = ls->nbr + (size_t)j * ls->Vcap;
-        if (j == 0) k_blur<true, false><<<bgrid, kThreads, 0, st>>>(nb, ls->acc, nullptr, nullptr, dst, vt, L);
-        else if (j == 1) k_blur<false, true><<<bgrid, kThreads, 0, st>>>(nb, nullptr, ls->acc, src, dst, vt, L);
-        else k_blur<false, false><<<bgrid, kThreads, 0, st>>>(nb, nullptr, nullptr, src, dst, vt, L);
-        ctx->launches++;
+        if (j == 0) { LCCRF_KERNEL(ctx, "k_blur"); k_blur<true, false><<<bgrid, kThreads, 0, st>>>(nb, ls->acc, nullptr, nullptr, dst, vt, L); }
+        else if (j == 1) { LCCRF_KERNEL(ctx, "k_blur"); k_blur<false, true><<<bgrid, kThreads, 0, st>>>(nb, nullptr, ls->acc, src, dst, vt, L); }
+        else { LCCRF_KERNEL(ctx, "k_blur"); k_blur<false, false><<<bgrid, kThreads, 0, st>>>(nb, nullptr, nullptr, src, dst, vt, L); }
         float *t = src;
         src = dst;
         dst = t;
@@ -181,15 +179,14 @@ static int launch_slice(Ctx *ctx, int mode, const Batch &b, LatticeSet *ls, cons
     const int grid = cdiv((long long)b.NT * L, kThreads);
     cudaStream_t st = ctx->stream;
     if (mode == kPlain)
-        k_slice<kPlain><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, values, out, b.NT, ls->D, L, ls->alpha,
-                                                    scale2, 0.f, nullptr, nullptr);
+        { LCCRF_KERNEL(ctx, "k_slice"); k_slice<kPlain><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, values, out, b.NT, ls->D, L, ls->alpha,
+                                                    scale2, 0.f, nullptr, nullptr); }
     else if (mode == kApplyFirst)
-        k_slice<kApplyFirst><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, values, out, b.NT, ls->D, L,
-                                                         ls->alpha, nullptr, ls->w, ls->norm, unary);
+        { LCCRF_KERNEL(ctx, "k_slice"); k_slice<kApplyFirst><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, values, out, b.NT, ls->D, L,
+                                                         ls->alpha, nullptr, ls->w, ls->norm, unary); }
     else
-        k_slice<kApplyAdd><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, values, out, b.NT, ls->D, L,
-                                                       ls->alpha, nullptr, ls->w, ls->norm, nullptr);
-    ctx->launches++;
+        { LCCRF_KERNEL(ctx, "k_slice"); k_slice<kApplyAdd><<<grid, kThreads, 0, st>>>(ls->offset, ls->bary, values, out, b.NT, ls->D, L,
+                                                       ls->alpha, nullptr, ls->w, ls->norm, nullptr); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }
@@ -201,8 +198,7 @@ int filter_full(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out_dev, const 
     if (generic_range && b.NT > 0) {
         LCCRF_TRY(ctx_scratch(ctx, ctx->misc, 64));
         float *s2 = (float *)ctx->misc.p + 8;
-        k_absmax_scale<<<1, 1024, 0, ctx->stream>>>(in_dev, (long long)b.NT * L, s2);
-        ctx->launches++;
+        { LCCRF_KERNEL(ctx, "k_absmax_scale"); k_absmax_scale<<<1, 1024, 0, ctx->stream>>>(in_dev, (long long)b.NT * L, s2); }
         scale2 = s2;
     }
     const float *vals = nullptr;
@@ -213,13 +209,11 @@ int filter_full(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out_dev, const 
 // PottsPotential3D ctor: norm_ = 1/(filter(1)+1e-20)   pairwise3d.h:22-27
 int potts_norm(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     if (b.NT == 0) return LCCRF_OK;
-    k_fill<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(ls->norm, 1.0f, b.NT);
-    ctx->launches++;
+    { LCCRF_KERNEL(ctx, "k_fill"); k_fill<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(ls->norm, 1.0f, b.NT); }
     const float *vals = nullptr;
     LCCRF_TRY(filter_splat_blur(ctx, b, ls, ls->norm, 1, nullptr, &vals));
     LCCRF_TRY(launch_slice(ctx, kPlain, b, ls, vals, ls->norm, 1, nullptr, nullptr));
-    k_norm_finish<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(ls->norm, b.NT);
-    ctx->launches++;
+    { LCCRF_KERNEL(ctx, "k_norm_finish"); k_norm_finish<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(ls->norm, b.NT); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }
@@ -233,8 +227,7 @@ int mf_potts_apply(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out, const f
     // (power-of-two scaling commutes with every rounding step)
     if (b.NT > 0) {
         float *s2 = (float *)ctx->misc.p + 8;
-        k_absmax_scale<<<1, 1024, 0, ctx->stream>>>(in, (long long)b.NT * L, s2);
-        ctx->launches++;
+        { LCCRF_KERNEL(ctx, "k_absmax_scale"); k_absmax_scale<<<1, 1024, 0, ctx->stream>>>(in, (long long)b.NT * L, s2); }
         scale2 = s2;
     }
     LCCRF_TRY(filter_splat_blur(ctx, b, ls, in, L, scale2, &vals));

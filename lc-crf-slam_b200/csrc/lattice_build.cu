@@ -367,18 +367,15 @@ int launch_build(Ctx *ctx, const BuildParams &p) {
     const int NP = p.NT + p.B;
     const long long S = (long long)NP * D;
     const int nblk = cdiv(S, kThreads);
-    k_embed<d><<<cdiv(NP, kThreads), kThreads, 0, st>>>(p);
-    k_mark<D><<<nblk, kThreads, 0, st>>>(p);
-    k_scan_blocks<<<1, 1024, 0, st>>>(p.blk_cnt, nblk, p.vbase + p.B);
-    k_assign<D><<<nblk, kThreads, 0, st>>>(p);
-    k_vbase<D><<<cdiv(p.B, 128), 128, 0, st>>>(p);
-    ctx->launches += 5;
+    { LCCRF_KERNEL(ctx, "k_embed"); k_embed<d><<<cdiv(NP, kThreads), kThreads, 0, st>>>(p); }
+    { LCCRF_KERNEL(ctx, "k_mark"); k_mark<D><<<nblk, kThreads, 0, st>>>(p); }
+    { LCCRF_KERNEL(ctx, "k_scan_blocks"); k_scan_blocks<<<1, 1024, 0, st>>>(p.blk_cnt, nblk, p.vbase + p.B); }
+    { LCCRF_KERNEL(ctx, "k_assign"); k_assign<D><<<nblk, kThreads, 0, st>>>(p); }
+    { LCCRF_KERNEL(ctx, "k_vbase"); k_vbase<D><<<cdiv(p.B, 128), 128, 0, st>>>(p); }
     if (p.NT > 0) {
-        k_offsets<D><<<cdiv(p.NT, kThreads), kThreads, 0, st>>>(p);
-        ctx->launches += 1;
+        { LCCRF_KERNEL(ctx, "k_offsets"); k_offsets<D><<<cdiv(p.NT, kThreads), kThreads, 0, st>>>(p); }
     }
-    k_neighbours<d><<<persistent_grid((long long)p.Vcap, kThreads, 4), kThreads, 0, st>>>(p);
-    ctx->launches += 1;
+    { LCCRF_KERNEL(ctx, "k_neighbours"); k_neighbours<d><<<persistent_grid((long long)p.Vcap, kThreads, 4), kThreads, 0, st>>>(p); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }

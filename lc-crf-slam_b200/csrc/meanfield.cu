@@ -135,8 +135,7 @@ k_axpy_norm(float *__restrict__ out, const float *__restrict__ tmp, const float 
 
 int launch_axpy_norm(Ctx *ctx, float *out, const float *tmp, const float *norm, float w, int NT, int L) {
     if (NT == 0) return LCCRF_OK;
-    k_axpy_norm<<<cdiv((long long)NT * L, kThreads), kThreads, 0, ctx->stream>>>(out, tmp, norm, w, NT, L);
-    ctx->launches++;
+    { LCCRF_KERNEL(ctx, "k_axpy_norm"); k_axpy_norm<<<cdiv((long long)NT * L, kThreads), kThreads, 0, ctx->stream>>>(out, tmp, norm, w, NT, L); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }
@@ -144,9 +143,8 @@ int launch_axpy_norm(Ctx *ctx, float *out, const float *tmp, const float *norm, 
 int mf_unary_from_label(Ctx *ctx, float *unary, const short *label_dev, int NT, int L, float u_energy,
                         const float *n_en_dev, const float *p_en_dev) {
     if (NT == 0) return LCCRF_OK;
-    k_unary_from_label<<<cdiv((long long)NT * L, kThreads), kThreads, 0, ctx->stream>>>(unary, label_dev, NT, L, u_energy,
-                                                                                       n_en_dev, p_en_dev);
-    ctx->launches++;
+    { LCCRF_KERNEL(ctx, "k_unary_from_label"); k_unary_from_label<<<cdiv((long long)NT * L, kThreads), kThreads, 0, ctx->stream>>>(unary, label_dev, NT, L, u_energy,
+                                                                                       n_en_dev, p_en_dev); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }
@@ -154,9 +152,15 @@ int mf_unary_from_label(Ctx *ctx, float *unary, const short *label_dev, int NT, 
 int mf_exp_and_normalize(Ctx *ctx, float *out, const float *in, int NT, int L, float scale, float relax) {
     if (NT == 0) return LCCRF_OK;
     const int grid = cdiv(NT, kThreads);
-    if (L == 2) k_exp_normalize<2><<<grid, kThreads, 0, ctx->stream>>>(out, in, NT, L, scale, relax);
-    else k_exp_normalize<0><<<grid, kThreads, 0, ctx->stream>>>(out, in, NT, L, scale, relax);
-    ctx->launches++;
+    if (L == 2) { LCCRF_KERNEL(ctx, "k_exp_normalize"); k_exp_normalize<2><<<grid, kThreads, 0, ctx->stream>>>(out, in, NT, L, scale, relax); }
+    else { LCCRF_KERNEL(ctx, "k_exp_normalize"); k_exp_normalize<0><<<grid, kThreads, 0, ctx->stream>>>(out, in, NT, L, scale, relax); }
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
+
+int mf_negate(Ctx *ctx, float *out, const float *in, long long n) {
+    if (n == 0) return LCCRF_OK;
+    { LCCRF_KERNEL(ctx, "k_negate"); k_negate<<<cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(out, in, n); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }
@@ -167,18 +171,14 @@ int mf_start(Ctx *ctx, Batch &b) { return mf_exp_and_normalize(ctx, b.cur, b.una
 // stepInference   densecrf_base.h:82-91
 int mf_step(Ctx *ctx, Batch &b, float relax) {
     if (b.NT == 0) return LCCRF_OK;
-    if (b.lat.empty()) {
-        k_negate<<<cdiv((long long)b.NT * b.L, kThreads), kThreads, 0, ctx->stream>>>(b.next, b.unary, (long long)b.NT * b.L);
-        ctx->launches++;
-    }
+    if (b.lat.empty()) LCCRF_TRY(mf_negate(ctx, b.next, b.unary, (long long)b.NT * b.L));
     for (size_t k = 0; k < b.lat.size(); k++) LCCRF_TRY(mf_apply_fused(ctx, b, b.lat[k], b.cur, b.next, b.unary, k == 0));
     return mf_exp_and_normalize(ctx, b.cur, b.next, b.NT, b.L, 1.0f, relax);
 }
 
 int mf_build_map(Ctx *ctx, Batch &b) {
     if (b.NT == 0) return LCCRF_OK;
-    k_build_map<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(b.map, b.cur, b.NT, b.L);
-    ctx->launches++;
+    { LCCRF_KERNEL(ctx, "k_build_map"); k_build_map<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(b.map, b.cur, b.NT, b.L); }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }

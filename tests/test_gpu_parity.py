@@ -1,0 +1,374 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/liblccrf oracle) and the committed golden fixtures.  Bit-exact for integer/index data
+(vertex ids, neighbour tables) and for barycentric bit patterns; marginals within 1e-4 relative
+(north_star); MAP labels identical except at reported near-ties."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from util import assert_map, assert_marginals, bits, rel_err, tie_features
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+synth = importlib.import_module("lc-crf-slam_b200.synth")
+
+
+def oracle_params():
+    from oracle.pyoracle import slam_params
+    return slam_params(**synth.SLAM_PARAMS)
+
+
+# ------------------------------------------------------------------ lattice: bit-exact
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7])
+def test_lattice_bit_exact(pkg, ctx, oracle, d):
+    rng = np.random.default_rng(100 + d)
+    for N in (0, 1, 3, 4, 5, 6, 7, 8, 257, 1000, 5003):
+        f = tie_features(rng, N, d)
+        lo = oracle.lattice(f)
+        lg = pkg.Lattice(ctx, f)
+        off, bary, nbr = lg.export()
+        assert lg.V == lo["V"], (d, N)
+        assert np.array_equal(off, lo["offset"]), (d, N)
+        assert np.array_equal(bits(bary), bits(lo["bary"])), (d, N)
+        assert np.array_equal(nbr, lo["nbr"]), (d, N)
+        oracle.lattice_free(lo)
+        lg.close()
+
+
+def test_lattice_phantom_lanes(pkg, ctx):
+    got = []
+    for N in (4, 5, 6, 7, 8):
+        f = np.array([[100 + 0.01 * i, 100] for i in range(N)], dtype=np.float32)
+        lg = pkg.Lattice(ctx, f)
+        got.append(lg.V)
+        lg.close()
+    assert got == [3, 6, 6, 6, 3]
+
+
+def test_lattice_golden_reference_vectors(pkg, ctx):
+    """fixtures produced by the unmodified reference headers (tests/golden/make_golden.py)"""
+    g = np.load(os.path.join(GOLD, "golden_ref.npz"))
+    for d, N in ((2, 6), (2, 257), (3, 130), (5, 203)):
+        k = "lat_d%d_n%d_" % (d, N)
+        lg = pkg.Lattice(ctx, g[k + "feat"])
+        off, bary, nbr = lg.export()
+        assert np.array_equal(off, g[k + "offset"])
+        assert np.array_equal(bits(bary), bits(g[k + "bary"]))
+        assert np.array_equal(nbr, g[k + "nbr"])
+        y = lg.filter(g[k + "x"])
+        assert rel_err(y, g[k + "y"]).max() < 1e-5
+        lg.close()
+
+
+def test_lattice_large_image_shapes(pkg, ctx, oracle):
+    """C2-shaped lattices: 640x480 Gaussian (d=2) and bilateral (d=5)."""
+    W, H = 640, 480
+    img, _ = synth.image_problem(W, H, 11)
+    for F, posdev, fd in ((2, 3.0, 0.0), (5, 60.0, 20.0)):
+        f = oracle.features_image(W, H, F, posdev, img if F == 5 else None, fd)
+        lo = oracle.lattice(f)
+        lg = pkg.Lattice(ctx, f)
+        off, bary, nbr = lg.export()
+        assert lg.V == lo["V"]
+        assert np.array_equal(off, lo["offset"]) and np.array_equal(bits(bary), bits(lo["bary"])) and np.array_equal(nbr, lo["nbr"])
+        oracle.lattice_free(lo)
+        lg.close()
+
+
+def test_lattice_key_range_error(pkg, ctx):
+    f = np.full((16, 2), 3.0e4, dtype=np.float32)  # elevates beyond the reference's short keys
+    with pytest.raises(pkg.LccrfError, match="short range"):
+        pkg.Lattice(ctx, f)
+    lg = pkg.Lattice(ctx, np.zeros((4, 2), np.float32))  # the context stays usable
+    assert lg.V == 3
+    lg.close()
+
+
+# ------------------------------------------------------------------ filter
+@pytest.mark.parametrize("d,N", [(2, 1000), (3, 777), (5, 2049)])
+def test_filter_parity_and_properties(pkg, ctx, oracle, d, N):
+    rng = np.random.default_rng(d * N)
+    f = tie_features(rng, N, d, 2.0)
+    lo = oracle.lattice(f)
+    lg = pkg.Lattice(ctx, f)
+    for L in (1, 2, 3, 21):
+        x = (rng.random((N, L)) * 7 - 2).astype(np.float32)
+        yo, yg = oracle.filter(lo, x), lg.filter(x)
+        scale = np.abs(yo).max()
+        assert np.abs(yg - yo).max() <= 2e-6 * scale, (d, N, L)
+        # linearity (size-independent property): filter(2x) == 2*filter(x) exactly (power-of-two scaling)
+        assert np.array_equal(bits(lg.filter(2 * x)), bits(2 * yg))
+        # determinism: integer accumulation -> run-to-run bit identical
+        assert np.array_equal(bits(lg.filter(x)), bits(yg))
+    oracle.lattice_free(lo)
+    lg.close()
+
+
+# ------------------------------------------------------------------ driver pieces
+def test_exp_and_normalize_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(3)
+    for L in (2, 3, 21):
+        x = (rng.normal(0, 8, (4001, L))).astype(np.float32)
+        x[::13] *= 4  # exercise the < -20 cut-off and the range-reduction loops
+        for scale, relax in ((-1.0, 1.0), (1.0, 1.0), (1.0, 0.5)):
+            prev = rng.random((4001, L)).astype(np.float32)
+            a = ctx.exp_and_normalize(x, scale, relax, prev)
+            b = oracle.exp_and_normalize(x, scale, relax, prev)
+            assert np.array_equal(bits(a), bits(b)), (L, scale, relax)
+
+
+# ------------------------------------------------------------------ SLAM CRF (Tracking.cc:1919-1930)
+def run_gpu_slam_crf(pkg, ctx, fr, lab, en, prm, iters=5):
+    crf = pkg.DenseCRF(ctx, fr.n, 2)
+    crf.setUnaryEnergyFromLabel(lab, energies=en)
+    crf.addPairwiseEnergy(np.stack([fr.observs / np.float32(prm.stdev_beta), fr.error / np.float32(prm.stdev_alpha)], 1), prm.w1)
+    crf.addPairwiseEnergy(fr.kp2d / np.float32(prm.point2d_stdev), prm.w2)
+    crf.inference(iters, True)
+    out = crf.getProbability(), crf.getMap(), (crf.potts_vertices(0), crf.potts_vertices(1))
+    crf.close()
+    return out
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 5, 2999, 3000, 3001, 3002, 100000])
+def test_slam_crf_parity(pkg, ctx, oracle, N):
+    prm_o, prm = oracle_params(), pkg.SlamParams.make()
+    en = pkg.label_energies(2, prm.confidence)
+    fr = synth.slam_frame(N, seed=N)
+    lab = oracle.rough_classify(fr.observs, fr.error, fr.depth, prm_o)
+    Qo, mo, Vo = oracle.slam_crf(fr.observs, fr.error, fr.kp2d, lab, en, prm_o)
+    Q, m, V = run_gpu_slam_crf(pkg, ctx, fr, lab, en, prm)
+    assert tuple(Vo) == V
+    if N:
+        assert_marginals(Q, Qo, what="N=%d" % N)
+        assert_map(m, mo, Qo, what="N=%d" % N)
+
+
+def test_slam_crf_golden_reference(pkg, ctx):
+    """marginals + MAP produced by the unmodified reference on a seeded 1003-point frame"""
+    g = np.load(os.path.join(GOLD, "golden_ref.npz"))
+    prm = pkg.SlamParams.make()
+    fr = synth.SlamFrame(g["slam_observs"], g["slam_error"], np.zeros_like(g["slam_error"]), g["slam_kp2d"], None)
+    Q, m, _ = run_gpu_slam_crf(pkg, ctx, fr, g["slam_label"], g["slam_energies"], prm)
+    assert_marginals(Q, g["slam_Q"], what="golden_ref")
+    assert_map(m, g["slam_map"], g["slam_Q"], what="golden_ref")
+
+
+def test_generic_labels_dims_relax_and_stepwise(pkg, ctx, oracle):
+    rng = np.random.default_rng(5)
+    N = 1500
+    for L, dims in ((3, (2, 3)), (4, (5,)), (21, (2,)), (2, ())):
+        feats = [tie_features(rng, N, d, 2.0) for d in dims]
+        unary = rng.random((N, L)).astype(np.float32) * 3
+        w = [3.0 + k for k in range(len(dims))]
+        for relax in (1.0, 0.5):
+            Qo, mo, _ = oracle.meanfield(unary, feats, w, 4, relax)
+            crf = pkg.DenseCRF(ctx, N, L)
+            crf.setUnaryEnergy(unary)
+            for f, wk in zip(feats, w):
+                crf.addPairwiseEnergy(f, wk)
+            crf.startInference()            # step-by-step API (densecrf_base.h:78-91)
+            for _ in range(4):
+                crf.stepInference(relax)
+            assert crf.getMap() is None     # map_ does not exist before buildMap (densecrf3d.h:139)
+            crf.buildMap()
+            assert_marginals(crf.getProbability(), Qo, what="L=%d dims=%s relax=%g" % (L, dims, relax))
+            assert_map(crf.getMap(), mo, Qo)
+            crf.close()
+
+
+def test_unary_entry_poke_and_unknown_labels(pkg, ctx, oracle):
+    N, L = 600, 3
+    rng = np.random.default_rng(8)
+    lab = rng.integers(-1, L, N).astype(np.int16)
+    en = pkg.label_energies(L, 0.6)
+    f = tie_features(rng, N, 2, 2.0)
+    unary = oracle.unary_from_label(lab, L, en[0], np.full(L, en[1], np.float32), np.full(L, en[2], np.float32))
+    unary[17, 2] = 0.25
+    Qo, mo, _ = oracle.meanfield(unary, [f], [4.0], 3)
+    crf = pkg.DenseCRF(ctx, N, L)
+    crf.setUnaryEnergyFromLabel(lab, energies=en)
+    crf.SetUnaryEnergtForPositiveNode(17, 2, 0.25)
+    crf.addPairwiseEnergy(f, 4.0)
+    crf.inference(3, True)
+    assert_marginals(crf.getProbability(), Qo)
+    assert_map(crf.getMap(), mo, Qo)
+    crf.close()
+
+
+def test_plugin_pieces_potts_apply(pkg, ctx, oracle):
+    """PottsPotential3D::apply on host arrays (the plugin path of the C++ mirror)."""
+    N, L = 900, 2
+    rng = np.random.default_rng(12)
+    f = tie_features(rng, N, 2, 2.0)
+    lo = oracle.lattice(f)
+    norm = oracle.potts_norm(lo)
+    x = rng.random((N, L)).astype(np.float32)
+    out0 = rng.normal(0, 1, (N, L)).astype(np.float32)
+    tmp_o = oracle.filter(lo, x)
+    exp = out0 + (np.float32(5.0) * norm)[:, None] * tmp_o
+    crf = pkg.DenseCRF(ctx, N, L)
+    crf.addPairwiseEnergy(f, 5.0)
+    out, tmp = crf.potts_apply(0, out0, x)
+    assert np.abs(tmp - tmp_o).max() <= 2e-6 * np.abs(tmp_o).max()
+    assert np.abs(out - exp).max() <= 1e-5 * np.abs(exp).max()
+    crf.close()
+    oracle.lattice_free(lo)
+
+
+# ------------------------------------------------------------------ golden image (the reference's own KAT)
+def test_golden_image_kat(pkg, ctx, oracle):
+    g = np.load(os.path.join(GOLD, "golden_im1.npz"))
+    W, H, M = int(g["W"]), int(g["H"]), 21
+    c = np.float32(0.5)
+    en = np.array([-np.log(np.float64(np.float32(1.0) / np.float32(M))), -np.log(np.float64((np.float32(1.0) - c) / np.float32(M - 1))),
+                   -np.log(np.float64(c))]).astype(np.float32)
+    crf = pkg.DenseCRF(ctx, W * H, M)
+    crf.setUnaryEnergyFromLabel(g["label"], energies=en)
+    crf.addPairwiseFromImage(W, H, 3.0, 3.0)
+    crf.addPairwiseFromImage(W, H, 10.0, 60.0, g["im"], 20.0)
+    crf.inference(10, True)
+    m, Q = crf.getMap(), crf.getProbability()
+    crf.close()
+    # oracle marginals (bit-equal to the reference's) to qualify any mismatch as a near-tie
+    unary = oracle.unary_from_label(g["label"], M, en[0], np.full(M, en[1], np.float32), np.full(M, en[2], np.float32))
+    Qo, mo, _ = oracle.meanfield(unary, [oracle.features_image(W, H, 2, 3.0), oracle.features_image(W, H, 5, 60.0, g["im"], 20.0)],
+                                 [3.0, 10.0], 10)
+    assert np.array_equal(mo, g["map"])
+    nties = assert_map(m, g["map"], Qo, what="res1_cpu.ppm")
+    assert nties <= 8
+    assert_marginals(Q, Qo, what="golden image marginals")
+
+
+def test_image_crf_c2_small(pkg, ctx, oracle):
+    """C2 recipe (DenseCRFCPU<2>, Gaussian + bilateral, 10 iterations) at 160x120."""
+    W, H = 160, 120
+    img, lab = synth.image_problem(W, H, 4)
+    en = pkg.label_energies(2, 0.7)
+    unary = oracle.unary_from_label(lab, 2, en[0], np.full(2, en[1], np.float32), np.full(2, en[2], np.float32))
+    Qo, mo, _ = oracle.meanfield(unary, [oracle.features_image(W, H, 2, 3.0), oracle.features_image(W, H, 5, 60.0, img, 20.0)],
+                                 [3.0, 10.0], 10)
+    crf = pkg.DenseCRF(ctx, W * H, 2)
+    crf.setUnaryEnergyFromLabel(lab, energies=en)
+    crf.addPairwiseFromImage(W, H, 3.0, 3.0)
+    crf.addPairwiseFromImage(W, H, 10.0, 60.0, img, 20.0)
+    crf.inference(10, True)
+    assert_marginals(crf.getProbability(), Qo)
+    assert_map(crf.getMap(), mo, Qo)
+    assert 0 < mo.sum() < W * H
+    crf.close()
+
+
+# ------------------------------------------------------------------ long-term unary
+@pytest.mark.parametrize("N,obs,ragged", [(1, 1, False), (31, 3, True), (5000, 64, True), (20000, 64, False), (300, 2500, True)])
+def test_map_point_unary_bit_exact(ctx, oracle, N, obs, ragged):
+    snap = synth.map_snapshot(N, obs, seed=N + obs, ragged=ragged)
+    ob, er, de = oracle.map_point_unary(snap)
+    gob, ger, gde = ctx.map_point_unary(snap)
+    assert np.array_equal(ob, gob)
+    assert np.array_equal(bits(er), bits(ger))
+    assert np.array_equal(bits(de), bits(gde))
+
+
+def test_rough_classify(pkg, ctx, oracle):
+    prm_o, prm = oracle_params(), pkg.SlamParams.make()
+    fr = synth.slam_frame(50000, 21)
+    for p4 in (None, np.random.default_rng(1).random(50000)):
+        lo = oracle.rough_classify(fr.observs, fr.error, fr.depth, prm_o, p4)
+        lg = ctx.rough_classify(fr.observs, fr.error, fr.depth, prm, p4)
+        # exp() is glibc expf on the host and exp(double)->float on the device: labels may only differ
+        # where the likelihood sum sits within rounding of the threshold
+        assert (lo != lg).sum() <= 2
+        assert 0 < lo.sum() < lo.size
+
+
+# ------------------------------------------------------------------ batched frames (C4) and the C3 pipeline
+def test_frames_batch_parity(pkg, ctx, oracle):
+    prm_o, prm = oracle_params(), pkg.SlamParams.make()
+    en = pkg.label_energies(2, prm.confidence)
+    rng = np.random.default_rng(42)
+    sizes = [0, 1, 4001, 4002, 4003, 4004] + rng.integers(4000, 6001, 10).tolist()
+    frames = [synth.slam_frame(n, seed=1000 + i) for i, n in enumerate(sizes)]
+    F = pkg.Frames(ctx, sizes, prm, en)
+    cat = lambda k: np.concatenate([getattr(f, k) for f in frames])
+    F.set_inputs(cat("observs"), cat("error"), cat("depth"), cat("kp2d"))
+    for graphs in (0, 1, 1):  # plain launches, capture, replay
+        ctx.set_option("graphs", graphs)
+        F.run()
+        mp, pr = F.get_outputs()
+        dbg = F.get_debug()
+        o = 0
+        for b, fr in enumerate(frames):
+            lab = oracle.rough_classify(fr.observs, fr.error, fr.depth, prm_o)
+            assert np.array_equal(lab, dbg["init_label"][o:o + fr.n])
+            Qo, mo, Vo = oracle.slam_crf(fr.observs, fr.error, fr.kp2d, lab, en, prm_o)
+            assert tuple(Vo) == tuple(dbg["V"][b]), b
+            if fr.n:
+                assert_marginals(pr[o:o + fr.n], Qo, what="problem %d" % b)
+                assert_map(mp[o:o + fr.n], mo, Qo, what="problem %d" % b)
+            o += fr.n
+    ab = F.algorithmic_bytes()
+    assert ab["total"] > 0 and ab["per_iteration"] > 0
+    F.close()
+
+
+def test_frames_from_map_snapshot_c3_small(pkg, ctx, oracle):
+    """C3 pipeline at reduced size: unary from the map snapshot -> classify -> CRF, all on the device."""
+    prm_o, prm = oracle_params(), pkg.SlamParams.make()
+    en = pkg.label_energies(2, prm.confidence)
+    snap = synth.map_snapshot(20000, 64, seed=5)
+    F = pkg.Frames(ctx, [snap.n], prm, en)
+    F.set_map_inputs(snap.xyz, snap.obs_ptr, snap.obs_kf, snap.obs_uv, snap.kf_pose, snap.kf_intr, snap.kf_bounds, snap.kp2d)
+    F.run()
+    F.run()
+    mp, pr = F.get_outputs()
+    dbg = F.get_debug()
+    ob, er, de = oracle.map_point_unary(snap)
+    assert np.array_equal(bits(er), bits(dbg["error"])) and np.array_equal(bits(de), bits(dbg["depth"]))
+    lab = oracle.rough_classify(ob, er, de, prm_o)
+    assert (lab != dbg["init_label"]).sum() <= 1
+    Qo, mo, Vo = oracle.slam_crf(ob, er, snap.kp2d, dbg["init_label"], en, prm_o)
+    assert tuple(Vo) == tuple(dbg["V"][0])
+    assert_marginals(pr, Qo)
+    assert_map(mp, mo, Qo)
+    assert 0 < mo.sum() < snap.n
+    F.close()
+
+
+def test_frames_rejects_points_without_observations(pkg, ctx):
+    snap = synth.map_snapshot(64, 4, seed=1)
+    ptr = snap.obs_ptr.copy()
+    ptr[10] = ptr[9]  # point 9 has no observation: Tracking.cc:1858 drops it before the CRF
+    F = pkg.Frames(ctx, [snap.n])
+    with pytest.raises(pkg.LccrfError, match="1858"):
+        F.set_map_inputs(snap.xyz, ptr, snap.obs_kf, snap.obs_uv, snap.kf_pose, snap.kf_intr, snap.kf_bounds, snap.kp2d)
+    F.close()
+
+
+def test_full_size_properties_c3(pkg, ctx):
+    """BASELINE full size (N=100k x 64 obs): size-independent properties instead of an oracle run --
+    determinism (bit-identical reruns), normalisation, MAP == argmax, problem independence in a batch."""
+    prm = pkg.SlamParams.make()
+    snap = synth.map_snapshot(100000, 64, seed=77)
+    F = pkg.Frames(ctx, [snap.n], prm)
+    F.set_map_inputs(snap.xyz, snap.obs_ptr, snap.obs_kf, snap.obs_uv, snap.kf_pose, snap.kf_intr, snap.kf_bounds, snap.kp2d)
+    F.run()
+    m1, p1 = F.get_outputs()
+    F.run()
+    m2, p2 = F.get_outputs()
+    assert np.array_equal(bits(p1), bits(p2)) and np.array_equal(m1, m2)
+    assert np.abs(p1.sum(1) - 1).max() < 1e-6
+    assert np.array_equal(m1, (p1[:, 1] > p1[:, 0]).astype(np.int16))
+    d1 = F.get_debug()
+    F.close()
+    # the same problem inside a batch of 3 gives bit-identical results (problems share no state)
+    fr = synth.slam_frame(3000, 5)
+    F3 = pkg.Frames(ctx, [fr.n, snap.n, fr.n], prm)
+    cat = lambda a, b: np.concatenate([a, b, a])
+    F3.set_inputs(cat(fr.observs, d1["observs"]), cat(fr.error, d1["error"]), cat(fr.depth, d1["depth"]), cat(fr.kp2d, snap.kp2d))
+    F3.run()
+    m3, p3 = F3.get_outputs()
+    assert np.array_equal(bits(p3[fr.n:fr.n + snap.n]), bits(p1))
+    assert np.array_equal(bits(p3[:fr.n]), bits(p3[fr.n + snap.n:]))
+    F3.close()

@@ -1,0 +1,89 @@
+"""CPU tests of the host-side logic: synthetic generators, problem sharding, and the N>1 launch
+path on gloo (world_size 2) -- the data path has no collective, only barrier + max-reduce of timings."""
+import importlib
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+synth = importlib.import_module("lc-crf-slam_b200.synth")
+shard = importlib.import_module("lc-crf-slam_b200.shard")
+
+
+def test_shard_contiguous_covers_everything_once():
+    rng = np.random.default_rng(0)
+    for n, world in ((1024, 8), (1024, 3), (5, 8), (8, 8), (1, 2), (0, 4), (17, 4)):
+        w = rng.integers(4000, 6001, n).tolist()
+        parts = shard.shard_contiguous(w, world)
+        assert len(parts) == world
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        for (a, b), (c, d) in zip(parts, parts[1:]):
+            assert b == c and a <= b
+        if n >= world:
+            loads = [sum(w[a:b]) for a, b in parts]
+            assert min(loads) > 0
+            assert max(loads) <= 1.25 * (sum(w) / world) + max(w)
+
+
+def test_shard_round_robin():
+    for world in (1, 2, 4, 8):
+        seen = sorted(sum((shard.shard_round_robin(8, world, r) for r in range(world)), []))
+        assert seen == list(range(8))
+
+
+def test_synth_shapes_and_determinism():
+    a, b = synth.slam_frame(3001, 7), synth.slam_frame(3001, 7)
+    assert a.n == 3001 and np.array_equal(a.error, b.error) and a.kp2d.shape == (3001, 2)
+    assert a.observs.min() >= 1 and 0.05 < a.dynamic.mean() < 0.5
+    s = synth.map_snapshot(1000, 64, 3)
+    assert s.nnz == 64000 and s.obs_ptr[-1] == s.nnz and s.obs_kf.max() < s.kf_pose.shape[0]
+    r = synth.map_snapshot(500, 32, 3, ragged=True)
+    assert np.diff(r.obs_ptr).min() >= 1
+    img, lab = synth.image_problem(64, 48, 1)
+    assert img.shape == (64 * 48, 3) and img.dtype == np.uint8 and set(np.unique(lab)) <= {-1, 0, 1}
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+WORKER = r"""
+import importlib, os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, %r)
+shard = importlib.import_module("lc-crf-slam_b200.shard")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sizes = [4000 + 37 * i %% 2000 for i in range(64)]
+a, b = shard.shard_contiguous(sizes, world)[rank]
+mine = torch.zeros(64, dtype=torch.int64); mine[a:b] = 1
+dist.barrier()
+t = torch.tensor([0.010 * (rank + 1)], dtype=torch.float64)      # per-rank elapsed time
+dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # max over ranks, as bench.py does
+cov = mine.clone(); dist.all_reduce(cov)                          # test-only: every problem owned exactly once
+n = torch.tensor([b - a]); dist.all_reduce(n)
+if rank == 0:
+    assert bool((cov == 1).all()) and int(n) == 64 and abs(float(t) - 0.010 * world) < 1e-12
+    print("OK", float(t), int(n))
+dist.destroy_process_group()
+"""
+
+
+def test_gloo_world2_sharding(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert "OK" in outs[0][0]
