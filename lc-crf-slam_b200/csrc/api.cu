@@ -392,7 +392,7 @@ int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L)
     }
     float *d_in = lat->io, *d_out = lat->io + n;
     LCCRF_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LCCRF_TRY(filter_full(ctx, lat->b, lat->ls, d_out, d_in, L, /*generic_range=*/true));
+    LCCRF_TRY(filter_full(ctx, lat->b, lat->ls, d_out, d_in, L));
     LCCRF_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
     return LCCRF_OK;

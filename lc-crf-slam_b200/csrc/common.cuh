@@ -42,23 +42,7 @@ static inline int persistent_grid(long long work_items, int threads = kThreads, 
     return (int)(need < 1 ? 1 : need);
 }
 
-// ------------------------------------------------------------------ fixed-point splat accumulator
-// Contributions bary*value (|.| <= ~1 after the per-call input scale) are accumulated as
-// signed 64-bit fixed point with kFixShift fractional bits: integer addition is associative, so
-// the vertex sums are independent of thread order (deterministic, no float atomics) and carry
-// ~2^-41 absolute error per contribution -- far below the fp32 rounding of the reference's
-// own sequential float sum.  Range: 2^(63-40) = 8.4M unit contributions per vertex.
-constexpr int kFixShift = 40;
-
 #ifdef __CUDACC__
-__device__ __forceinline__ long long to_fix(float c) {
-    // c * 2^40 is exact in double (24-bit mantissa, power-of-two scale); one rounding to integer
-    return __double2ll_rn((double)c * (double)(1ull << kFixShift));
-}
-__device__ __forceinline__ float from_fix(long long a) {
-    return (float)((double)a * (1.0 / (double)(1ull << kFixShift)));
-}
-
 // ------------------------------------------------------------------ hash of a 64-bit key word
 __device__ __forceinline__ uint32_t mix64(uint64_t x) {
     x ^= x >> 33;

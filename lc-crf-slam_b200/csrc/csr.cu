@@ -1,0 +1,334 @@
+// csr.cu -- vertex-sorted view of a lattice set: for every lattice vertex the list of (point, barycentric
+// weight) entries that splat onto it, IN POINT ORDER.
+//
+// The reference splats sequentially over points (permutohedral_cpu.h:653-661), so the float value of a
+// vertex is the left-to-right sum of its contributions in point order.  Sorting the N*(d+1) entries by
+// (vertex, point) once per lattice turns the splat into a segmented reduction over contiguous rows --
+// no atomics, and a row walked front to back reproduces the reference's rounding bit for bit.
+//
+// Stable counting sort by vertex id, parallel over chunks of points:
+//   k_csr_zero / k_csr_count   per-(chunk, vertex) entry counts                (integer atomics only)
+//   k_csr_prefix               per vertex: exclusive prefix over its problem's chunks; row length
+//   scan (3 launches)          row_ptr = exclusive scan of row lengths over all vertices of the batch
+//   k_csr_fill                 every chunk walks its entries in scan order; warps commit in turn, lanes rank
+//                              themselves with match.any, so equal vertices keep their point order
+#include "engine.cuh"
+
+namespace lccrf {
+
+namespace {
+
+constexpr int kFillThreads = 1024;
+constexpr int kFillWarps = kFillThreads / 32;
+constexpr int kCursorSmemInts = 14336;  // 56 KB of shared cursors: lattices up to 14k vertices per problem
+
+struct CsrParams {
+    int G;                   // chunks
+    int D;
+    const int *chunk_prob;   // [G]
+    const int *chunk_s0;     // [G] first entry (point*D) of the chunk
+    const int *chunk_s1;     // [G] one past the last entry
+    const long long *chunk_tbl;  // [G] base of the chunk's count row in tbl (stride = worst-case V of the problem)
+    const int *prob_chunk0;  // [B+1] first chunk of each problem
+    const int *offset;       // [NT*D] global vertex ids
+    const float *bary;       // [NT*D]
+    const int *vbase;        // [B+1]
+    const int *vert_prob;    // [V]
+    int *tbl;
+    int *row_len;            // [Vcap+1] -> row_ptr after the scan
+    int2 *ent;               // [NT*D] {point, bary bits} sorted by (vertex, point)
+};
+
+__global__ void __launch_bounds__(kThreads) k_csr_zero(CsrParams p) {
+    const int g = blockIdx.x;
+    const int b = __ldg(p.chunk_prob + g);
+    const int Vb = __ldg(p.vbase + b + 1) - __ldg(p.vbase + b);
+    int *row = p.tbl + __ldg(p.chunk_tbl + g);
+    for (int v = threadIdx.x; v < Vb; v += kThreads) row[v] = 0;
+}
+
+__global__ void __launch_bounds__(kThreads) k_csr_count(CsrParams p) {
+    const int g = blockIdx.x;
+    const int b = __ldg(p.chunk_prob + g);
+    const int vb = __ldg(p.vbase + b);
+    int *row = p.tbl + __ldg(p.chunk_tbl + g);
+    const int s0 = __ldg(p.chunk_s0 + g), s1 = __ldg(p.chunk_s1 + g);
+    const unsigned lane = threadIdx.x & 31;
+    for (int base = s0; base < s1; base += kThreads) {
+        const int s = base + threadIdx.x;
+        const int v = s < s1 ? __ldg(p.offset + s) - vb : -1;
+        const unsigned grp = __match_any_sync(0xffffffffu, v);
+        if (v >= 0 && (__ffs(grp) - 1) == (int)lane) atomicAdd(row + v, __popc(grp));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_csr_prefix(CsrParams p, int B) {
+    const int V = __ldg(p.vbase + B);
+    for (int v = blockIdx.x * kThreads + threadIdx.x; v < V; v += gridDim.x * kThreads) {
+        const int b = __ldg(p.vert_prob + v);
+        const int lv = v - __ldg(p.vbase + b);
+        const int g0 = __ldg(p.prob_chunk0 + b), g1 = __ldg(p.prob_chunk0 + b + 1);
+        int run = 0;
+        for (int g = g0; g < g1; g++) {
+            int *c = p.tbl + __ldg(p.chunk_tbl + g) + lv;
+            const int n = *c;
+            *c = run;
+            run += n;
+        }
+        p.row_len[v] = run;
+    }
+}
+
+// ---- generic exclusive scan of ints whose length lives on the device (3 launches) ----
+__global__ void __launch_bounds__(1024) k_scan_local(int *x, const int *n_ptr, int *blk_tot) {
+    __shared__ int ws[32];
+    const int n = __ldg(n_ptr);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int blk = blockIdx.x; blk * 1024 < n + 1; blk += gridDim.x) {  // n+1: the row_ptr sentinel
+        const int idx = blk * 1024 + threadIdx.x;
+        const int v = idx < n ? x[idx] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane == 31) ws[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int t = ws[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            ws[lane] = t;
+        }
+        __syncthreads();
+        const int excl = (wid ? ws[wid - 1] : 0) + s - v;
+        if (idx <= n) x[idx] = excl;
+        if (threadIdx.x == 1023) blk_tot[blk] = ws[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tot(int *blk_tot, const int *n_ptr) {
+    // exclusive scan of the block totals, single CTA (ceil((n+1)/1024) values)
+    __shared__ int ws[32];
+    __shared__ int carry_s;
+    const int nblk = (__ldg(n_ptr) + 1 + 1023) / 1024;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int start = 0; start < nblk; start += 1024) {
+        const int idx = start + threadIdx.x;
+        const int v = idx < nblk ? blk_tot[idx] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane == 31) ws[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int t = ws[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            ws[lane] = t;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (idx < nblk) blk_tot[idx] = carry + (wid ? ws[wid - 1] : 0) + s - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + ws[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(int *x, const int *n_ptr, const int *blk_tot) {
+    const int n = __ldg(n_ptr);
+    for (int blk = blockIdx.x; blk * 1024 < n + 1; blk += gridDim.x) {
+        const int idx = blk * 1024 + threadIdx.x;
+        if (idx <= n) x[idx] += __ldg(blk_tot + blk);
+    }
+}
+
+// every chunk walks its entries in scan order, 1024 per round; warps take turns so that the per-vertex
+// cursors advance in entry order; inside a warp equal vertices are ranked by lane (= entry order)
+template <bool SMEM_CURSORS>
+__global__ void __launch_bounds__(kFillThreads) k_csr_fill(CsrParams p) {
+    extern __shared__ int s_cur[];
+    __shared__ volatile int turn;
+    const int g = blockIdx.x;
+    const int b = __ldg(p.chunk_prob + g);
+    const int vb = __ldg(p.vbase + b);
+    const int Vb = __ldg(p.vbase + b + 1) - vb;
+    int *row = p.tbl + __ldg(p.chunk_tbl + g);
+    if (SMEM_CURSORS != (Vb <= kCursorSmemInts)) return;  // the other instantiation handles this chunk
+    const int s0 = __ldg(p.chunk_s0 + g), s1 = __ldg(p.chunk_s1 + g);
+    const unsigned lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    if (SMEM_CURSORS)
+        for (int v = threadIdx.x; v < Vb; v += kFillThreads) s_cur[v] = row[v];
+    if (threadIdx.x == 0) turn = 0;
+    __syncthreads();
+    int round = 0;
+    for (int base = s0; base < s1; base += kFillThreads, round++) {
+        const int s = base + threadIdx.x;
+        const bool valid = s < s1;
+        int v = -1, rp = 0;
+        float w = 0.f;
+        if (valid) {
+            v = __ldg(p.offset + s);
+            w = __ldg(p.bary + s);
+            rp = __ldg(p.row_len + v);  // row_ptr after the scan
+            v -= vb;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, v);
+        const int leader = __ffs(grp) - 1;
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        const int my_turn = round * kFillWarps + wid;
+        while (turn != my_turn) { /* spin: warps of this CTA commit in order */ }
+        __threadfence_block();
+        int cur = 0;
+        if (valid && (int)lane == leader) {
+            if (SMEM_CURSORS) {
+                cur = s_cur[v];
+                s_cur[v] = cur + __popc(grp);
+            } else {
+                cur = ((volatile int *)row)[v];
+                ((volatile int *)row)[v] = cur + __popc(grp);
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) turn = my_turn + 1;
+        cur = __shfl_sync(0xffffffffu, cur, leader);
+        if (valid) p.ent[rp + cur + rank] = make_int2(s / p.D, __float_as_int(w));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ med,
+               int *__restrict__ lng, int *__restrict__ counts) {
+    const int V = __ldg(vtotal);
+    for (int v = blockIdx.x * kThreads + threadIdx.x; v < V; v += gridDim.x * kThreads) {
+        const int len = __ldg(row_ptr + v + 1) - __ldg(row_ptr + v);
+        if (len >= kLongRow) lng[atomicAdd(counts + 1, 1)] = v;       // list order is irrelevant: rows are independent
+        else if (len >= kMedRow) med[atomicAdd(counts, 1)] = v;
+    }
+}
+
+}  // namespace
+
+int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
+    const int D = ls->D;
+    std::vector<int> chunk_prob, chunk_s0, chunk_s1, prob_chunk0(b.B + 1);
+    std::vector<long long> chunk_tbl;
+    long long tbl = 0;
+    for (int i = 0; i < b.B; i++) {
+        prob_chunk0[i] = (int)chunk_prob.size();
+        const int p0 = b.h_prob_ptr[i], p1 = b.h_prob_ptr[i + 1];
+        const long long stride = ((long long)(p1 - p0) + 1) * D;  // worst-case vertex count of the problem
+        for (int c = p0; c < p1; c += kCsrChunkPoints) {
+            chunk_prob.push_back(i);
+            chunk_s0.push_back(c * D);
+            chunk_s1.push_back((c + kCsrChunkPoints < p1 ? c + kCsrChunkPoints : p1) * D);
+            chunk_tbl.push_back(tbl);
+            tbl += stride;
+        }
+    }
+    prob_chunk0[b.B] = (int)chunk_prob.size();
+    ls->csr_chunks = (int)chunk_prob.size();
+    if (tbl > (1ll << 31) - 1) return fail(LCCRF_ERR_ARG, "CSR count table would exceed 2^31 entries");
+    const size_t G = (size_t)(ls->csr_chunks > 0 ? ls->csr_chunks : 1);
+    int rc = LCCRF_OK;
+    rc |= dev_alloc(ctx, (void **)&ls->chunk_prob, G * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->chunk_s0, G * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->chunk_s1, G * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->chunk_tbl, G * 8);
+    rc |= dev_alloc(ctx, (void **)&ls->prob_chunk0, (size_t)(b.B + 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->csr_tbl, (size_t)(tbl > 0 ? tbl : 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->row_ptr, ((size_t)ls->Vcap + 2) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->csr_ent, (size_t)(b.NT > 0 ? b.NT : 1) * D * sizeof(int2));
+    rc |= dev_alloc(ctx, (void **)&ls->scan_tot, ((size_t)ls->Vcap / 1024 + 2) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->row_list_med, ((size_t)ls->Vcap + 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->row_list_long, ((size_t)ls->Vcap + 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 2 * 4);
+    if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    if (ls->csr_chunks > 0) {
+        LCCRF_CUDA(cudaMemcpyAsync(ls->chunk_prob, chunk_prob.data(), G * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(ls->chunk_s0, chunk_s0.data(), G * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(ls->chunk_s1, chunk_s1.data(), G * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(ls->chunk_tbl, chunk_tbl.data(), G * 8, cudaMemcpyHostToDevice, st));
+    }
+    LCCRF_CUDA(cudaMemcpyAsync(ls->prob_chunk0, prob_chunk0.data(), (size_t)(b.B + 1) * 4, cudaMemcpyHostToDevice, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    return LCCRF_OK;
+}
+
+void csr_destroy(Ctx *ctx, LatticeSet *ls) {
+    dev_free(ctx, ls->chunk_prob);
+    dev_free(ctx, ls->chunk_s0);
+    dev_free(ctx, ls->chunk_s1);
+    dev_free(ctx, ls->chunk_tbl);
+    dev_free(ctx, ls->prob_chunk0);
+    dev_free(ctx, ls->csr_tbl);
+    dev_free(ctx, ls->row_ptr);
+    dev_free(ctx, ls->csr_ent);
+    dev_free(ctx, ls->scan_tot);
+    dev_free(ctx, ls->row_list_med);
+    dev_free(ctx, ls->row_list_long);
+    dev_free(ctx, ls->row_counts);
+}
+
+int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
+    cudaStream_t st = ctx->stream;
+    CsrParams p;
+    p.G = ls->csr_chunks;
+    p.D = ls->D;
+    p.chunk_prob = ls->chunk_prob;
+    p.chunk_s0 = ls->chunk_s0;
+    p.chunk_s1 = ls->chunk_s1;
+    p.chunk_tbl = ls->chunk_tbl;
+    p.prob_chunk0 = ls->prob_chunk0;
+    p.offset = ls->offset;
+    p.bary = ls->bary;
+    p.vbase = ls->vbase;
+    p.vert_prob = ls->vert_prob;
+    p.tbl = ls->csr_tbl;
+    p.row_len = ls->row_ptr;
+    p.ent = ls->csr_ent;
+    const int *vt = ls->vbase + ls->B;
+    if (p.G > 0) {
+        { LCCRF_KERNEL(ctx, "k_csr_zero"); k_csr_zero<<<p.G, kThreads, 0, st>>>(p); }
+        { LCCRF_KERNEL(ctx, "k_csr_count"); k_csr_count<<<p.G, kThreads, 0, st>>>(p); }
+    }
+    const int vgrid = persistent_grid((long long)ls->Vcap, kThreads, 4);
+    { LCCRF_KERNEL(ctx, "k_csr_prefix"); k_csr_prefix<<<vgrid, kThreads, 0, st>>>(p, b.B); }
+    const int sgrid = persistent_grid((long long)ls->Vcap + 1, 1024, 2);
+    { LCCRF_KERNEL(ctx, "k_scan_local"); k_scan_local<<<sgrid, 1024, 0, st>>>(ls->row_ptr, vt, ls->scan_tot); }
+    { LCCRF_KERNEL(ctx, "k_scan_tot"); k_scan_tot<<<1, 1024, 0, st>>>(ls->scan_tot, vt); }
+    { LCCRF_KERNEL(ctx, "k_scan_add"); k_scan_add<<<sgrid, 1024, 0, st>>>(ls->row_ptr, vt, ls->scan_tot); }
+    if (p.G > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            LCCRF_CUDA(cudaFuncSetAttribute(k_csr_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kCursorSmemInts * (int)sizeof(int)));
+            attr_set = true;
+        }
+        { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<true><<<p.G, kFillThreads, kCursorSmemInts * sizeof(int), st>>>(p); }
+        { LCCRF_KERNEL(ctx, "k_csr_fill_g"); k_csr_fill<false><<<p.G, kFillThreads, 0, st>>>(p); }
+    }
+    LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 2 * sizeof(int), st));
+    { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_med, ls->row_list_long, ls->row_counts); }
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
+
+}  // namespace lccrf

@@ -31,11 +31,25 @@ struct LatticeSet {
     int *tab_base = nullptr;    // [B+1] first hash slot of each problem's open-addressing region (build only)
     long long tab_slots = 0;
     float *norm = nullptr;      // [NT] 1/(filter(1)+1e-20)   (pairwise3d.h:22-27)
+    // vertex-sorted view for the splat (csr.cu): row v = entries [row_ptr[v], row_ptr[v+1]) in point order
+    int *row_ptr = nullptr;     // [Vcap+2]
+    int2 *csr_ent = nullptr;    // [NT*D] {global point index, bary bits}
+    int csr_chunks = 0;
+    int *chunk_prob = nullptr, *chunk_s0 = nullptr, *chunk_s1 = nullptr, *prob_chunk0 = nullptr;
+    long long *chunk_tbl = nullptr;
+    int *csr_tbl = nullptr, *scan_tot = nullptr;
+    // rows by length class (filled by csr_build): [0, kMedRow) lane-sequential, [kMedRow, kLongRow) one warp
+    // per row, [kLongRow, ..) one CTA per row -- the latter two with the exact ordered scan (filter.cu)
+    int *row_list_med = nullptr, *row_list_long = nullptr;  // [Vcap] each
+    int *row_counts = nullptr;                              // [2] device: #medium, #long
     // filter workspace
-    long long *acc = nullptr;   // [Vcap*Lmax] fixed-point splat accumulators (kept zero between calls)
     float *valA = nullptr, *valB = nullptr;  // [Vcap*Lmax] blur ping-pong
     int Lmax = 0;
 };
+
+constexpr int kCsrChunkPoints = 8192;
+constexpr int kMedRow = 96;     // rows at least this long leave the lane-sequential kernel
+constexpr int kLongRow = 3072;  // rows at least this long get a whole CTA  // points per chunk of the parallel stable counting sort
 
 struct Batch {
     Ctx *ctx = nullptr;
@@ -107,12 +121,14 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
 void lattice_set_destroy(Ctx *ctx, LatticeSet *ls);
 int lattice_set_build(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *feat_dev);
 int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L);  // (re)allocate the filter workspace for L labels
-// filter (filter.cu): out/in device [NT*L]; in_max = upper bound of |in| (power-of-two scaling of the accumulator)
-// scale2_dev: optional device pair {2^-e, 2^e} bringing |in| <= 1 (nullptr: inputs already in [-1, 1])
+// vertex-sorted CSR of a built lattice set (csr.cu)
+int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls);
+void csr_destroy(Ctx *ctx, LatticeSet *ls);
+int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls);
+// filter (filter.cu): out/in device [NT*L]
 int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_dev, int L,
-                      const float *scale2_dev, const float **values_out);
-int filter_full(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out_dev, const float *in_dev, int L,
-                bool generic_range);
+                      const float **values_out);
+int filter_full(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out_dev, const float *in_dev, int L);
 int potts_norm(Ctx *ctx, const Batch &b, LatticeSet *ls);
 // mean field (meanfield.cu)
 int mf_unary_from_label(Ctx *ctx, float *unary, const short *label_dev, int NT, int L, float u_energy,

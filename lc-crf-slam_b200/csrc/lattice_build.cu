@@ -408,7 +408,6 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
     rc |= dev_alloc(ctx, (void **)&ls->vbase, (size_t)(b.B + 1) * sizeof(int));
     rc |= dev_alloc(ctx, (void **)&ls->norm, (size_t)(b.NT > 0 ? b.NT : 1) * sizeof(float));
     if (Lmax > 0) {
-        rc |= dev_alloc(ctx, (void **)&ls->acc, (size_t)ls->Vcap * Lmax * sizeof(long long), /*zero=*/true);
         rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * Lmax * sizeof(float));
         rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * Lmax * sizeof(float));
     }
@@ -441,6 +440,10 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
         lattice_set_destroy(ctx, ls);
         return fail(LCCRF_ERR_CUDA, std::string("tab_base upload: ") + cudaGetErrorString(e));
     }
+    if (csr_create(ctx, b, ls) != LCCRF_OK) {
+        lattice_set_destroy(ctx, ls);
+        return LCCRF_ERR_CUDA;
+    }
     *out = ls;
     return LCCRF_OK;
 }
@@ -448,14 +451,11 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
 int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     if (L <= ls->Lmax) return LCCRF_OK;
     if (L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "label count exceeds LCCRF_MAX_L");
-    dev_free(ctx, ls->acc);
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
-    ls->acc = nullptr;
     ls->valA = ls->valB = nullptr;
     ls->Lmax = 0;
     int rc = LCCRF_OK;
-    rc |= dev_alloc(ctx, (void **)&ls->acc, (size_t)ls->Vcap * L * sizeof(long long), /*zero=*/true);
     rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * L * sizeof(float));
     rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * L * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
@@ -472,10 +472,10 @@ void lattice_set_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->vert_prob);
     dev_free(ctx, ls->vbase);
     dev_free(ctx, ls->norm);
-    dev_free(ctx, ls->acc);
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
     dev_free(ctx, ls->tab_base);
+    csr_destroy(ctx, ls);
     delete ls;
 }
 
@@ -520,16 +520,19 @@ int lattice_set_build(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *fea
     for (int i = 0; i < d; i++) p.scale[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * (double)inv_std_dev);
     p.invD = 1.0f / (d + 1);
     p.fD = (float)(d + 1);
+    int rc = LCCRF_ERR_ARG;
     switch (d) {
-        case 1: return launch_build<1>(ctx, p);
-        case 2: return launch_build<2>(ctx, p);
-        case 3: return launch_build<3>(ctx, p);
-        case 4: return launch_build<4>(ctx, p);
-        case 5: return launch_build<5>(ctx, p);
-        case 6: return launch_build<6>(ctx, p);
-        case 7: return launch_build<7>(ctx, p);
+        case 1: rc = launch_build<1>(ctx, p); break;
+        case 2: rc = launch_build<2>(ctx, p); break;
+        case 3: rc = launch_build<3>(ctx, p); break;
+        case 4: rc = launch_build<4>(ctx, p); break;
+        case 5: rc = launch_build<5>(ctx, p); break;
+        case 6: rc = launch_build<6>(ctx, p); break;
+        case 7: rc = launch_build<7>(ctx, p); break;
+        default: return fail(LCCRF_ERR_ARG, "unsupported feature dimension");
     }
-    return fail(LCCRF_ERR_ARG, "unsupported feature dimension");
+    LCCRF_TRY(rc);
+    return csr_build(ctx, b, ls);
 }
 
 }  // namespace lccrf

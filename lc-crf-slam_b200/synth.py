@@ -117,7 +117,7 @@ def map_snapshot(n: int, obs_per_point: int, seed: int, n_kf: int = 256, intr=TU
         pose[k] = np.concatenate([R, tcw[:, None]], axis=1).reshape(-1)
     # current-frame keypoints and depths -> world points (current frame = identity pose)
     xy = np.stack([rng.uniform(20, IMG_W - 20, n), rng.uniform(20, IMG_H - 20, n)], axis=1)
-    z = rng.uniform(1.0, 5.0, n)
+    z = np.clip(rng.normal(2.75, 0.45, n), 1.0, 5.0)  # around u_depth (TUM3.yaml:98)
     xyz = np.stack([(xy[:, 0] - cx) / fx * z, (xy[:, 1] - cy) / fy * z, z], axis=1)
     dyn = _dynamic_mask(rng, xy, dyn_frac)
     if ragged:
@@ -135,7 +135,7 @@ def map_snapshot(n: int, obs_per_point: int, seed: int, n_kf: int = 256, intr=TU
     Xc = np.einsum('nij,nj->ni', P[:, :, :3], X) + P[:, :, 3]
     u = fx * Xc[:, 0] / Xc[:, 2] + cx
     v = fy * Xc[:, 1] / Xc[:, 2] + cy
-    uv = np.stack([u, v], axis=1) + rng.normal(0, 0.8, (nnz, 2))
+    uv = np.stack([u, v], axis=1) + rng.normal(0, 1.25, (nnz, 2))  # residual ~ u_alpha for static points
     d = dyn[pt]
     drift = rng.uniform(5, 20, nnz) * d
     ang = rng.uniform(0, 2 * np.pi, nnz)

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from util import assert_map, assert_marginals
+from util import assert_bit_exact, assert_map, assert_marginals
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -65,8 +65,8 @@ def test_tracking_callsite_dropin(pkg, oracle, tmp_path, N):
         qr, mr, _ = oracle.slam_crf(fr.observs, fr.error, fr.kp2d, lab, pkg.label_energies(2, prm.confidence),
                                     slam_params(**synth.SLAM_PARAMS))
     if N:
-        assert_marginals(q, qr)
-        assert_map(m, mr, qr)
+        assert_bit_exact(q, qr)
+        assert np.array_equal(m, mr)
 
 
 PLUGIN_SRC = r"""
@@ -132,8 +132,8 @@ def test_plugin_potential_on_host_pointers(pkg, ctx, oracle, tmp_path):
     feat = (np.array(vals[:2 * N], np.float32) * np.float32(20)).reshape(N, 2)
     unary = (np.array(vals[2 * N:], np.float32) * np.float32(2)).reshape(N, 2)
     Qo, mo, _ = oracle.meanfield(unary, [feat], [4.0], 3)
-    assert_marginals(res["plain"][1], Qo)
-    assert_map(res["plain"][0], mo, Qo)
+    assert_bit_exact(res["plain"][1], Qo)
+    assert np.array_equal(res["plain"][0], mo)
     # with the plugin: emulate the host loop with oracle pieces
     lat = oracle.lattice(feat)
     norm = oracle.potts_norm(lat)
@@ -191,4 +191,4 @@ int main(int argc, char **argv) {
     r = subprocess.run([exe, inp, out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     m = np.frombuffer(open(out, "rb").read(), dtype=np.int16)
-    assert (m != g["map"]).sum() <= 8, int((m != g["map"]).sum())
+    assert np.array_equal(m, g["map"]), int((m != g["map"]).sum())

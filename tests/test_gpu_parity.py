@@ -1,14 +1,16 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle
-(oracle/liblccrf oracle) and the committed golden fixtures.  Bit-exact for integer/index data
-(vertex ids, neighbour tables) and for barycentric bit patterns; marginals within 1e-4 relative
-(north_star); MAP labels identical except at reported near-ties."""
+(oracle/liboracle.so) and the committed golden fixtures.  Bit-exact for integer/index data (vertex ids,
+neighbour tables) and for barycentric bit patterns.  north_star asks for marginals within 1e-4 relative
+and MAP labels identical except at near-ties; the CUDA path keeps the reference's operation order
+(ordered segmented splat), so the tests assert the stronger property: marginals BIT-identical, MAP
+identical.  Only the init-label classifier (glibc expf vs device exp) is tolerance-based."""
 import importlib
 import os
 
 import numpy as np
 import pytest
 
-from util import assert_map, assert_marginals, bits, rel_err, tie_features
+from util import assert_bit_exact, assert_map, assert_marginals, bits, rel_err, tie_features
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -57,8 +59,7 @@ def test_lattice_golden_reference_vectors(pkg, ctx):
         assert np.array_equal(off, g[k + "offset"])
         assert np.array_equal(bits(bary), bits(g[k + "bary"]))
         assert np.array_equal(nbr, g[k + "nbr"])
-        y = lg.filter(g[k + "x"])
-        assert rel_err(y, g[k + "y"]).max() < 1e-5
+        assert_bit_exact(lg.filter(g[k + "x"]), g[k + "y"], what=k)
         lg.close()
 
 
@@ -96,8 +97,7 @@ def test_filter_parity_and_properties(pkg, ctx, oracle, d, N):
     for L in (1, 2, 3, 21):
         x = (rng.random((N, L)) * 7 - 2).astype(np.float32)
         yo, yg = oracle.filter(lo, x), lg.filter(x)
-        scale = np.abs(yo).max()
-        assert np.abs(yg - yo).max() <= 2e-6 * scale, (d, N, L)
+        assert_bit_exact(yg, yo, what="filter d=%d N=%d L=%d" % (d, N, L))
         # linearity (size-independent property): filter(2x) == 2*filter(x) exactly (power-of-two scaling)
         assert np.array_equal(bits(lg.filter(2 * x)), bits(2 * yg))
         # determinism: integer accumulation -> run-to-run bit identical
@@ -141,8 +141,9 @@ def test_slam_crf_parity(pkg, ctx, oracle, N):
     Q, m, V = run_gpu_slam_crf(pkg, ctx, fr, lab, en, prm)
     assert tuple(Vo) == V
     if N:
-        assert_marginals(Q, Qo, what="N=%d" % N)
-        assert_map(m, mo, Qo, what="N=%d" % N)
+        assert_marginals(Q, Qo, what="N=%d" % N)   # the north_star gate
+        assert_bit_exact(Q, Qo, what="N=%d" % N)   # what the ordered splat actually delivers
+        assert np.array_equal(m, mo)
 
 
 def test_slam_crf_golden_reference(pkg, ctx):
@@ -151,8 +152,8 @@ def test_slam_crf_golden_reference(pkg, ctx):
     prm = pkg.SlamParams.make()
     fr = synth.SlamFrame(g["slam_observs"], g["slam_error"], np.zeros_like(g["slam_error"]), g["slam_kp2d"], None)
     Q, m, _ = run_gpu_slam_crf(pkg, ctx, fr, g["slam_label"], g["slam_energies"], prm)
-    assert_marginals(Q, g["slam_Q"], what="golden_ref")
-    assert_map(m, g["slam_map"], g["slam_Q"], what="golden_ref")
+    assert_bit_exact(Q, g["slam_Q"], what="golden_ref")
+    assert np.array_equal(m, g["slam_map"])
 
 
 def test_generic_labels_dims_relax_and_stepwise(pkg, ctx, oracle):
@@ -173,8 +174,8 @@ def test_generic_labels_dims_relax_and_stepwise(pkg, ctx, oracle):
                 crf.stepInference(relax)
             assert crf.getMap() is None     # map_ does not exist before buildMap (densecrf3d.h:139)
             crf.buildMap()
-            assert_marginals(crf.getProbability(), Qo, what="L=%d dims=%s relax=%g" % (L, dims, relax))
-            assert_map(crf.getMap(), mo, Qo)
+            assert_bit_exact(crf.getProbability(), Qo, what="L=%d dims=%s relax=%g" % (L, dims, relax))
+            assert np.array_equal(crf.getMap(), mo)
             crf.close()
 
 
@@ -192,8 +193,8 @@ def test_unary_entry_poke_and_unknown_labels(pkg, ctx, oracle):
     crf.SetUnaryEnergtForPositiveNode(17, 2, 0.25)
     crf.addPairwiseEnergy(f, 4.0)
     crf.inference(3, True)
-    assert_marginals(crf.getProbability(), Qo)
-    assert_map(crf.getMap(), mo, Qo)
+    assert_bit_exact(crf.getProbability(), Qo)
+    assert np.array_equal(crf.getMap(), mo)
     crf.close()
 
 
@@ -211,8 +212,8 @@ def test_plugin_pieces_potts_apply(pkg, ctx, oracle):
     crf = pkg.DenseCRF(ctx, N, L)
     crf.addPairwiseEnergy(f, 5.0)
     out, tmp = crf.potts_apply(0, out0, x)
-    assert np.abs(tmp - tmp_o).max() <= 2e-6 * np.abs(tmp_o).max()
-    assert np.abs(out - exp).max() <= 1e-5 * np.abs(exp).max()
+    assert_bit_exact(tmp, tmp_o)
+    assert_bit_exact(out, exp)
     crf.close()
     oracle.lattice_free(lo)
 
@@ -236,9 +237,8 @@ def test_golden_image_kat(pkg, ctx, oracle):
     Qo, mo, _ = oracle.meanfield(unary, [oracle.features_image(W, H, 2, 3.0), oracle.features_image(W, H, 5, 60.0, g["im"], 20.0)],
                                  [3.0, 10.0], 10)
     assert np.array_equal(mo, g["map"])
-    nties = assert_map(m, g["map"], Qo, what="res1_cpu.ppm")
-    assert nties <= 8
-    assert_marginals(Q, Qo, what="golden image marginals")
+    assert np.array_equal(m, g["map"]), "%d px differ from res1_cpu.ppm" % int((m != g["map"]).sum())
+    assert_bit_exact(Q, Qo, what="golden image marginals")
 
 
 def test_image_crf_c2_small(pkg, ctx, oracle):
@@ -254,8 +254,8 @@ def test_image_crf_c2_small(pkg, ctx, oracle):
     crf.addPairwiseFromImage(W, H, 3.0, 3.0)
     crf.addPairwiseFromImage(W, H, 10.0, 60.0, img, 20.0)
     crf.inference(10, True)
-    assert_marginals(crf.getProbability(), Qo)
-    assert_map(crf.getMap(), mo, Qo)
+    assert_bit_exact(crf.getProbability(), Qo)
+    assert np.array_equal(crf.getMap(), mo)
     assert 0 < mo.sum() < W * H
     crf.close()
 
@@ -305,8 +305,8 @@ def test_frames_batch_parity(pkg, ctx, oracle):
             Qo, mo, Vo = oracle.slam_crf(fr.observs, fr.error, fr.kp2d, lab, en, prm_o)
             assert tuple(Vo) == tuple(dbg["V"][b]), b
             if fr.n:
-                assert_marginals(pr[o:o + fr.n], Qo, what="problem %d" % b)
-                assert_map(mp[o:o + fr.n], mo, Qo, what="problem %d" % b)
+                assert_bit_exact(pr[o:o + fr.n], Qo, what="problem %d" % b)
+                assert np.array_equal(mp[o:o + fr.n], mo)
             o += fr.n
     ab = F.algorithmic_bytes()
     assert ab["total"] > 0 and ab["per_iteration"] > 0
@@ -330,8 +330,8 @@ def test_frames_from_map_snapshot_c3_small(pkg, ctx, oracle):
     assert (lab != dbg["init_label"]).sum() <= 1
     Qo, mo, Vo = oracle.slam_crf(ob, er, snap.kp2d, dbg["init_label"], en, prm_o)
     assert tuple(Vo) == tuple(dbg["V"][0])
-    assert_marginals(pr, Qo)
-    assert_map(mp, mo, Qo)
+    assert_bit_exact(pr, Qo)
+    assert np.array_equal(mp, mo)
     assert 0 < mo.sum() < snap.n
     F.close()
 

@@ -22,6 +22,15 @@ def assert_marginals(Q, Qref, tol=REL_TOL, what=""):
     return float(r.max())
 
 
+def assert_bit_exact(a, ref, what=""):
+    """The CUDA path keeps the reference's operation order everywhere (splat rows in point order, blur and
+    slice associations, fast_exp), so floating-point outputs are expected to be BIT-identical."""
+    a, ref = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(ref, np.float32)
+    assert a.shape == ref.shape, f"{what}: shape {a.shape} vs {ref.shape}"
+    bad = int((a.view(np.int32) != ref.view(np.int32)).sum())
+    assert bad == 0, f"{what}: {bad} of {a.size} values differ in bits (max rel {rel_err(a, ref).max():.3e})"
+
+
 def assert_map(m, mref, Qref, what=""):
     """MAP labels identical except where the reference's top-2 marginals differ by < NEAR_TIE."""
     m, mref = np.asarray(m), np.asarray(mref)
