@@ -89,8 +89,10 @@ def concat_snapshots(snaps):
         kf.append(s.obs_kf + ko)
         eo += s.nnz
         ko += s.kf_pose.shape[0]
+    kf_ptr = np.zeros(len(snaps) + 1, dtype=np.int32)
+    np.cumsum([s.kf_pose.shape[0] for s in snaps], out=kf_ptr[1:])
     return dict(xyz=xyz, obs_ptr=np.concatenate(ptr).astype(np.int32), obs_kf=np.concatenate(kf).astype(np.int32),
-                obs_uv=obs_uv, kf_pose=kf_pose, kf_intr=kf_intr, kf_bounds=kf_bounds, kp2d=kp2d)
+                obs_uv=obs_uv, kf_pose=kf_pose, kf_intr=kf_intr, kf_bounds=kf_bounds, kp2d=kp2d, kf_ptr=kf_ptr)
 
 
 # ---------------------------------------------------------------------------------- clocks
@@ -264,7 +266,7 @@ def run_gpu_arm(args):
 
         def upload():
             F.set_map_inputs(host["xyz"], host["obs_ptr"], host["obs_kf"], host["obs_uv"], host["kf_pose"],
-                             host["kf_intr"], host["kf_bounds"], host["kp2d"])
+                             host["kf_intr"], host["kf_bounds"], host["kp2d"], host["kf_ptr"])
         h2d = sum(int(v.nbytes) for v in host.values())
     else:
         host = {}

@@ -171,10 +171,12 @@ void lccrf_frames_destroy(lccrf_frames *fr);
 int lccrf_frames_set_inputs(lccrf_frames *fr, const float *observs, const float *error, const float *depth,
                             const float *kp2d);
 /* alternatively derive observs/error/depth on the device from a map snapshot (lccrf_map_point_unary layout);
- * every point must have >= 1 observation (Tracking.cc:1858 drops the others before the CRF) */
+ * every point must have >= 1 observation (Tracking.cc:1858 drops the others before the CRF).
+ * kf_ptr (optional, [B+1]): problem b only references keyframes [kf_ptr[b], kf_ptr[b+1]) -- lets the unary kernel
+ * keep the current problem's keyframe table in shared memory; obs_kf stays a global keyframe index. */
 int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const int *obs_kf,
                                 const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
-                                const float *kf_bounds, const float *kp2d);
+                                const float *kf_bounds, const float *kp2d, const int *kf_ptr);
 /* device-resident run of the whole batch, asynchronous on the context's stream */
 int lccrf_frames_run(lccrf_frames *fr);
 /* copy results back (synchronises): map [NT] (0 = moving, 1 = static), prob [NT*2]; either may be NULL */

@@ -97,7 +97,7 @@ SYMBOLS = {
     "lccrf_frames_create": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(SlamParams), _vp, C.POINTER(_vp)]),
     "lccrf_frames_destroy": (None, [_vp]),
     "lccrf_frames_set_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
-    "lccrf_frames_set_map_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_set_map_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_run": (C.c_int, [_vp]),
     "lccrf_frames_get_outputs": (C.c_int, [_vp, _vp, _vp]),
     "lccrf_frames_get_debug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -372,13 +372,13 @@ class Frames:
         self._keep = a
         self.ctx._check(self.ctx.lib.lccrf_frames_set_inputs(self.h, *[_ptr(x) for x in a]))
 
-    def set_map_inputs(self, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d):
+    def set_map_inputs(self, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr=None):
         xyz, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d = (_arr(x, np.float32) for x in (xyz, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d))
-        obs_ptr, obs_kf = _arr(obs_ptr, np.int32), _arr(obs_kf, np.int32)
-        self._keep = [xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d]
+        obs_ptr, obs_kf, kf_ptr = _arr(obs_ptr, np.int32), _arr(obs_kf, np.int32), _arr(kf_ptr, np.int32)
+        self._keep = [xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr]
         self.ctx._check(self.ctx.lib.lccrf_frames_set_map_inputs(
             self.h, _ptr(xyz), _ptr(obs_ptr), _ptr(obs_kf), _ptr(obs_uv), kf_pose.shape[0], _ptr(kf_pose),
-            _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d)))
+            _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d), _ptr(kf_ptr)))
 
     def run(self):
         self.ctx._check(self.ctx.lib.lccrf_frames_run(self.h))

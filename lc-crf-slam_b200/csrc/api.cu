@@ -158,6 +158,8 @@ struct lccrf_frames {
     float *xyz = nullptr, *obs_uv = nullptr, *kf_pose = nullptr, *kf_intr = nullptr, *kf_bounds = nullptr;
     int *obs_ptr = nullptr, *obs_kf = nullptr;
     void *kf_packed = nullptr;
+    int *kf_ptr = nullptr;  // [B+1] keyframe slice of each problem (optional)
+    bool have_kf_ptr = false;
     int nKF = 0;
     long long nnz = 0, nnz_cap = 0;
     int nKF_cap = 0;
@@ -809,6 +811,7 @@ void lccrf_frames_destroy(lccrf_frames *fr) {
     dev_free(ctx, fr->obs_ptr);
     dev_free(ctx, fr->obs_kf);
     dev_free(ctx, fr->kf_packed);
+    dev_free(ctx, fr->kf_ptr);
     delete fr;
 }
 
@@ -837,7 +840,7 @@ int lccrf_frames_set_inputs(lccrf_frames *fr, const float *observs, const float 
 
 int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const int *obs_kf,
                                 const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
-                                const float *kf_bounds, const float *kp2d) {
+                                const float *kf_bounds, const float *kp2d, const int *kf_ptr) {
     if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
     Ctx *ctx = fr->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
@@ -888,6 +891,27 @@ int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *o
     fr->nKF = nKF;
     fr->nnz = nnz;
     cudaStream_t st = ctx->stream;
+    if (kf_ptr) {
+        if (kf_ptr[0] != 0 || kf_ptr[fr->b.B] != nKF) return fail(LCCRF_ERR_ARG, "kf_ptr must span [0, nKF]");
+        for (int i = 0; i < fr->b.B; i++)
+            if (kf_ptr[i + 1] < kf_ptr[i]) return fail(LCCRF_ERR_ARG, "kf_ptr must be non-decreasing");
+        if (!fr->kf_ptr) {
+            LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_ptr, (size_t)(fr->b.B + 1) * 4));
+            realloc_graph = true;
+        }
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_ptr, kf_ptr, (size_t)(fr->b.B + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (!fr->have_kf_ptr && fr->graph) {
+            cudaGraphExecDestroy(fr->graph);
+            fr->graph = nullptr;
+        }
+        fr->have_kf_ptr = true;
+    } else {
+        if (fr->have_kf_ptr && fr->graph) {
+            cudaGraphExecDestroy(fr->graph);
+            fr->graph = nullptr;
+        }
+        fr->have_kf_ptr = false;
+    }
     if (NT > 0) {
         LCCRF_CUDA(cudaMemcpyAsync(fr->xyz, xyz, (size_t)NT * 12, cudaMemcpyHostToDevice, st));
         LCCRF_CUDA(cudaMemcpyAsync(fr->obs_ptr, obs_ptr, (size_t)(NT + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -912,8 +936,9 @@ static int frames_enqueue(lccrf_frames *fr) {
     const lccrf_slam_params &prm = fr->prm;
     if (fr->from_map) {
         LCCRF_TRY(unary_pack_kf(ctx, fr->kf_packed, fr->kf_pose, fr->kf_intr, fr->kf_bounds, fr->nKF));
-        LCCRF_TRY(unary_map_points_packed(ctx, NT, fr->xyz, fr->obs_ptr, fr->obs_kf, fr->obs_uv, fr->kf_packed,
-                                          fr->observs, fr->error, fr->depth));
+        LCCRF_TRY(unary_map_points_packed(ctx, NT, fr->nKF, fr->xyz, fr->obs_ptr, fr->obs_kf, fr->obs_uv, fr->kf_packed,
+                                          fr->observs, fr->error, fr->depth, b.prob_ptr,
+                                          fr->have_kf_ptr ? fr->kf_ptr : nullptr, b.B));
     }
     // RroughClassify -> setUnaryEnergyFromLabel   (Tracking.cc:1871,1921)
     LCCRF_TRY(unary_classify(ctx, NT, fr->observs, fr->error, fr->depth, nullptr, prm, fr->label));

@@ -19,7 +19,6 @@ namespace lccrf {
 namespace {
 
 constexpr int kFillThreads = 1024;
-constexpr int kFillWarps = kFillThreads / 32;
 constexpr int kCursorSmemInts = 14336;  // 56 KB of shared cursors: lattices up to 14k vertices per problem
 
 struct CsrParams {
@@ -47,18 +46,25 @@ __global__ void __launch_bounds__(kThreads) k_csr_zero(CsrParams p) {
     for (int v = threadIdx.x; v < Vb; v += kThreads) row[v] = 0;
 }
 
-__global__ void __launch_bounds__(kThreads) k_csr_count(CsrParams p) {
+__global__ void __launch_bounds__(kFillThreads) k_csr_count(CsrParams p) {
     const int g = blockIdx.x;
     const int b = __ldg(p.chunk_prob + g);
     const int vb = __ldg(p.vbase + b);
     int *row = p.tbl + __ldg(p.chunk_tbl + g);
     const int s0 = __ldg(p.chunk_s0 + g), s1 = __ldg(p.chunk_s1 + g);
     const unsigned lane = threadIdx.x & 31;
-    for (int base = s0; base < s1; base += kThreads) {
-        const int s = base + threadIdx.x;
-        const int v = s < s1 ? __ldg(p.offset + s) - vb : -1;
-        const unsigned grp = __match_any_sync(0xffffffffu, v);
-        if (v >= 0 && (__ffs(grp) - 1) == (int)lane) atomicAdd(row + v, __popc(grp));
+    for (int base = s0; base < s1; base += 4 * kFillThreads) {
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s = base + j * kFillThreads + threadIdx.x;
+            v[j] = s < s1 ? __ldg(p.offset + s) - vb : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned grp = __match_any_sync(0xffffffffu, v[j]);
+            if (v[j] >= 0 && (__ffs(grp) - 1) == (int)lane) atomicAdd(row + v[j], __popc(grp));
+        }
     }
 }
 
@@ -157,58 +163,89 @@ __global__ void __launch_bounds__(1024) k_scan_add(int *x, const int *n_ptr, con
     }
 }
 
-// every chunk walks its entries in scan order, 1024 per round; warps take turns so that the per-vertex
-// cursors advance in entry order; inside a warp equal vertices are ranked by lane (= entry order)
-template <bool SMEM_CURSORS>
-__global__ void __launch_bounds__(kFillThreads) k_csr_fill(CsrParams p) {
+// Stable placement.  A CTA owns one chunk; its kFillWarps warps own consecutive sub-chunks.
+//   HIER (lattice of the problem has <= kHierV vertices): per-(warp, vertex) counts in shared memory, prefix over
+//        the warps, then every warp walks its own sub-chunk in entry order with its own cursors -- no hand-offs.
+//   otherwise: warp 0 walks the whole chunk in entry order with one cursor row (shared if it fits, else global).
+// Inside a 32-entry group equal vertices are ranked by lane (= entry order) with match.any.
+constexpr int kFillWarpsH = 8;
+constexpr int kHierV = kCursorSmemInts / kFillWarpsH;  // 1792
+
+template <int MODE>  // 0: hierarchical shared, 1: single warp + shared cursors, 2: single warp + global cursors
+__device__ __forceinline__ void fill_walk(const CsrParams &p, int vb, int a, int z, int *cur_row, unsigned lane) {
+    for (int base = a; base < z; base += 32) {
+        const int s = base + (int)lane;
+        int v = -1, rp = 0;
+        float w = 0.f;
+        if (s < z) {
+            const int gv = __ldg(p.offset + s);
+            w = __ldg(p.bary + s);
+            rp = __ldg(p.row_len + gv);  // row_ptr after the scan
+            v = gv - vb;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, v);
+        const int leader = __ffs(grp) - 1;
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        int cur = 0;
+        if (v >= 0 && (int)lane == leader) {
+            if (MODE == 2) {
+                cur = ((volatile int *)cur_row)[v];
+                ((volatile int *)cur_row)[v] = cur + __popc(grp);
+            } else {
+                cur = cur_row[v];
+                cur_row[v] = cur + __popc(grp);
+            }
+        }
+        __syncwarp();  // the next group may hit the same vertex
+        cur = __shfl_sync(0xffffffffu, cur, leader);
+        if (v >= 0) p.ent[rp + cur + rank] = make_int2(s / p.D, __float_as_int(w));
+    }
+}
+
+__global__ void __launch_bounds__(kFillWarpsH * 32) k_csr_fill(CsrParams p) {
     extern __shared__ int s_cur[];
-    __shared__ volatile int turn;
     const int g = blockIdx.x;
     const int b = __ldg(p.chunk_prob + g);
     const int vb = __ldg(p.vbase + b);
     const int Vb = __ldg(p.vbase + b + 1) - vb;
     int *row = p.tbl + __ldg(p.chunk_tbl + g);
-    if (SMEM_CURSORS != (Vb <= kCursorSmemInts)) return;  // the other instantiation handles this chunk
     const int s0 = __ldg(p.chunk_s0 + g), s1 = __ldg(p.chunk_s1 + g);
     const unsigned lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
-    if (SMEM_CURSORS)
-        for (int v = threadIdx.x; v < Vb; v += kFillThreads) s_cur[v] = row[v];
-    if (threadIdx.x == 0) turn = 0;
-    __syncthreads();
-    int round = 0;
-    for (int base = s0; base < s1; base += kFillThreads, round++) {
-        const int s = base + threadIdx.x;
-        const bool valid = s < s1;
-        int v = -1, rp = 0;
-        float w = 0.f;
-        if (valid) {
-            v = __ldg(p.offset + s);
-            w = __ldg(p.bary + s);
-            rp = __ldg(p.row_len + v);  // row_ptr after the scan
-            v -= vb;
+    if (Vb <= kHierV) {
+        // sub-chunk of warp w: [s0 + w*sub, s0 + (w+1)*sub), sub a multiple of 32
+        const int sub = ((s1 - s0 + kFillWarpsH - 1) / kFillWarpsH + 31) & ~31;
+        const int a = min(s0 + wid * sub, s1), z = min(a + sub, s1);
+        int *mine = s_cur + wid * Vb;
+        for (int v = threadIdx.x; v < kFillWarpsH * Vb; v += kFillWarpsH * 32) s_cur[v] = 0;
+        __syncthreads();
+        for (int base = a; base < z; base += 32) {  // counts of this warp's sub-chunk
+            const int s = base + (int)lane;
+            const int v = s < z ? __ldg(p.offset + s) - vb : -1;
+            const unsigned grp = __match_any_sync(0xffffffffu, v);
+            if (v >= 0 && (__ffs(grp) - 1) == (int)lane) mine[v] += __popc(grp);
+            __syncwarp();
         }
-        const unsigned grp = __match_any_sync(0xffffffffu, v);
-        const int leader = __ffs(grp) - 1;
-        const int rank = __popc(grp & ((1u << lane) - 1u));
-        const int my_turn = round * kFillWarps + wid;
-        while (turn != my_turn) { /* spin: warps of this CTA commit in order */ }
-        __threadfence_block();
-        int cur = 0;
-        if (valid && (int)lane == leader) {
-            if (SMEM_CURSORS) {
-                cur = s_cur[v];
-                s_cur[v] = cur + __popc(grp);
-            } else {
-                cur = ((volatile int *)row)[v];
-                ((volatile int *)row)[v] = cur + __popc(grp);
+        __syncthreads();
+        for (int v = threadIdx.x; v < Vb; v += kFillWarpsH * 32) {  // exclusive prefix over the warps + chunk start
+            int run = row[v];
+#pragma unroll
+            for (int w = 0; w < kFillWarpsH; w++) {
+                const int n = s_cur[w * Vb + v];
+                s_cur[w * Vb + v] = run;
+                run += n;
             }
         }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) turn = my_turn + 1;
-        cur = __shfl_sync(0xffffffffu, cur, leader);
-        if (valid) p.ent[rp + cur + rank] = make_int2(s / p.D, __float_as_int(w));
+        __syncthreads();
+        fill_walk<0>(p, vb, a, z, mine, lane);
+    } else if (wid == 0) {
+        if (Vb <= kCursorSmemInts) {
+            for (int v = (int)lane; v < Vb; v += 32) s_cur[v] = row[v];
+            __syncwarp();
+            fill_walk<1>(p, vb, s0, s1, s_cur, lane);
+        } else {
+            fill_walk<2>(p, vb, s0, s1, row, lane);
+        }
     }
 }
 
@@ -307,7 +344,7 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     const int *vt = ls->vbase + ls->B;
     if (p.G > 0) {
         { LCCRF_KERNEL(ctx, "k_csr_zero"); k_csr_zero<<<p.G, kThreads, 0, st>>>(p); }
-        { LCCRF_KERNEL(ctx, "k_csr_count"); k_csr_count<<<p.G, kThreads, 0, st>>>(p); }
+        { LCCRF_KERNEL(ctx, "k_csr_count"); k_csr_count<<<p.G, kFillThreads, 0, st>>>(p); }
     }
     const int vgrid = persistent_grid((long long)ls->Vcap, kThreads, 4);
     { LCCRF_KERNEL(ctx, "k_csr_prefix"); k_csr_prefix<<<vgrid, kThreads, 0, st>>>(p, b.B); }
@@ -318,12 +355,11 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     if (p.G > 0) {
         static bool attr_set = false;
         if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_csr_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            LCCRF_CUDA(cudaFuncSetAttribute(k_csr_fill, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             kCursorSmemInts * (int)sizeof(int)));
             attr_set = true;
         }
-        { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<true><<<p.G, kFillThreads, kCursorSmemInts * sizeof(int), st>>>(p); }
-        { LCCRF_KERNEL(ctx, "k_csr_fill_g"); k_csr_fill<false><<<p.G, kFillThreads, 0, st>>>(p); }
+        { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<<<p.G, kFillWarpsH * 32, kCursorSmemInts * sizeof(int), st>>>(p); }
     }
     LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 2 * sizeof(int), st));
     { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_med, ls->row_list_long, ls->row_counts); }

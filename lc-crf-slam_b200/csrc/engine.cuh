@@ -44,12 +44,13 @@ struct LatticeSet {
     int *row_counts = nullptr;                              // [2] device: #medium, #long
     // filter workspace
     float *valA = nullptr, *valB = nullptr;  // [Vcap*Lmax] blur ping-pong
+    float *prod = nullptr;                   // [NT*D*Lmax] bary*value of every entry, in vertex-sorted order
     int Lmax = 0;
 };
 
-constexpr int kCsrChunkPoints = 8192;
+constexpr int kCsrChunkPoints = 4096;
 constexpr int kMedRow = 96;     // rows at least this long leave the lane-sequential kernel
-constexpr int kLongRow = 3072;  // rows at least this long get a whole CTA  // points per chunk of the parallel stable counting sort
+constexpr int kLongRow = 1024;  // rows at least this long get a whole CTA  // points per chunk of the parallel stable counting sort
 
 struct Batch {
     Ctx *ctx = nullptr;
@@ -144,14 +145,17 @@ int mf_potts_apply(Ctx *ctx, const Batch &b, LatticeSet *ls, float *out, const f
 int mf_apply_fused(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *cur, float *next, const float *unary,
                    bool first);
 int launch_axpy_norm(Ctx *ctx, float *out, const float *tmp, const float *norm, float w, int NT, int L);
+// fused point pass for L == 2: slice of every lattice + Potts apply + softmax (+ MAP) in one kernel
+int mf_point_pass_l2(Ctx *ctx, Batch &b, const float *const *values, float relax, bool with_map);
 // features (unary.cu)
 int feat_div2(Ctx *ctx, float *feat, const float *a, int stride_a, float sa, const float *b, int stride_b,
               float sb, int N);
 int feat_image(Ctx *ctx, float *feat, int W, int H, int F, float posdev, const void *img_dev, int is_u8,
                float featuredev);
 int unary_pack_kf(Ctx *ctx, void *kf_packed /*nKF*80 B*/, const float *pose, const float *intr, const float *bnd, int nKF);
-int unary_map_points_packed(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
-                            const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth);
+int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                            const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
+                            const int *prob_ptr, const int *kf_ptr, int B);
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                      const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
                      const float *kf_bounds, float *observs, float *error, float *depth);

@@ -17,43 +17,118 @@ namespace lccrf {
 namespace {
 
 // ---------------------------------------------------------------- splat
-// Segmented reduction over the vertex-sorted entries (csr.cu).  A lane owns one (vertex row, label) pair
-// and walks the row front to back: values[v][l] = (((0 + w0*x0) + w1*x1) + ...) in point order, every
-// product and sum individually rounded -- the reference's splat loop (:653-661) bit for bit.  32/LP rows
-// share a warp (LP = label count rounded up to a power of two), the labels of a row sit in adjacent lanes
-// so the gathers of in[point][0..L) coalesce.
+// Segmented reduction over the vertex-sorted entries (csr.cu).  values[v][l] = (((0 + w0*x0) + w1*x1) + ...)
+// over the row of v in point order, every product and sum individually rounded -- the reference's splat loop
+// (:653-661) bit for bit.  Three kernels:
+//   k_products      prod[e][l] = bary[e] * in[point[e]][l] for every entry, in vertex-sorted order: one fully
+//                   parallel, coalesced pass (the only gather of the splat)
+//   k_splat_staged  rows shorter than kLongRow: a warp owns G = 32/LP consecutive rows (LP = label count rounded up
+//                   to a power of two) = one contiguous slab of prod; the slab is copied to shared memory with wide
+//                   coalesced loads, then lane (row, label) adds its row front to back -- ordered, no DRAM latency
+//                   in the dependent chain
+//   k_splat_scan    rows of kLongRow entries and more: exact parallel scan (below)
+template <int LT>
+__global__ void __launch_bounds__(kThreads)
+k_products(const int2 *__restrict__ ent, const float *__restrict__ in, float *__restrict__ prod, long long E, int L_rt) {
+    const int L = LT > 0 ? LT : L_rt;
+    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    const int2 t = __ldg(ent + e);
+    const float w = __int_as_float(t.y);
+    if (LT == 2) {
+        const float2 x = __ldg((const float2 *)in + t.x);
+        ((float2 *)prod)[e] = make_float2(__fmul_rn(w, x.x), __fmul_rn(w, x.y));
+    } else if (LT == 1) {
+        prod[e] = __fmul_rn(w, __ldg(in + t.x));
+    } else {
+        for (int l = 0; l < L; l++) prod[e * L + l] = __fmul_rn(w, __ldg(in + (size_t)t.x * L + l));
+    }
+}
+
+constexpr int kStageFloats = 2048;  // per warp
+__device__ __forceinline__ int spad(int idx) { return idx + (idx >> 5); }
+
 template <int LP>
 __global__ void __launch_bounds__(kThreads)
-k_splat(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-        float *__restrict__ val, const int *__restrict__ vtotal, int L, int l0) {
+k_splat_staged(const int *__restrict__ row_ptr, const float *__restrict__ prod, float *__restrict__ val,
+               const int *__restrict__ vtotal, int L) {
     constexpr int G = 32 / LP;
+    extern __shared__ float s_all[];
     const int V = __ldg(vtotal);
-    const int lane = threadIdx.x & 31;
-    const int g = lane / LP, l = l0 + lane % LP;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *s_prod = s_all + (size_t)wid * (kStageFloats + kStageFloats / 32);
+    const int g = lane / LP;
+    const int cap = (kStageFloats - 4) / L;  // entries per staged chunk (4 floats of alignment slack)
     const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kThreads) >> 5;
-    for (long long rb = (long long)warp * G; rb < V; rb += (long long)nwarps * G) {
-        const int v = (int)rb + g;
-        const bool act = v < V && l < L;
-        int e = act ? __ldg(row_ptr + v) : 0;
-        int e1 = act ? __ldg(row_ptr + v + 1) : 0;
-        const bool mine = e1 - e < kMedRow;  // longer rows belong to k_splat_scan
-        if (!mine) e1 = e;
-        float acc = 0.0f;
-        for (; e + 4 <= e1; e += 4) {  // independent loads first, then the ordered chain
-            const int2 t0 = __ldg(ent + e), t1 = __ldg(ent + e + 1), t2 = __ldg(ent + e + 2), t3 = __ldg(ent + e + 3);
-            const float x0 = __ldg(in + (size_t)t0.x * L + l), x1 = __ldg(in + (size_t)t1.x * L + l);
-            const float x2 = __ldg(in + (size_t)t2.x * L + l), x3 = __ldg(in + (size_t)t3.x * L + l);
-            acc = __fadd_rn(acc, __fmul_rn(__int_as_float(t0.y), x0));
-            acc = __fadd_rn(acc, __fmul_rn(__int_as_float(t1.y), x1));
-            acc = __fadd_rn(acc, __fmul_rn(__int_as_float(t2.y), x2));
-            acc = __fadd_rn(acc, __fmul_rn(__int_as_float(t3.y), x3));
+    for (int l0 = 0; l0 < L; l0 += LP) {  // L > 32: several label passes over the same rows
+        const int l = l0 + lane % LP;
+        for (long long rb = (long long)warp * G; rb < V; rb += (long long)nwarps * G) {
+            const int v = (int)rb + g;
+            const int rs = v < V ? __ldg(row_ptr + v) : 0;
+            const int re = v < V ? __ldg(row_ptr + v + 1) : rs;
+            const bool mine = v < V && l < L && (re - rs) < kLongRow;  // longer rows belong to k_splat_scan
+            const int E0 = __shfl_sync(0xffffffffu, rs, 0);
+            const int E1 = __ldg(row_ptr + min((int)rb + G, V));
+            float acc = 0.0f;
+            int gcur = 0;  // row of the group that contains cb (moves forward only)
+            for (int cb = E0; cb < E1;) {
+                int rs_c, re_c;
+                for (;;) {
+                    rs_c = __shfl_sync(0xffffffffu, rs, gcur * LP);
+                    re_c = __shfl_sync(0xffffffffu, re, gcur * LP);
+                    if (re_c > cb || gcur == G - 1) break;
+                    gcur++;
+                }
+                if (re_c - rs_c >= kLongRow && cb >= rs_c && cb < re_c) {  // inside a long row: jump over it
+                    cb = re_c;
+                    continue;
+                }
+                const int ce = min(cb + cap, E1);
+                // phase 1: the slab prod[cb*L, ce*L) -> shared memory with 128-bit loads from the enclosing
+                // 16-byte aligned window, all lanes, every load independent (one memory round trip per chunk)
+                const long long f0 = (long long)cb * L;
+                const long long a0 = f0 & ~3ll;
+                const int shift = (int)(f0 - a0);
+                const int nq = ((ce - cb) * L + shift + 3) >> 2;  // float4 count (prod is padded by 4 floats)
+                {   // nq <= 512: at most 16 float4 per lane, all loaded before the first shared store
+                    float4 x[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int q = lane + 32 * j;
+                        if (q < nq) x[j] = __ldg((const float4 *)(prod + a0) + q);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int q = lane + 32 * j;
+                        if (q < nq) {
+                            const int o = spad(q * 4);
+                            s_prod[o] = x[j].x;
+                            s_prod[o + 1] = x[j].y;
+                            s_prod[o + 2] = x[j].z;
+                            s_prod[o + 3] = x[j].w;
+                        }
+                    }
+                }
+                __syncwarp();
+                // phase 2: ordered accumulation
+                if (mine) {
+                    const int a = max(rs, cb), z = min(re, ce);
+                    int e = a;
+                    for (; e + 8 <= z; e += 8) {  // independent shared loads first, then the ordered chain
+                        float x[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) x[q] = s_prod[spad((e + q - cb) * L + l + shift)];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, x[q]);
+                    }
+                    for (; e < z; e++) acc = __fadd_rn(acc, s_prod[spad((e - cb) * L + l + shift)]);
+                }
+                __syncwarp();
+                cb = ce;
+            }
+            if (mine) val[(size_t)v * L + l] = acc;
         }
-        for (; e < e1; e++) {
-            const int2 t = __ldg(ent + e);
-            acc = __fadd_rn(acc, __fmul_rn(__int_as_float(t.y), __ldg(in + (size_t)t.x * L + l)));
-        }
-        if (act && mine) val[(size_t)v * L + l] = acc;
     }
 }
 
@@ -87,20 +162,26 @@ struct ScanShared {
 // IT consecutive entries of each chunk of NW*32*IT.  All threads of the group call this with identical arguments;
 // tid = thread index inside the group.  Returns the same value in every thread.
 template <int NW, int IT>
-__device__ float row_sum_exact(const int2 *__restrict__ ent, int e0, int e1, const float *__restrict__ in, int L, int l,
-                               int tid, ScanShared<NW> &sh) {
+__device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, int L, int l, int tid, ScanShared<NW> &sh) {
     constexpr int T = NW * 32, CH = T * IT;
     const int lane = tid & 31, wid = tid >> 5;
     float s = 0.0f;
+    float cn[IT];  // next chunk's contributions, loaded while the current chunk is being scanned
+#pragma unroll
+    for (int k = 0; k < IT; k++) {
+        cn[k] = 0.0f;
+        if (e0 + tid * IT + k < e1) cn[k] = __ldg(prod + (size_t)(e0 + tid * IT + k) * L + l);
+    }
     for (int cb = e0; cb < e1; cb += CH) {
         float c[IT];
-        const int base = cb + tid * IT;
 #pragma unroll
-        for (int k = 0; k < IT; k++) {
-            c[k] = 0.0f;
-            if (base + k < e1) {
-                const int2 t = __ldg(ent + base + k);
-                c[k] = __fmul_rn(__int_as_float(t.y), __ldg(in + (size_t)t.x * L + l));
+        for (int k = 0; k < IT; k++) c[k] = cn[k];
+        {
+            const int nbase = cb + CH + tid * IT;
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                cn[k] = 0.0f;
+                if (nbase + k < e1) cn[k] = __ldg(prod + (size_t)(nbase + k) * L + l);
             }
         }
         const int n_chunk = min(CH, e1 - cb);
@@ -158,22 +239,25 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, int e0, int e1, con
 #pragma unroll
             for (int k = 0; k < IT; k++) {
                 if (li0 + k >= st && li0 + k < n_chunk) {
-                    ScanPair a;
                     const float q = __fmul_rn(c[k], inv_u);
+                    int ni;
+                    float fr = 0.0f;
                     if (!(fabsf(q) < 16777216.0f)) {  // also NaN / inf: forces "leaves the binade"
-                        a.a0 = a.a1 = q > 0.0f ? (1 << 24) : -(1 << 24);
+                        ni = q > 0.0f ? (1 << 24) : -(1 << 24);
                     } else {
-                        const float nf = floorf(q);
-                        const float fr = __fsub_rn(q, nf);  // exact, in [0, 1)
-                        const int ni = (int)nf;
-                        if (fr == 0.5f) {
-                            a.a0 = ni + (ni & 1);
-                            a.a1 = ni + ((ni + 1) & 1);
-                        } else {
-                            a.a0 = a.a1 = ni + (fr > 0.5f ? 1 : 0);
-                        }
+                        ni = __float2int_rd(q);
+                        fr = __fsub_rn(q, (float)ni);  // exact, in [0, 1)
                     }
-                    tot = scan_combine(tot, a);
+                    if (fr != 0.5f) {  // common case: the same increment for either parity
+                        const int inc1 = ni + (fr > 0.5f ? 1 : 0);
+                        tot.a0 += inc1;
+                        tot.a1 += inc1;
+                    } else {           // tie: round half to even
+                        ScanPair a;
+                        a.a0 = ni + (ni & 1);
+                        a.a1 = ni + ((ni + 1) & 1);
+                        tot = scan_combine(tot, a);
+                    }
                     hi0 = max(hi0, tot.a0);
                     lo0 = min(lo0, tot.a0);
                     hi1 = max(hi1, tot.a1);
@@ -257,8 +341,8 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, int e0, int e1, con
 // one group (warp or CTA) per (row, label) task; rows come from a device-side list
 template <int NW, int IT>
 __global__ void __launch_bounds__(NW * 32 > kThreads ? NW * 32 : kThreads)
-k_splat_scan(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-             float *__restrict__ val, const int *__restrict__ list, const int *__restrict__ count, int L) {
+k_splat_scan(const int *__restrict__ row_ptr, const float *__restrict__ prod, float *__restrict__ val,
+             const int *__restrict__ list, const int *__restrict__ count, int L) {
     constexpr int GROUPS = NW == 1 ? kThreads / 32 : 1;  // groups per CTA
     __shared__ ScanShared<NW> sh[GROUPS];
     const long long n = (long long)__ldg(count) * L;
@@ -267,7 +351,7 @@ k_splat_scan(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, cons
     for (long long k = (long long)blockIdx.x * GROUPS + gid; k < n; k += (long long)gridDim.x * GROUPS) {
         const int v = __ldg(list + (int)(k / L)), l = (int)(k % L);
         const int e0 = __ldg(row_ptr + v), e1 = __ldg(row_ptr + v + 1);
-        const float s = row_sum_exact<NW, IT>(ent, e0, e1, in, L, l, tid, sh[gid]);
+        const float s = row_sum_exact<NW, IT>(prod, e0, e1, L, l, tid, sh[gid]);
         if (tid == 0) val[(size_t)v * L + l] = s;
         if (NW > 1) __syncthreads();
     }
@@ -287,6 +371,57 @@ k_blur(const int2 *__restrict__ nbr_j, const float *__restrict__ src, float *__r
         const float a = nb.x >= 0 ? __ldg(src + (size_t)nb.x * L + l) : 0.f;
         const float b = nb.y >= 0 ? __ldg(src + (size_t)nb.y * L + l) : 0.f;
         dst[t] = __fadd_rn(o, __fmul_rn(0.5f, __fadd_rn(a, b)));
+    }
+}
+
+// all D blur passes of one problem inside one CTA (shared-memory ping-pong when the lattice fits, global otherwise):
+// replaces D launch-bound passes when a batch holds several problems or the lattice is small
+constexpr int kBlurFusedFloats = 24576;  // 96 KB
+__global__ void __launch_bounds__(1024)
+k_blur_fused(const int2 *__restrict__ nbr, int Vcap, const int *__restrict__ vbase, float *__restrict__ A,
+             float *__restrict__ B, int L, int D) {
+    extern __shared__ float s_blur[];
+    const int b = blockIdx.x;
+    const int vb = __ldg(vbase + b);
+    const int n = (__ldg(vbase + b + 1) - vb) * L;
+    float *gA = A + (size_t)vb * L, *gB = B + (size_t)vb * L;
+    if (2 * n <= kBlurFusedFloats) {
+        float *src = s_blur, *dst = s_blur + n;
+        for (int t = threadIdx.x; t < n; t += 1024) src[t] = gA[t];
+        __syncthreads();
+        for (int j = 0; j < D; j++) {
+            const int2 *nb_j = nbr + (size_t)j * Vcap + vb;
+            for (int t = threadIdx.x; t < n; t += 1024) {
+                const int v = t / L, l = t - v * L;
+                const int2 nb = __ldg(nb_j + v);
+                const float a = nb.x >= 0 ? src[(nb.x - vb) * L + l] : 0.f;
+                const float c = nb.y >= 0 ? src[(nb.y - vb) * L + l] : 0.f;
+                dst[t] = __fadd_rn(src[t], __fmul_rn(0.5f, __fadd_rn(a, c)));
+            }
+            __syncthreads();
+            float *tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+        for (int t = threadIdx.x; t < n; t += 1024) gB[t] = src[t];
+    } else {
+        float *src = gA, *dst = gB;
+        for (int j = 0; j < D; j++) {
+            const int2 *nb_j = nbr + (size_t)j * Vcap + vb;
+            for (int t = threadIdx.x; t < n; t += 1024) {
+                const int v = t / L, l = t - v * L;
+                const int2 nb = __ldg(nb_j + v);
+                const float a = nb.x >= 0 ? src[(size_t)(nb.x - vb) * L + l] : 0.f;
+                const float c = nb.y >= 0 ? src[(size_t)(nb.y - vb) * L + l] : 0.f;
+                dst[t] = __fadd_rn(src[t], __fmul_rn(0.5f, __fadd_rn(a, c)));
+            }
+            __syncthreads();
+            float *tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+        if (src != gB)
+            for (int t = threadIdx.x; t < n; t += 1024) gB[t] = src[t];
     }
 }
 
@@ -332,33 +467,58 @@ __global__ void k_fill(float *__restrict__ x, float v, int n) {
 int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_dev, int L, const float **values_out) {
     cudaStream_t st = ctx->stream;
     if (L > ls->Lmax) return fail(LCCRF_ERR_ARG, "filter: L exceeds the lattice workspace");
-    (void)b;
     const int D = ls->D;
     const int *vt = ls->vbase + ls->B;
     float *src = ls->valA, *dst = ls->valB;
+    const long long E = (long long)b.NT * D;
+    if (E > 0) {
+        LCCRF_KERNEL(ctx, "k_products");
+        const int grid = cdiv(E, kThreads);
+        if (L == 1) k_products<1><<<grid, kThreads, 0, st>>>(ls->csr_ent, in_dev, ls->prod, E, L);
+        else if (L == 2) k_products<2><<<grid, kThreads, 0, st>>>(ls->csr_ent, in_dev, ls->prod, E, L);
+        else k_products<0><<<grid, kThreads, 0, st>>>(ls->csr_ent, in_dev, ls->prod, E, L);
+    }
     {
         int LP = 1;
         while (LP < L && LP < 32) LP <<= 1;
-        const int grid = persistent_grid((long long)ls->Vcap * LP, kThreads, 8);
-        for (int l0 = 0; l0 < L; l0 += 32) {
-            LCCRF_KERNEL(ctx, "k_splat");
-            switch (LP) {
-                case 1: k_splat<1><<<grid, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, vt, L, l0); break;
-                case 2: k_splat<2><<<grid, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, vt, L, l0); break;
-                case 4: k_splat<4><<<grid, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, vt, L, l0); break;
-                case 8: k_splat<8><<<grid, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, vt, L, l0); break;
-                case 16: k_splat<16><<<grid, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, vt, L, l0); break;
-                default: k_splat<32><<<grid, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, vt, L, l0); break;
-            }
+        const int grid = persistent_grid((long long)ls->Vcap * LP, kThreads, 3);
+        const size_t smem = (size_t)(kThreads / 32) * (kStageFloats + kStageFloats / 32) * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        LCCRF_KERNEL(ctx, "k_splat_staged");
+        switch (LP) {
+            case 1: k_splat_staged<1><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
+            case 2: k_splat_staged<2><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
+            case 4: k_splat_staged<4><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
+            case 8: k_splat_staged<8><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
+            case 16: k_splat_staged<16><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
+            default: k_splat_staged<32><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
         }
     }
-    {   // medium rows: one warp each; long rows: one CTA each (exact ordered scan)
-        LCCRF_KERNEL(ctx, "k_splat_scan_warp");
-        k_splat_scan<1, 4><<<kNumSMs * 8, kThreads, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_med, ls->row_counts, L);
-    }
-    {
+    {   // long rows: one CTA each, exact ordered scan
         LCCRF_KERNEL(ctx, "k_splat_scan_cta");
-        k_splat_scan<32, 8><<<kNumSMs * 2, 1024, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts + 1, L);
+        k_splat_scan<8, 8><<<kNumSMs * 8, kThreads, 0, st>>>(ls->row_ptr, ls->prod, src, ls->row_list_long, ls->row_counts + 1, L);
+    }
+    if (b.B >= 2 || b.maxN <= 32768) {  // one CTA per problem runs all D passes
+        static bool attr_set = false;
+        if (!attr_set) {
+            LCCRF_CUDA(cudaFuncSetAttribute(k_blur_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kBlurFusedFloats * (int)sizeof(float)));
+            attr_set = true;
+        }
+        LCCRF_KERNEL(ctx, "k_blur_fused");
+        k_blur_fused<<<b.B, 1024, kBlurFusedFloats * sizeof(float), st>>>(ls->nbr, ls->Vcap, ls->vbase, src, dst, L, D);
+        *values_out = dst;
+        LCCRF_CUDA(cudaGetLastError());
+        return LCCRF_OK;
     }
     const int bgrid = persistent_grid((long long)ls->Vcap * L, kThreads, 8);
     for (int j = 0; j < D; j++) {

@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(kThreads) k_embed(BuildParams p) {
             uint64_t w = word_level<d>(kc, lev, slot - base);
             slot = hash_insert(p.key[lev], base, mask, w);
         }
-        atomicMin(p.first + slot, ip * D + r);
+        // most points find an earlier first occurrence already recorded: skip the atomic (hot vertices
+        // would otherwise serialise tens of thousands of atomicMin on one address)
+        if (__ldcg(p.first + slot) > ip * D + r) atomicMin(p.first + slot, ip * D + r);
         es[r] = slot;
         if (!phantom) p.bary[(size_t)i * D + r] = bc[r];
     }
@@ -279,20 +281,23 @@ __global__ void __launch_bounds__(kThreads) k_assign(BuildParams p) {
     }
 }
 
-// vbase[b] = number of first occurrences before problem b's first scan position
+// vbase[b] = number of first occurrences before problem b's first scan position; one warp per problem
 template <int D>
-__global__ void k_vbase(BuildParams p) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kThreads) k_vbase(BuildParams p) {
+    const int b = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (b >= p.B) return;
     const int S = (p.NT + p.B) * D;
     const int sb = (__ldg(p.prob_ptr + b) + b) * D;
     const int blk = sb / kThreads;
-    int cnt = __ldg(p.blk_cnt + blk);
-    for (int s = blk * kThreads; s < sb; s++) {
+    int cnt = 0;
+    for (int s = blk * kThreads + lane; s < sb; s += 32) {
         int slot;
         cnt += is_first(p, s, S, slot) ? 1 : 0;
     }
-    p.vbase[b] = cnt;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) p.vbase[b] = __ldg(p.blk_cnt + blk) + cnt;
 }
 
 template <int D>
@@ -371,7 +376,7 @@ int launch_build(Ctx *ctx, const BuildParams &p) {
     { LCCRF_KERNEL(ctx, "k_mark"); k_mark<D><<<nblk, kThreads, 0, st>>>(p); }
     { LCCRF_KERNEL(ctx, "k_scan_blocks"); k_scan_blocks<<<1, 1024, 0, st>>>(p.blk_cnt, nblk, p.vbase + p.B); }
     { LCCRF_KERNEL(ctx, "k_assign"); k_assign<D><<<nblk, kThreads, 0, st>>>(p); }
-    { LCCRF_KERNEL(ctx, "k_vbase"); k_vbase<D><<<cdiv(p.B, 128), 128, 0, st>>>(p); }
+    { LCCRF_KERNEL(ctx, "k_vbase"); k_vbase<D><<<cdiv((long long)p.B * 32, kThreads), kThreads, 0, st>>>(p); }
     if (p.NT > 0) {
         { LCCRF_KERNEL(ctx, "k_offsets"); k_offsets<D><<<cdiv(p.NT, kThreads), kThreads, 0, st>>>(p); }
     }
@@ -410,6 +415,7 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
     if (Lmax > 0) {
         rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * Lmax * sizeof(float));
         rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * Lmax * sizeof(float));
+        rc |= dev_alloc(ctx, (void **)&ls->prod, (nent * Lmax + 8) * sizeof(float));
     }
     rc |= dev_alloc(ctx, (void **)&ls->tab_base, (size_t)(b.B + 1) * sizeof(int));
     if (rc != LCCRF_OK) {
@@ -453,11 +459,13 @@ int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     if (L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "label count exceeds LCCRF_MAX_L");
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
-    ls->valA = ls->valB = nullptr;
+    dev_free(ctx, ls->prod);
+    ls->valA = ls->valB = ls->prod = nullptr;
     ls->Lmax = 0;
     int rc = LCCRF_OK;
     rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * L * sizeof(float));
     rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * L * sizeof(float));
+    rc |= dev_alloc(ctx, (void **)&ls->prod, ((size_t)(ls->NT > 0 ? ls->NT : 1) * ls->D * L + 8) * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
     ls->Lmax = L;
     return LCCRF_OK;
@@ -474,6 +482,7 @@ void lattice_set_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->norm);
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
+    dev_free(ctx, ls->prod);
     dev_free(ctx, ls->tab_base);
     csr_destroy(ctx, ls);
     delete ls;

@@ -131,7 +131,82 @@ k_axpy_norm(float *__restrict__ out, const float *__restrict__ tmp, const float 
     out[t] = __fadd_rn(out[t], __fmul_rn(__fmul_rn(w, norm[i]), tmp[t]));  // pairwise3d.h:75-77
 }
 
+// ---- fused point pass, L == 2: for every point, slice all K lattices (permutohedral_cpu.h:684-694), apply the
+// Potts weights (pairwise3d.h:73-78) onto -unary (densecrf3d.h:155-158) and normalise (densecrf3d.h:71-98); same
+// operation order as the unfused kernels, so the result is bit-identical
+struct MfLat {
+    const int *offset;
+    const float *bary;
+    const float2 *val;
+    const float *norm;
+    float w, alpha;
+    int D;
+};
+struct MfArgs {
+    int K;
+    MfLat lat[LCCRF_MAX_K];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_mf_point_l2(MfArgs a, const float2 *__restrict__ unary, float2 *__restrict__ cur, short *__restrict__ map, int NT,
+              float relax) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= NT) return;
+    const float2 u = __ldg(unary + i);
+    float n0 = -u.x, n1 = -u.y;
+    for (int k = 0; k < a.K; k++) {
+        const MfLat &lt = a.lat[k];
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int r = 0; r < lt.D; r++) {
+            const int id = __ldg(lt.offset + (size_t)i * lt.D + r);
+            const float wa = __fmul_rn(__ldg(lt.bary + (size_t)i * lt.D + r), lt.alpha);
+            const float2 v = __ldg(lt.val + id);
+            s0 = __fadd_rn(s0, __fmul_rn(wa, v.x));
+            s1 = __fadd_rn(s1, __fmul_rn(wa, v.y));
+        }
+        const float wn = __fmul_rn(lt.w, __ldg(lt.norm + i));
+        n0 = __fadd_rn(n0, __fmul_rn(wn, s0));
+        n1 = __fadd_rn(n1, __fmul_rn(wn, s1));
+    }
+    // expAndNormalize(current_, next_, 1.0, relax)
+    float mx = n0;
+    if (mx < n1) mx = n1;
+    float v0 = fast_exp(__fsub_rn(n0, mx)), v1 = fast_exp(__fsub_rn(n1, mx));
+    const float tt = __fadd_rn(__fadd_rn(0.0f, v0), v1);
+    v0 = __fdiv_rn(v0, tt);
+    v1 = __fdiv_rn(v1, tt);
+    if (relax != 1.0f) {
+        const float2 old = cur[i];
+        const float om = __fsub_rn(1.0f, relax);
+        v0 = __fadd_rn(__fmul_rn(om, old.x), __fmul_rn(relax, v0));
+        v1 = __fadd_rn(__fmul_rn(om, old.y), __fmul_rn(relax, v1));
+    }
+    cur[i] = make_float2(v0, v1);
+    if (map) map[i] = (v0 < v1) ? 1 : 0;  // buildMap: strict <, first maximum wins
+}
+
 }  // namespace
+
+int mf_point_pass_l2(Ctx *ctx, Batch &b, const float *const *values, float relax, bool with_map) {
+    if (b.NT == 0) return LCCRF_OK;
+    MfArgs a;
+    a.K = (int)b.lat.size();
+    for (int k = 0; k < a.K; k++) {
+        const LatticeSet *ls = b.lat[k];
+        a.lat[k].offset = ls->offset;
+        a.lat[k].bary = ls->bary;
+        a.lat[k].val = (const float2 *)values[k];
+        a.lat[k].norm = ls->norm;
+        a.lat[k].w = ls->w;
+        a.lat[k].alpha = ls->alpha;
+        a.lat[k].D = ls->D;
+    }
+    LCCRF_KERNEL(ctx, "k_mf_point_l2");
+    k_mf_point_l2<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(a, (const float2 *)b.unary, (float2 *)b.cur,
+                                                                       with_map ? b.map : nullptr, b.NT, relax);
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
+}
 
 int launch_axpy_norm(Ctx *ctx, float *out, const float *tmp, const float *norm, float w, int NT, int L) {
     if (NT == 0) return LCCRF_OK;
@@ -171,6 +246,12 @@ int mf_start(Ctx *ctx, Batch &b) { return mf_exp_and_normalize(ctx, b.cur, b.una
 // stepInference   densecrf_base.h:82-91
 int mf_step(Ctx *ctx, Batch &b, float relax) {
     if (b.NT == 0) return LCCRF_OK;
+    if (b.L == 2 && !b.lat.empty() && ctx->opt_fused) {
+        // splat + blur of every lattice from the same Q, then ONE point pass
+        const float *vals[LCCRF_MAX_K];
+        for (size_t k = 0; k < b.lat.size(); k++) LCCRF_TRY(filter_splat_blur(ctx, b, b.lat[k], b.cur, 2, &vals[k]));
+        return mf_point_pass_l2(ctx, b, vals, relax, false);
+    }
     if (b.lat.empty()) LCCRF_TRY(mf_negate(ctx, b.next, b.unary, (long long)b.NT * b.L));
     for (size_t k = 0; k < b.lat.size(); k++) LCCRF_TRY(mf_apply_fused(ctx, b, b.lat[k], b.cur, b.next, b.unary, k == 0));
     return mf_exp_and_normalize(ctx, b.cur, b.next, b.NT, b.L, 1.0f, relax);

@@ -372,3 +372,35 @@ def test_full_size_properties_c3(pkg, ctx):
     assert np.array_equal(bits(p3[fr.n:fr.n + snap.n]), bits(p1))
     assert np.array_equal(bits(p3[:fr.n]), bits(p3[fr.n + snap.n:]))
     F3.close()
+
+
+def test_frames_map_batch_keyframe_slices(pkg, ctx, oracle):
+    """Batched C3-style problems with per-problem keyframe slices (kf_ptr): shared-memory slice path,
+    global-table path and the oracle must agree bit for bit."""
+    prm_o, prm = oracle_params(), pkg.SlamParams.make()
+    en = pkg.label_energies(2, prm.confidence)
+    snaps = [synth.map_snapshot(n, o, seed=90 + i, n_kf=300, ragged=r) for i, (n, o, r) in
+             enumerate(((2500, 64, False), (130, 7, True), (4000, 20, True), (31, 64, False)))]
+    sys_path_bench = importlib.import_module("bench")
+    cat = sys_path_bench.concat_snapshots(snaps)
+    assert cat["kf_pose"].shape[0] == 1200  # > 640: the whole table does not fit shared memory
+    F = pkg.Frames(ctx, [s.n for s in snaps], prm, en)
+    outs = []
+    for kf_ptr in (cat["kf_ptr"], None):
+        F.set_map_inputs(cat["xyz"], cat["obs_ptr"], cat["obs_kf"], cat["obs_uv"], cat["kf_pose"], cat["kf_intr"],
+                         cat["kf_bounds"], cat["kp2d"], kf_ptr)
+        F.run()
+        F.run()
+        outs.append((F.get_outputs(), F.get_debug()))
+    (m0, p0), d0 = outs[0]
+    (m1, p1), d1 = outs[1]
+    assert np.array_equal(bits(p0), bits(p1)) and np.array_equal(m0, m1)
+    o = 0
+    for s in snaps:
+        ob, er, de = oracle.map_point_unary(s)
+        assert np.array_equal(bits(er), bits(d0["error"][o:o + s.n])) and np.array_equal(bits(de), bits(d0["depth"][o:o + s.n]))
+        Qo, mo, _ = oracle.slam_crf(ob, er, s.kp2d, d0["init_label"][o:o + s.n], en, prm_o)
+        assert_bit_exact(p0[o:o + s.n], Qo)
+        assert np.array_equal(m0[o:o + s.n], mo)
+        o += s.n
+    F.close()
