@@ -181,6 +181,21 @@ int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *o
 int lccrf_frames_run(lccrf_frames *fr);
 /* copy results back (synchronises): map [NT] (0 = moving, 1 = static), prob [NT*2]; either may be NULL */
 int lccrf_frames_get_outputs(lccrf_frames *fr, short *map, float *prob);
+/* Pipelined end-to-end submission, depth 2.  One call = one step through host buffers: the step's inputs go up on a
+ * dedicated copy stream into input slot `slot` (0 or 1), the batch runs on the context's stream as soon as they have
+ * landed, and map [NT] / prob [NT*2] (either may be NULL) come back into the caller's buffers.  The call returns
+ * without waiting; lccrf_frames_wait(fr, slot) blocks until that submission's outputs are in host memory.  Alternating
+ * the two slots overlaps the upload of step i+1 with the compute of step i.  Host buffers should be pinned and must
+ * stay valid until the matching wait.
+ * submit_map: map-snapshot inputs (lccrf_frames_set_map_inputs layout); obs_kf holds int32 (obs_kf_bytes = 4) or
+ * uint16 (obs_kf_bytes = 2, nKF <= 65536) keyframe indices.  submit: direct per-frame vectors (set_inputs layout). */
+int lccrf_frames_submit_map(lccrf_frames *fr, int slot, const float *xyz, const int *obs_ptr, const void *obs_kf,
+                            int obs_kf_bytes, const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                            const float *kf_bounds, const float *kp2d, const int *kf_ptr, short *map_out,
+                            float *prob_out);
+int lccrf_frames_submit(lccrf_frames *fr, int slot, const float *observs, const float *error, const float *depth,
+                        const float *kp2d, short *map_out, float *prob_out);
+int lccrf_frames_wait(lccrf_frames *fr, int slot);
 /* diagnostics: init labels [NT], unary-derived vectors, per-problem lattice sizes [B*2] */
 int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth,
                            int *V);

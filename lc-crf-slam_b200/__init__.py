@@ -100,6 +100,9 @@ SYMBOLS = {
     "lccrf_frames_set_map_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_run": (C.c_int, [_vp]),
     "lccrf_frames_get_outputs": (C.c_int, [_vp, _vp, _vp]),
+    "lccrf_frames_submit_map": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_submit": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_wait": (C.c_int, [_vp, C.c_int]),
     "lccrf_frames_get_debug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -388,6 +391,22 @@ class Frames:
         pr = (np.empty((self.NT, 2), dtype=np.float32) if prob_out is None else prob_out) if want_prob else None
         self.ctx._check(self.ctx.lib.lccrf_frames_get_outputs(self.h, _ptr(mp), _ptr(pr)))
         return mp, pr
+
+    def submit_map(self, slot, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr, map_out, prob_out):
+        """Pipelined step through HOST buffers (no conversion or copy here: pass contiguous, ideally pinned, arrays;
+        obs_kf may be int32 or uint16).  Returns immediately; call wait(slot) before reading map_out / prob_out."""
+        kb = obs_kf.dtype.itemsize
+        assert obs_kf.dtype in (np.int32, np.uint16)
+        self.ctx._check(self.ctx.lib.lccrf_frames_submit_map(
+            self.h, slot, _ptr(xyz), _ptr(obs_ptr), _ptr(obs_kf), kb, _ptr(obs_uv), kf_pose.shape[0], _ptr(kf_pose),
+            _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d), _ptr(kf_ptr), _ptr(map_out), _ptr(prob_out)))
+
+    def submit(self, slot, observs, error, depth, kp2d, map_out, prob_out):
+        self.ctx._check(self.ctx.lib.lccrf_frames_submit(self.h, slot, _ptr(observs), _ptr(error), _ptr(depth), _ptr(kp2d),
+                                                          _ptr(map_out), _ptr(prob_out)))
+
+    def wait(self, slot):
+        self.ctx._check(self.ctx.lib.lccrf_frames_wait(self.h, slot))
 
     def get_debug(self):
         lab = np.empty(self.NT, dtype=np.int16)

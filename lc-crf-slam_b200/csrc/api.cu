@@ -144,28 +144,43 @@ struct lccrf_crf {
     float *d_energies = nullptr;  // n_en[L], p_en[L]
 };
 
+// one set of device-resident inputs of a frames batch.  Two sets exist so that lccrf_frames_submit_* can upload
+// step i+1 on the copy stream while step i computes (the graph of a slot reads that slot's buffers).
+struct FrameInputs {
+    // direct inputs (Tracking.cc:1849-1870 vectors) -- used when !from_map
+    float *observs = nullptr, *error = nullptr, *depth = nullptr;
+    float *kp2d = nullptr;  // [NT*2], both modes
+    // map snapshot
+    bool from_map = false;
+    float *xyz = nullptr, *obs_uv = nullptr, *kf_pose = nullptr, *kf_intr = nullptr, *kf_bounds = nullptr;
+    int *obs_ptr = nullptr;
+    void *obs_kf = nullptr;  // int32 or uint16 keyframe indices
+    int obs_kf_bytes = 4;
+    void *kf_packed = nullptr;
+    int *kf_ptr = nullptr;  // [B+1] keyframe slice of each problem (optional)
+    bool have_kf_ptr = false;
+    int nKF = 0, nKF_cap = 0;
+    long long nnz = 0, nnz_cap = 0;
+    bool have_inputs = false;
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_launches = 0, graph_gen = 0;
+    cudaEvent_t up_done = nullptr, run_done = nullptr, out_done = nullptr;
+    int *h_status = nullptr;  // pinned copy of the device status word taken after this slot's run
+    bool in_flight = false;
+};
+
 struct lccrf_frames {
     Ctx *ctx = nullptr;
     Batch b;
     lccrf_slam_params prm;
     float energies[3];
     float *d_en = nullptr;  // n_en[2], p_en[2]
-    float *observs = nullptr, *error = nullptr, *depth = nullptr, *kp2d = nullptr;  // device [NT], [NT*2]
+    float *observs = nullptr, *error = nullptr, *depth = nullptr;  // device [NT]: outputs of the unary kernel
     short *label = nullptr;
     float *feat = nullptr;  // [NT*2]
-    // map snapshot (optional)
-    bool from_map = false;
-    float *xyz = nullptr, *obs_uv = nullptr, *kf_pose = nullptr, *kf_intr = nullptr, *kf_bounds = nullptr;
-    int *obs_ptr = nullptr, *obs_kf = nullptr;
-    void *kf_packed = nullptr;
-    int *kf_ptr = nullptr;  // [B+1] keyframe slice of each problem (optional)
-    bool have_kf_ptr = false;
-    int nKF = 0;
-    long long nnz = 0, nnz_cap = 0;
-    int nKF_cap = 0;
-    bool have_inputs = false, ran = false;
-    cudaGraphExec_t graph = nullptr;
-    uint64_t graph_launches = 0, graph_gen = 0;
+    FrameInputs in[2];
+    int last_slot = 0;
+    bool ran = false;
 };
 
 extern "C" {
@@ -235,6 +250,7 @@ void lccrf_ctx_destroy(lccrf_ctx *h) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_status);
     cudaFreeHost(c->h_status);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete h;
 }
@@ -766,7 +782,6 @@ int lccrf_frames_create(lccrf_ctx *h, int B, const int *prob_ptr, const lccrf_sl
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->observs, n * 4);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->error, n * 4);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->depth, n * 4);
-    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->kp2d, n * 8);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->feat, n * 8);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->label, n * 2);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->d_en, 4 * sizeof(float));
@@ -789,62 +804,87 @@ int lccrf_frames_create(lccrf_ctx *h, int B, const int *prob_ptr, const lccrf_sl
     return LCCRF_OK;
 }
 
+static void frame_inputs_drop_graph(FrameInputs &in) {
+    if (in.graph) cudaGraphExecDestroy(in.graph);
+    in.graph = nullptr;
+}
+
+static void frame_inputs_release(Ctx *ctx, FrameInputs &in) {
+    frame_inputs_drop_graph(in);
+    dev_free(ctx, in.observs);
+    dev_free(ctx, in.error);
+    dev_free(ctx, in.depth);
+    dev_free(ctx, in.kp2d);
+    dev_free(ctx, in.xyz);
+    dev_free(ctx, in.obs_uv);
+    dev_free(ctx, in.kf_pose);
+    dev_free(ctx, in.kf_intr);
+    dev_free(ctx, in.kf_bounds);
+    dev_free(ctx, in.obs_ptr);
+    dev_free(ctx, in.obs_kf);
+    dev_free(ctx, in.kf_packed);
+    dev_free(ctx, in.kf_ptr);
+    if (in.up_done) cudaEventDestroy(in.up_done);
+    if (in.run_done) cudaEventDestroy(in.run_done);
+    if (in.out_done) cudaEventDestroy(in.out_done);
+    if (in.h_status) cudaFreeHost(in.h_status);
+    in = FrameInputs();
+}
+
 void lccrf_frames_destroy(lccrf_frames *fr) {
     if (!fr) return;
     Ctx *ctx = fr->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (fr->graph) cudaGraphExecDestroy(fr->graph);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &in : fr->in) frame_inputs_release(ctx, in);
     batch_release(ctx, fr->b);
     dev_free(ctx, fr->observs);
     dev_free(ctx, fr->error);
     dev_free(ctx, fr->depth);
-    dev_free(ctx, fr->kp2d);
     dev_free(ctx, fr->feat);
     dev_free(ctx, fr->label);
     dev_free(ctx, fr->d_en);
-    dev_free(ctx, fr->xyz);
-    dev_free(ctx, fr->obs_uv);
-    dev_free(ctx, fr->kf_pose);
-    dev_free(ctx, fr->kf_intr);
-    dev_free(ctx, fr->kf_bounds);
-    dev_free(ctx, fr->obs_ptr);
-    dev_free(ctx, fr->obs_kf);
-    dev_free(ctx, fr->kf_packed);
-    dev_free(ctx, fr->kf_ptr);
     delete fr;
 }
 
-int lccrf_frames_set_inputs(lccrf_frames *fr, const float *observs, const float *error, const float *depth,
-                            const float *kp2d) {
-    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+// upload the direct per-frame vectors of one step into input set `in` on stream `st`
+static int frames_upload_direct(lccrf_frames *fr, FrameInputs &in, cudaStream_t st, const float *observs,
+                                const float *error, const float *depth, const float *kp2d) {
     Ctx *ctx = fr->ctx;
-    LCCRF_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)fr->b.NT;
+    if (n && (!observs || !error || !depth || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (!in.observs) {
+        const size_t m = n ? n : 1;
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.observs, m * 4));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.error, m * 4));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.depth, m * 4));
+        frame_inputs_drop_graph(in);
+    }
+    if (!in.kp2d) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kp2d, (n ? n : 1) * 8));
+        frame_inputs_drop_graph(in);
+    }
+    if (in.from_map) frame_inputs_drop_graph(in);
+    in.from_map = false;
     if (n) {
-        if (!observs || !error || !depth || !kp2d) return fail(LCCRF_ERR_ARG, "NULL argument");
-        cudaStream_t st = ctx->stream;
-        LCCRF_CUDA(cudaMemcpyAsync(fr->observs, observs, n * 4, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->error, error, n * 4, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->depth, depth, n * 4, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->kp2d, kp2d, n * 8, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.observs, observs, n * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.error, error, n * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.depth, depth, n * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.kp2d, kp2d, n * 8, cudaMemcpyHostToDevice, st));
     }
-    if (fr->from_map && fr->graph) {
-        cudaGraphExecDestroy(fr->graph);
-        fr->graph = nullptr;
-    }
-    fr->from_map = false;
-    fr->have_inputs = true;
+    in.have_inputs = true;
     return LCCRF_OK;
 }
 
-int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const int *obs_kf,
-                                const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
-                                const float *kf_bounds, const float *kp2d, const int *kf_ptr) {
-    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+// validate + upload a map snapshot of one step into input set `in` on stream `st`
+static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st, const float *xyz, const int *obs_ptr,
+                             const void *obs_kf, int obs_kf_bytes, const float *obs_uv, int nKF, const float *kf_pose,
+                             const float *kf_intr, const float *kf_bounds, const float *kp2d, const int *kf_ptr) {
     Ctx *ctx = fr->ctx;
-    LCCRF_CUDA(cudaSetDevice(ctx->device));
     const int NT = fr->b.NT;
+    if (obs_kf_bytes != 4 && obs_kf_bytes != 2) return fail(LCCRF_ERR_ARG, "obs_kf_bytes must be 4 (int32) or 2 (uint16)");
+    if (obs_kf_bytes == 2 && nKF > 65536) return fail(LCCRF_ERR_ARG, "uint16 keyframe indices need nKF <= 65536");
     if (NT > 0 && (!xyz || !obs_ptr || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
     const long long nnz = NT > 0 ? obs_ptr[NT] : 0;
     if (NT > 0 && obs_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "obs_ptr must start at 0");
@@ -854,101 +894,113 @@ int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *o
     // (obs_ptr is host data, so this is a host-side structural check, not device work)
     for (int i = 0; i < NT; i++)
         if (obs_ptr[i + 1] <= obs_ptr[i]) return fail(LCCRF_ERR_ARG, "every point needs >= 1 observation (Tracking.cc:1858)");
-    bool realloc_graph = false;
-    if (nnz > fr->nnz_cap || !fr->obs_kf) {
-        dev_free(ctx, fr->obs_kf);
-        dev_free(ctx, fr->obs_uv);
-        fr->obs_kf = nullptr;
-        fr->obs_uv = nullptr;
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->obs_kf, (size_t)(nnz ? nnz : 1) * 4));
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->obs_uv, (size_t)(nnz ? nnz : 1) * 8));
-        fr->nnz_cap = nnz;
-        realloc_graph = true;
-    }
-    if (nKF > fr->nKF_cap || !fr->kf_pose) {
-        dev_free(ctx, fr->kf_pose);
-        dev_free(ctx, fr->kf_intr);
-        dev_free(ctx, fr->kf_bounds);
-        dev_free(ctx, fr->kf_packed);
-        const size_t k = (size_t)(nKF ? nKF : 1);
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_pose, k * 48));
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_intr, k * 16));
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_bounds, k * 16));
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_packed, k * 80));
-        fr->nKF_cap = nKF;
-        realloc_graph = true;
-    }
-    if (!fr->xyz) {
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->xyz, (size_t)(NT ? NT : 1) * 12));
-        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->obs_ptr, (size_t)(NT + 1) * 4));
-        realloc_graph = true;
-    }
-    if (fr->nKF != nKF || fr->nnz != nnz || !fr->from_map) realloc_graph = true;
-    if (realloc_graph && fr->graph) {
-        cudaGraphExecDestroy(fr->graph);
-        fr->graph = nullptr;
-    }
-    fr->nKF = nKF;
-    fr->nnz = nnz;
-    cudaStream_t st = ctx->stream;
     if (kf_ptr) {
         if (kf_ptr[0] != 0 || kf_ptr[fr->b.B] != nKF) return fail(LCCRF_ERR_ARG, "kf_ptr must span [0, nKF]");
         for (int i = 0; i < fr->b.B; i++)
             if (kf_ptr[i + 1] < kf_ptr[i]) return fail(LCCRF_ERR_ARG, "kf_ptr must be non-decreasing");
-        if (!fr->kf_ptr) {
-            LCCRF_TRY(dev_alloc(ctx, (void **)&fr->kf_ptr, (size_t)(fr->b.B + 1) * 4));
-            realloc_graph = true;
-        }
-        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_ptr, kf_ptr, (size_t)(fr->b.B + 1) * 4, cudaMemcpyHostToDevice, st));
-        if (!fr->have_kf_ptr && fr->graph) {
-            cudaGraphExecDestroy(fr->graph);
-            fr->graph = nullptr;
-        }
-        fr->have_kf_ptr = true;
-    } else {
-        if (fr->have_kf_ptr && fr->graph) {
-            cudaGraphExecDestroy(fr->graph);
-            fr->graph = nullptr;
-        }
-        fr->have_kf_ptr = false;
     }
+    bool regraph = false;
+    if (nnz > in.nnz_cap || !in.obs_kf || in.obs_kf_bytes != obs_kf_bytes) {
+        dev_free(ctx, in.obs_kf);
+        dev_free(ctx, in.obs_uv);
+        in.obs_kf = nullptr;
+        in.obs_uv = nullptr;
+        const long long cap = nnz > in.nnz_cap ? nnz : in.nnz_cap;
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_kf, (size_t)(cap ? cap : 1) * 4));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_uv, (size_t)(cap ? cap : 1) * 8));
+        in.nnz_cap = cap;
+        regraph = true;
+    }
+    if (nKF > in.nKF_cap || !in.kf_pose) {
+        dev_free(ctx, in.kf_pose);
+        dev_free(ctx, in.kf_intr);
+        dev_free(ctx, in.kf_bounds);
+        dev_free(ctx, in.kf_packed);
+        const size_t k = (size_t)(nKF ? nKF : 1);
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_pose, k * 48));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_intr, k * 16));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_bounds, k * 16));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_packed, k * 80));
+        in.nKF_cap = nKF;
+        regraph = true;
+    }
+    if (!in.xyz) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.xyz, (size_t)(NT ? NT : 1) * 12));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_ptr, (size_t)(NT + 1) * 4));
+        regraph = true;
+    }
+    if (!in.kp2d) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kp2d, (size_t)(NT ? NT : 1) * 8));
+        regraph = true;
+    }
+    if (kf_ptr && !in.kf_ptr) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_ptr, (size_t)(fr->b.B + 1) * 4));
+        regraph = true;
+    }
+    if (in.nKF != nKF || in.nnz != nnz || !in.from_map || in.have_kf_ptr != (kf_ptr != nullptr)) regraph = true;
+    if (regraph) frame_inputs_drop_graph(in);
+    in.nKF = nKF;
+    in.nnz = nnz;
+    in.obs_kf_bytes = obs_kf_bytes;
+    in.have_kf_ptr = kf_ptr != nullptr;
+    if (kf_ptr) LCCRF_CUDA(cudaMemcpyAsync(in.kf_ptr, kf_ptr, (size_t)(fr->b.B + 1) * 4, cudaMemcpyHostToDevice, st));
     if (NT > 0) {
-        LCCRF_CUDA(cudaMemcpyAsync(fr->xyz, xyz, (size_t)NT * 12, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->obs_ptr, obs_ptr, (size_t)(NT + 1) * 4, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->kp2d, kp2d, (size_t)NT * 8, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.xyz, xyz, (size_t)NT * 12, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.obs_ptr, obs_ptr, (size_t)(NT + 1) * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.kp2d, kp2d, (size_t)NT * 8, cudaMemcpyHostToDevice, st));
     }
     if (nnz > 0) {
-        LCCRF_CUDA(cudaMemcpyAsync(fr->obs_kf, obs_kf, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->obs_uv, obs_uv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_pose, kf_pose, (size_t)nKF * 48, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_intr, kf_intr, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(fr->kf_bounds, kf_bounds, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.obs_kf, obs_kf, (size_t)nnz * obs_kf_bytes, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.obs_uv, obs_uv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.kf_pose, kf_pose, (size_t)nKF * 48, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.kf_intr, kf_intr, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.kf_bounds, kf_bounds, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
     }
-    fr->from_map = true;
-    fr->have_inputs = true;
+    in.from_map = true;
+    in.have_inputs = true;
     return LCCRF_OK;
 }
 
-static int frames_enqueue(lccrf_frames *fr) {
+int lccrf_frames_set_inputs(lccrf_frames *fr, const float *observs, const float *error, const float *depth,
+                            const float *kp2d) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
+    return frames_upload_direct(fr, fr->in[0], fr->ctx->stream, observs, error, depth, kp2d);
+}
+
+int lccrf_frames_set_map_inputs(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const int *obs_kf,
+                                const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                                const float *kf_bounds, const float *kp2d, const int *kf_ptr) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
+    return frames_upload_map(fr, fr->in[0], fr->ctx->stream, xyz, obs_ptr, obs_kf, 4, obs_uv, nKF, kf_pose, kf_intr,
+                             kf_bounds, kp2d, kf_ptr);
+}
+
+static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
     Ctx *ctx = fr->ctx;
     Batch &b = fr->b;
     const int NT = b.NT;
     const lccrf_slam_params &prm = fr->prm;
-    if (fr->from_map) {
-        LCCRF_TRY(unary_pack_kf(ctx, fr->kf_packed, fr->kf_pose, fr->kf_intr, fr->kf_bounds, fr->nKF));
-        LCCRF_TRY(unary_map_points_packed(ctx, NT, fr->nKF, fr->xyz, fr->obs_ptr, fr->obs_kf, fr->obs_uv, fr->kf_packed,
-                                          fr->observs, fr->error, fr->depth, b.prob_ptr,
-                                          fr->have_kf_ptr ? fr->kf_ptr : nullptr, b.B));
+    const float *observs = in.observs, *error = in.error, *depth = in.depth;
+    if (in.from_map) {
+        LCCRF_TRY(unary_pack_kf(ctx, in.kf_packed, in.kf_pose, in.kf_intr, in.kf_bounds, in.nKF));
+        LCCRF_TRY(unary_map_points_packed(ctx, NT, in.nKF, in.xyz, in.obs_ptr, in.obs_kf, in.obs_kf_bytes, in.obs_uv,
+                                          in.kf_packed, fr->observs, fr->error, fr->depth, b.prob_ptr,
+                                          in.have_kf_ptr ? in.kf_ptr : nullptr, b.B));
+        observs = fr->observs;
+        error = fr->error;
+        depth = fr->depth;
     }
     // RroughClassify -> setUnaryEnergyFromLabel   (Tracking.cc:1871,1921)
-    LCCRF_TRY(unary_classify(ctx, NT, fr->observs, fr->error, fr->depth, nullptr, prm, fr->label));
+    LCCRF_TRY(unary_classify(ctx, NT, observs, error, depth, nullptr, prm, fr->label));
     LCCRF_TRY(mf_unary_from_label(ctx, b.unary, fr->label, NT, 2, fr->energies[0], fr->d_en, fr->d_en + 2));
     // appearanceKernel(N, w1, vobservs, verrors, mObservStdev, mRpjErrorStdev)   (Tracking.cc:1923)
-    LCCRF_TRY(feat_div2(ctx, fr->feat, fr->observs, 1, prm.stdev_beta, fr->error, 1, prm.stdev_alpha, NT));
+    LCCRF_TRY(feat_div2(ctx, fr->feat, observs, 1, prm.stdev_beta, error, 1, prm.stdev_alpha, NT));
     LCCRF_TRY(lattice_set_build(ctx, b, b.lat[0], fr->feat));
     LCCRF_TRY(potts_norm(ctx, b, b.lat[0]));
     // smoothKernel(N, w2, vpoints, vcorrd2d, mPoint3dStdev, mPoint2dStdev): 2-D branch   (Tracking.cc:1926)
-    LCCRF_TRY(feat_div2(ctx, fr->feat, fr->kp2d, 2, prm.point2d_stdev, fr->kp2d + 1, 2, prm.point2d_stdev, NT));
+    LCCRF_TRY(feat_div2(ctx, fr->feat, in.kp2d, 2, prm.point2d_stdev, in.kp2d + 1, 2, prm.point2d_stdev, NT));
     LCCRF_TRY(lattice_set_build(ctx, b, b.lat[1], fr->feat));
     LCCRF_TRY(potts_norm(ctx, b, b.lat[1]));
     // inference(iters, true)   (Tracking.cc:1929)
@@ -958,29 +1010,25 @@ static int frames_enqueue(lccrf_frames *fr) {
     return LCCRF_OK;
 }
 
-int lccrf_frames_run(lccrf_frames *fr) {
-    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
-    if (!fr->have_inputs) return fail(LCCRF_ERR_STATE, "frames_run before set_inputs");
+// run the batch from input set `in` on ctx->stream: CUDA-graph replay when enabled
+static int frames_run_slot(lccrf_frames *fr, FrameInputs &in) {
     Ctx *ctx = fr->ctx;
-    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    if (!in.have_inputs) return fail(LCCRF_ERR_STATE, "frames_run before set_inputs");
     if (!ctx->opt_graphs || ctx->opt_profile) {
-        LCCRF_TRY(frames_enqueue(fr));
+        LCCRF_TRY(frames_enqueue(fr, in));
         fr->ran = true;
         return LCCRF_OK;
     }
-    if (fr->graph && fr->graph_gen != ctx->scratch_gen) {  // a scratch buffer moved since capture
-        cudaGraphExecDestroy(fr->graph);
-        fr->graph = nullptr;
-    }
-    if (!fr->graph) {
+    if (in.graph && in.graph_gen != ctx->scratch_gen) frame_inputs_drop_graph(in);  // a scratch buffer moved since capture
+    if (!in.graph) {
         // make sure every scratch buffer has its final size before capture (no allocation inside the graph)
         const uint64_t l0 = ctx->launches;
-        LCCRF_TRY(frames_enqueue(fr));
+        LCCRF_TRY(frames_enqueue(fr, in));
         LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
         const uint64_t per_run = ctx->launches - l0;
         cudaGraph_t g = nullptr;
         LCCRF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = frames_enqueue(fr);
+        int rc = frames_enqueue(fr, in);
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         ctx->launches -= per_run;  // the capture pass launched nothing
         if (rc != LCCRF_OK) {
@@ -988,18 +1036,25 @@ int lccrf_frames_run(lccrf_frames *fr) {
             return rc;
         }
         if (e != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&fr->graph, g, 0);
+        e = cudaGraphInstantiate(&in.graph, g, 0);
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-        fr->graph_launches = per_run;
-        fr->graph_gen = ctx->scratch_gen;
+        in.graph_launches = per_run;
+        in.graph_gen = ctx->scratch_gen;
         fr->ran = true;
         return LCCRF_OK;  // the warm-up pass above already produced this call's results
     }
-    LCCRF_CUDA(cudaGraphLaunch(fr->graph, ctx->stream));
-    ctx->launches += fr->graph_launches;
+    LCCRF_CUDA(cudaGraphLaunch(in.graph, ctx->stream));
+    ctx->launches += in.graph_launches;
     fr->ran = true;
     return LCCRF_OK;
+}
+
+int lccrf_frames_run(lccrf_frames *fr) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
+    fr->last_slot = 0;
+    return frames_run_slot(fr, fr->in[0]);
 }
 
 int lccrf_frames_get_outputs(lccrf_frames *fr, short *map, float *prob) {
@@ -1014,6 +1069,83 @@ int lccrf_frames_get_outputs(lccrf_frames *fr, short *map, float *prob) {
     return check_status(ctx);
 }
 
+// ---- pipelined end-to-end submission (two input slots) ----
+static int frames_submit_prologue(lccrf_frames *fr, int slot, FrameInputs **in_out) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (slot < 0 || slot > 1) return fail(LCCRF_ERR_ARG, "slot must be 0 or 1");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) LCCRF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    FrameInputs &in = fr->in[slot];
+    if (in.in_flight) return fail(LCCRF_ERR_STATE, "slot still in flight: call lccrf_frames_wait first");
+    if (!in.up_done) {
+        LCCRF_CUDA(cudaEventCreateWithFlags(&in.up_done, cudaEventDisableTiming));
+        LCCRF_CUDA(cudaEventCreateWithFlags(&in.run_done, cudaEventDisableTiming));
+        LCCRF_CUDA(cudaEventCreateWithFlags(&in.out_done, cudaEventDisableTiming));
+        LCCRF_CUDA(cudaEventRecord(in.run_done, ctx->stream));
+        LCCRF_CUDA(cudaHostAlloc((void **)&in.h_status, sizeof(int), cudaHostAllocDefault));
+        *in.h_status = 0;
+    }
+    // the copy stream may overwrite this slot only after the last run that read it
+    LCCRF_CUDA(cudaStreamWaitEvent(ctx->copy_stream, in.run_done, 0));
+    *in_out = &in;
+    return LCCRF_OK;
+}
+
+static int frames_submit_epilogue(lccrf_frames *fr, int slot, FrameInputs &in, short *map_out, float *prob_out) {
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaEventRecord(in.up_done, ctx->copy_stream));
+    LCCRF_CUDA(cudaStreamWaitEvent(ctx->stream, in.up_done, 0));
+    if (!in.graph && ctx->opt_graphs && !ctx->opt_profile) {
+        // first use of the slot: the capture pass synchronises; make sure the upload has landed first
+        LCCRF_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    }
+    LCCRF_TRY(frames_run_slot(fr, in));
+    LCCRF_CUDA(cudaEventRecord(in.run_done, ctx->stream));
+    const size_t n = (size_t)fr->b.NT;
+    if (n && map_out) LCCRF_CUDA(cudaMemcpyAsync(map_out, fr->b.map, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && prob_out) LCCRF_CUDA(cudaMemcpyAsync(prob_out, fr->b.cur, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaMemcpyAsync(in.h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaEventRecord(in.out_done, ctx->stream));
+    in.in_flight = true;
+    fr->last_slot = slot;
+    return LCCRF_OK;
+}
+
+int lccrf_frames_submit_map(lccrf_frames *fr, int slot, const float *xyz, const int *obs_ptr, const void *obs_kf,
+                            int obs_kf_bytes, const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
+                            const float *kf_bounds, const float *kp2d, const int *kf_ptr, short *map_out,
+                            float *prob_out) {
+    FrameInputs *in = nullptr;
+    LCCRF_TRY(frames_submit_prologue(fr, slot, &in));
+    LCCRF_TRY(frames_upload_map(fr, *in, fr->ctx->copy_stream, xyz, obs_ptr, obs_kf, obs_kf_bytes, obs_uv, nKF, kf_pose,
+                                kf_intr, kf_bounds, kp2d, kf_ptr));
+    return frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
+}
+
+int lccrf_frames_submit(lccrf_frames *fr, int slot, const float *observs, const float *error, const float *depth,
+                        const float *kp2d, short *map_out, float *prob_out) {
+    FrameInputs *in = nullptr;
+    LCCRF_TRY(frames_submit_prologue(fr, slot, &in));
+    LCCRF_TRY(frames_upload_direct(fr, *in, fr->ctx->copy_stream, observs, error, depth, kp2d));
+    return frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
+}
+
+int lccrf_frames_wait(lccrf_frames *fr, int slot) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (slot < 0 || slot > 1) return fail(LCCRF_ERR_ARG, "slot must be 0 or 1");
+    FrameInputs &in = fr->in[slot];
+    if (!in.in_flight) return LCCRF_OK;
+    LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
+    LCCRF_CUDA(cudaEventSynchronize(in.out_done));
+    in.in_flight = false;
+    if (*in.h_status & 1) {
+        cudaMemsetAsync(fr->ctx->d_status, 0, sizeof(int), fr->ctx->stream);
+        return fail(LCCRF_ERR_RANGE, "lattice key outside the reference's short range (permutohedral_cpu.h:373)");
+    }
+    return LCCRF_OK;
+}
+
 int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth, int *V) {
     if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
     if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_get_debug before frames_run");
@@ -1021,10 +1153,13 @@ int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, 
     LCCRF_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)fr->b.NT;
     cudaStream_t st = ctx->stream;
+    const FrameInputs &in = fr->in[fr->last_slot];
+    const float *d_obs = in.from_map ? fr->observs : in.observs, *d_err = in.from_map ? fr->error : in.error,
+                *d_dep = in.from_map ? fr->depth : in.depth;
     if (n && init_label) LCCRF_CUDA(cudaMemcpyAsync(init_label, fr->label, n * 2, cudaMemcpyDeviceToHost, st));
-    if (n && observs) LCCRF_CUDA(cudaMemcpyAsync(observs, fr->observs, n * 4, cudaMemcpyDeviceToHost, st));
-    if (n && error) LCCRF_CUDA(cudaMemcpyAsync(error, fr->error, n * 4, cudaMemcpyDeviceToHost, st));
-    if (n && depth) LCCRF_CUDA(cudaMemcpyAsync(depth, fr->depth, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n && observs) LCCRF_CUDA(cudaMemcpyAsync(observs, d_obs, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n && error) LCCRF_CUDA(cudaMemcpyAsync(error, d_err, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n && depth) LCCRF_CUDA(cudaMemcpyAsync(depth, d_dep, n * 4, cudaMemcpyDeviceToHost, st));
     std::vector<int> vb[2];
     if (V) {
         for (int k = 0; k < 2; k++) {
@@ -1059,7 +1194,8 @@ int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_
         it_tot += Bit;
     }
     double u = 0;
-    if (fr->from_map) u = (double)fr->nnz * 12 + (double)fr->b.NT * 24 + (double)fr->nKF * 80;
+    const FrameInputs &in = fr->in[fr->last_slot];
+    if (in.from_map) u = (double)in.nnz * 12 + (double)fr->b.NT * 24 + (double)in.nKF * 80;
     if (total) *total = tot + u;
     if (per_iteration) *per_iteration = it_tot;
     if (unary) *unary = u;

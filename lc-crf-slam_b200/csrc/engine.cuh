@@ -68,6 +68,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // uploads of the pipelined submit path (created on first use)
     uint64_t launches = 0;
     uint64_t scratch_gen = 0;  // bumped whenever a scratch buffer moves (captured graphs hold raw pointers)
     int opt_graphs = 1;
@@ -153,8 +154,8 @@ int feat_div2(Ctx *ctx, float *feat, const float *a, int stride_a, float sa, con
 int feat_image(Ctx *ctx, float *feat, int W, int H, int F, float posdev, const void *img_dev, int is_u8,
                float featuredev);
 int unary_pack_kf(Ctx *ctx, void *kf_packed /*nKF*80 B*/, const float *pose, const float *intr, const float *bnd, int nKF);
-int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const int *obs_ptr, const int *obs_kf,
-                            const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
+int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const int *obs_ptr, const void *obs_kf,
+                            int obs_kf_bytes, const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
                             const int *prob_ptr, const int *kf_ptr, int B);
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                      const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,

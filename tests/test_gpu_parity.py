@@ -404,3 +404,44 @@ def test_frames_map_batch_keyframe_slices(pkg, ctx, oracle):
         assert np.array_equal(m0[o:o + s.n], mo)
         o += s.n
     F.close()
+
+
+def test_frames_pipelined_submit_matches_run(pkg, ctx, oracle):
+    """lccrf_frames_submit_map / submit / wait (two input slots, copy stream, uint16 keyframe indices) deliver the
+    bits of set_inputs + run + get_outputs, for alternating inputs in both slots."""
+    prm = pkg.SlamParams.make()
+    en = pkg.label_energies(2, prm.confidence)
+    snapA = synth.map_snapshot(6001, 24, seed=11, ragged=True)
+    snapB = synth.map_snapshot(6001, 24, seed=12, ragged=True)
+    F = pkg.Frames(ctx, [snapA.n], prm, en)
+    want = []
+    for s in (snapA, snapB):
+        F.set_map_inputs(s.xyz, s.obs_ptr, s.obs_kf, s.obs_uv, s.kf_pose, s.kf_intr, s.kf_bounds, s.kp2d)
+        F.run()
+        want.append(F.get_outputs())
+    assert not np.array_equal(want[0][0], want[1][0])
+    outs = [(np.empty(snapA.n, np.int16), np.empty((snapA.n, 2), np.float32)) for _ in range(2)]
+    seq = [(snapA, np.int32), (snapB, np.uint16), (snapB, np.int32), (snapA, np.uint16), (snapA, np.int32)]
+    for i, (s, dt) in enumerate(seq):
+        slot = i & 1
+        if i >= 2:
+            F.wait(slot)
+            ps, _ = seq[i - 2]
+            w = want[0] if ps is snapA else want[1]
+            assert np.array_equal(outs[slot][0], w[0]) and np.array_equal(bits(outs[slot][1]), bits(w[1])), i
+        kf = np.ascontiguousarray(s.obs_kf.astype(dt))
+        F.submit_map(slot, s.xyz, s.obs_ptr, kf, s.obs_uv, s.kf_pose, s.kf_intr, s.kf_bounds, s.kp2d, None, *outs[slot])
+        F._keep_kf = getattr(F, "_keep_kf", []) + [kf]
+    F.wait(0)
+    F.wait(1)
+    with pytest.raises(pkg.LccrfError):
+        F.wait(2)
+    # direct-vector variant
+    fr = synth.slam_frame(snapA.n, seed=3)
+    F.set_inputs(fr.observs, fr.error, fr.depth, fr.kp2d)
+    F.run()
+    wm, wp = F.get_outputs()
+    F.submit(1, fr.observs, fr.error, fr.depth, fr.kp2d, *outs[1])
+    F.wait(1)
+    assert np.array_equal(outs[1][0], wm) and np.array_equal(bits(outs[1][1]), bits(wp))
+    F.close()
