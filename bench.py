@@ -213,16 +213,27 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------- GPU arm
-def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, L=2, D=3):
-    """Algorithmic bytes of ONE launch of a kernel over the whole batch (DESIGN.md 'Kernels'): the
-    SURVEY 8(d) per-unit figures x the units one launch processes.  V_tot: vertices of the lattice set
-    the launch works on (mean over the two sets where a kernel serves both)."""
+# Kernels that together implement one stage are timed as a group (one "launch" of the group = one launch of its
+# first kernel): the ordered splat runs as k_splat_rows (short rows) + k_splat_scan_* (long rows) per filter call.
+KERNEL_GROUPS = {"splat": ("k_splat_rows", "k_splat_scan_256", "k_splat_scan_1024")}
+
+
+def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, kf_bytes=4, T=5, L=2, D=3, K=2):
+    """ALGORITHMIC bytes of ONE launch of a kernel (or kernel group) over the whole batch (DESIGN.md 'Kernels'):
+    the SURVEY 8(d) per-unit figures x the units one launch processes.  V_tot: vertices of the lattice set the
+    launch works on (mean over the two sets where a kernel serves both)."""
+    E = N_tot * D
+    n_calls = K * (T + 1)  # filter calls per step: T iterations (L labels) + 1 norm (1 label) per lattice set
+    splat_io = (K * (N_tot * 4 + V_tot * 4) + K * T * (N_tot * L * 4 + V_tot * L * 4)) / n_calls
     return {
-        "k_map_point_unary": nnz * 12 + N_tot * 24 + nKF * 80,       # B_u
-        "k_splat": N_tot * D * 8 + N_tot * L * 4 + V_tot * L * 8,    # offset+bary, in, accumulators
-        "k_blur": V_tot * (2 * L * 4 + 8),                           # read+write values, neighbour pair
-        "k_slice": N_tot * D * 8 + N_tot * L * 4 * 2 + N_tot * 4 + V_tot * L * 4,
+        "k_map_point_unary": nnz * (kf_bytes + 8) + N_tot * (12 + 4 + 12) + nKF * 80,   # B_u
+        "splat": E * 8 + splat_io,                                   # (point, weight) entries + in + vertex sums
+        "k_blur_fused": D * V_tot * (8 * L + 8),                     # B_blur
+        "k_mf_point_l2": N_tot * (K * D * 8 + K * 4 + 2 * L * 4) + K * V_tot * L * 4,  # slice x K + apply + softmax
+        "k_slice": N_tot * D * 8 + N_tot * 4 * 2 + V_tot * 4,
         "k_embed": N_tot * (2 * 4 + D * 8),                          # features in, slot + bary out
+        "k_csr_fill": E * 8 + E * 8,                                 # offset + bary in, sorted entries out
+        "k_csr_count": E * 4,
         "k_exp_normalize": 2 * N_tot * L * 4,
     }.get(name)
 
@@ -360,7 +371,7 @@ def run_gpu_arm(args):
         return
 
     # ---- roofline of the dominant kernel (rank 0): per-kernel CUDA events on the launching stream
-    roofline, shares = None, None
+    roofline, shares, kernel_ms = None, None, None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -375,22 +386,43 @@ def run_gpu_arm(args):
                 F.run()
             rep = ctx.profile_report()
             ctx.set_option("profile", 0)
-        tot = sum(v[1] for v in rep.values()) or 1.0
-        shares = {k: round(v[1] / tot, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+        # fold kernel groups
+        grp = {}
+        for k, (cnt, tms) in rep.items():
+            g = next((gn for gn, members in KERNEL_GROUPS.items() if k in members), k)
+            c0, t0_ = grp.get(g, (0, 0.0))
+            first = g == k or k == KERNEL_GROUPS[g][0]
+            grp[g] = (c0 + (cnt if first else 0), t0_ + tms)
+        tot = sum(v[1] for v in grp.values()) or 1.0
+        shares = {k: round(v[1] / tot, 4) for k, v in sorted(grp.items(), key=lambda kv: -kv[1][1])}
+        kernel_ms = {k: round(v[1] / max(v[0], 1), 5) for k, v in grp.items()}
         dbg = F.get_debug()
         Vtot = float(dbg["V"].sum()) / 2.0  # mean over the two lattice sets
+        kf_bytes = int(host["obs_kf"].dtype.itemsize) if args.workload == "c3" else 4
+        rl_all = {}
+        for k, (cnt, tms) in grp.items():
+            ab = algorithmic_kernel_bytes(k, NT, Vtot, nnz, nKF, kf_bytes, T=prm.iters)
+            if ab is not None and cnt:
+                rl_all[k] = round(ab / (tms / cnt * 1e-3) / 1e9, 1)
         top = next(iter(shares))
-        cnt, tms = rep[top]
-        ab = algorithmic_kernel_bytes(top, NT, Vtot, nnz, nKF)
+        cnt, tms = grp[top]
+        ab = algorithmic_kernel_bytes(top, NT, Vtot, nnz, nKF, kf_bytes, T=prm.iters)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the last ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top)
+        members = KERNEL_GROUPS.get(top, (top,))
         if ab is not None:
             per_launch_ms = tms / cnt
             ach = ab / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                        "avg_launch_ms": per_launch_ms, "share_of_step": shares[top]}
+            roofline = {"kernel": "+".join(members), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": ab, "avg_launch_ms": per_launch_ms,
+                        "share_of_step": shares[top], "achieved_gbs_all_kernels": rl_all,
+                        "note": "per-kernel CUDA events on the launching stream, concurrency and graphs off while profiling"}
         else:
-            roofline = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                        "traffic": None, "peak_source": peak_src, "share_of_step": shares[top]}
+            roofline = {"kernel": "+".join(members), "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s",
+                        "frac": None, "traffic": traffic, "peak_source": peak_src, "share_of_step": shares[top]}
     abytes = F.algorithmic_bytes()
 
     # ---- CPU baseline on this box's host cores (bounded sample)
@@ -398,10 +430,11 @@ def run_gpu_arm(args):
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         sample = [problems[i % len(problems)] for i in range(cores if args.workload != "c4" else 4 * cores)]
-        v, kind, dt = time_cpu(args.workload, sample, cores)
+        reps = 8 if args.workload == "c3" else 64  # ~10-30 s of CPU work in total
+        v, kind, dt = time_cpu(args.workload, sample, cores, repeats=reps)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "%d problems on %d host threads in %.1f s; CRF = %s, unary = oracle port" % (
-                   len(sample), cores, dt, "reference headers compiled in place" if kind == "reference" else "oracle port")}
+                   reps * len(sample), cores, dt, "reference headers compiled in place" if kind == "reference" else "oracle port")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -416,6 +449,7 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "kernel_shares": shares,
+        "kernel_avg_launch_ms": kernel_ms,
         "algorithmic_bytes_per_step": abytes,
         "step_hbm_frac": (abytes["total"] / (ms / args.steps * 1e-3) / 1e9) / peak,
         "cpu_baseline": cpu,

@@ -37,28 +37,47 @@ int ctx_scratch(Ctx *ctx, Ctx::Scratch &s, size_t bytes, bool pinned) {
     if (bytes <= s.bytes && s.p) return LCCRF_OK;
     size_t want = bytes + bytes / 4 + 256;
     ctx->scratch_gen++;
+    // growth is rare (first use of a shape) and may happen on either branch: order it against both streams
+    if (s.p) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    }
     if (pinned) {
-        if (s.p) {
-            cudaStreamSynchronize(ctx->stream);
-            cudaFreeHost(s.p);
-        }
+        if (s.p) cudaFreeHost(s.p);
         s.p = nullptr;
         s.bytes = 0;
         LCCRF_CUDA(cudaHostAlloc(&s.p, want, cudaHostAllocDefault));
     } else {
-        if (s.p) cudaFreeAsync(s.p, ctx->stream);
+        if (s.p) cudaFree(s.p);
         s.p = nullptr;
         s.bytes = 0;
-        LCCRF_CUDA(cudaMallocAsync(&s.p, want, ctx->stream));
+        LCCRF_CUDA(cudaMalloc(&s.p, want));
     }
     s.bytes = want;
     return LCCRF_OK;
 }
 
+bool ctx_concurrent(const Ctx *ctx) { return ctx->opt_concurrent && !ctx->opt_profile && ctx->aux_stream; }
+
+int ctx_fork(Ctx *ctx) {
+    if (!ctx_concurrent(ctx)) return LCCRF_OK;
+    LCCRF_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    LCCRF_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    return LCCRF_OK;
+}
+
+int ctx_join(Ctx *ctx) {
+    if (!ctx_concurrent(ctx)) return LCCRF_OK;
+    LCCRF_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    LCCRF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return LCCRF_OK;
+}
+
 static void scratch_release(Ctx *ctx, Ctx::Scratch &s, bool pinned) {
+    (void)ctx;
     if (!s.p) return;
     if (pinned) cudaFreeHost(s.p);
-    else cudaFreeAsync(s.p, ctx->stream);
+    else cudaFree(s.p);
     s.p = nullptr;
     s.bytes = 0;
 }
@@ -160,6 +179,7 @@ struct FrameInputs {
     int *kf_ptr = nullptr;  // [B+1] keyframe slice of each problem (optional)
     bool have_kf_ptr = false;
     int nKF = 0, nKF_cap = 0;
+    int kf_slice_max = 0;  // largest per-problem keyframe slice (0 = unknown)
     long long nnz = 0, nnz_cap = 0;
     bool have_inputs = false;
     cudaGraphExec_t graph = nullptr;
@@ -177,7 +197,7 @@ struct lccrf_frames {
     float *d_en = nullptr;  // n_en[2], p_en[2]
     float *observs = nullptr, *error = nullptr, *depth = nullptr;  // device [NT]: outputs of the unary kernel
     short *label = nullptr;
-    float *feat = nullptr;  // [NT*2]
+    float *feat = nullptr, *feat2 = nullptr;  // [NT*2] features of the appearance / smoothness kernel
     FrameInputs in[2];
     int last_slot = 0;
     bool ran = false;
@@ -216,6 +236,12 @@ int lccrf_ctx_create(int device, lccrf_ctx **out) {
         return fail(LCCRF_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
     }
     h->c.own_stream = true;
+    if (cudaStreamCreateWithFlags(&h->c.aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->c.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete h;
+        return fail(LCCRF_ERR_CUDA, "aux stream / event creation failed");
+    }
     // keep freed blocks cached in the stream-ordered pool: per-frame CRF objects allocate and free constantly
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -237,11 +263,14 @@ void lccrf_ctx_destroy(lccrf_ctx *h) {
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto &s : c->hash_keys) scratch_release(c, s, false);
-    scratch_release(c, c->hash_first, false);
-    scratch_release(c, c->hash_id, false);
-    scratch_release(c, c->ent_slot, false);
-    scratch_release(c, c->blk_cnt, false);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+    for (auto &bs : c->bs) {
+        for (auto &s : bs.hash_keys) scratch_release(c, s, false);
+        scratch_release(c, bs.hash_first, false);
+        scratch_release(c, bs.hash_id, false);
+        scratch_release(c, bs.ent_slot, false);
+        scratch_release(c, bs.blk_cnt, false);
+    }
     scratch_release(c, c->misc, false);
     scratch_release(c, c->feat, false);
     scratch_release(c, c->dev_io, false);
@@ -251,6 +280,9 @@ void lccrf_ctx_destroy(lccrf_ctx *h) {
     cudaFree(c->d_status);
     cudaFreeHost(c->h_status);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete h;
 }
@@ -284,6 +316,7 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
     if (!strcmp(name, "graphs")) h->c.opt_graphs = value;
     else if (!strcmp(name, "fused")) h->c.opt_fused = value;
     else if (!strcmp(name, "profile")) h->c.opt_profile = value;
+    else if (!strcmp(name, "concurrent")) h->c.opt_concurrent = value;
     else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);
     return LCCRF_OK;
 }
@@ -783,6 +816,7 @@ int lccrf_frames_create(lccrf_ctx *h, int B, const int *prob_ptr, const lccrf_sl
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->error, n * 4);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->depth, n * 4);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->feat, n * 8);
+    if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->feat2, n * 8);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->label, n * 2);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&fr->d_en, 4 * sizeof(float));
     if (rc == LCCRF_OK) {
@@ -843,6 +877,7 @@ void lccrf_frames_destroy(lccrf_frames *fr) {
     dev_free(ctx, fr->error);
     dev_free(ctx, fr->depth);
     dev_free(ctx, fr->feat);
+    dev_free(ctx, fr->feat2);
     dev_free(ctx, fr->label);
     dev_free(ctx, fr->d_en);
     delete fr;
@@ -894,12 +929,17 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
     // (obs_ptr is host data, so this is a host-side structural check, not device work)
     for (int i = 0; i < NT; i++)
         if (obs_ptr[i + 1] <= obs_ptr[i]) return fail(LCCRF_ERR_ARG, "every point needs >= 1 observation (Tracking.cc:1858)");
+    int slice_max = 0;
     if (kf_ptr) {
         if (kf_ptr[0] != 0 || kf_ptr[fr->b.B] != nKF) return fail(LCCRF_ERR_ARG, "kf_ptr must span [0, nKF]");
-        for (int i = 0; i < fr->b.B; i++)
+        for (int i = 0; i < fr->b.B; i++) {
             if (kf_ptr[i + 1] < kf_ptr[i]) return fail(LCCRF_ERR_ARG, "kf_ptr must be non-decreasing");
+            if (kf_ptr[i + 1] - kf_ptr[i] > slice_max) slice_max = kf_ptr[i + 1] - kf_ptr[i];
+        }
     }
     bool regraph = false;
+    if (slice_max != in.kf_slice_max) regraph = true;  // the launch geometry of the unary kernel depends on it
+    in.kf_slice_max = slice_max;
     if (nnz > in.nnz_cap || !in.obs_kf || in.obs_kf_bytes != obs_kf_bytes) {
         dev_free(ctx, in.obs_kf);
         dev_free(ctx, in.obs_uv);
@@ -982,12 +1022,22 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
     Batch &b = fr->b;
     const int NT = b.NT;
     const lccrf_slam_params &prm = fr->prm;
+    // the two pairwise kernels are independent until the first mean-field step: the smoothness kernel (keypoints
+    // only) forks off before the unary, the appearance kernel follows the unary on the main branch
+    LCCRF_TRY(ctx_fork(ctx));
+    {
+        // smoothKernel(N, w2, vpoints, vcorrd2d, mPoint3dStdev, mPoint2dStdev): 2-D branch   (Tracking.cc:1926)
+        AuxScope aux(ctx);
+        LCCRF_TRY(feat_div2(ctx, fr->feat2, in.kp2d, 2, prm.point2d_stdev, in.kp2d + 1, 2, prm.point2d_stdev, NT));
+        LCCRF_TRY(lattice_set_build(ctx, b, b.lat[1], fr->feat2));
+        LCCRF_TRY(potts_norm(ctx, b, b.lat[1]));
+    }
     const float *observs = in.observs, *error = in.error, *depth = in.depth;
     if (in.from_map) {
         LCCRF_TRY(unary_pack_kf(ctx, in.kf_packed, in.kf_pose, in.kf_intr, in.kf_bounds, in.nKF));
         LCCRF_TRY(unary_map_points_packed(ctx, NT, in.nKF, in.xyz, in.obs_ptr, in.obs_kf, in.obs_kf_bytes, in.obs_uv,
                                           in.kf_packed, fr->observs, fr->error, fr->depth, b.prob_ptr,
-                                          in.have_kf_ptr ? in.kf_ptr : nullptr, b.B));
+                                          in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max));
         observs = fr->observs;
         error = fr->error;
         depth = fr->depth;
@@ -999,10 +1049,7 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
     LCCRF_TRY(feat_div2(ctx, fr->feat, observs, 1, prm.stdev_beta, error, 1, prm.stdev_alpha, NT));
     LCCRF_TRY(lattice_set_build(ctx, b, b.lat[0], fr->feat));
     LCCRF_TRY(potts_norm(ctx, b, b.lat[0]));
-    // smoothKernel(N, w2, vpoints, vcorrd2d, mPoint3dStdev, mPoint2dStdev): 2-D branch   (Tracking.cc:1926)
-    LCCRF_TRY(feat_div2(ctx, fr->feat, in.kp2d, 2, prm.point2d_stdev, in.kp2d + 1, 2, prm.point2d_stdev, NT));
-    LCCRF_TRY(lattice_set_build(ctx, b, b.lat[1], fr->feat));
-    LCCRF_TRY(potts_norm(ctx, b, b.lat[1]));
+    LCCRF_TRY(ctx_join(ctx));
     // inference(iters, true)   (Tracking.cc:1929)
     LCCRF_TRY(mf_start(ctx, b));
     for (int it = 0; it < prm.iters; it++) LCCRF_TRY(mf_step(ctx, b, 1.0f));

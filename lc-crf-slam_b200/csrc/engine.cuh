@@ -38,19 +38,22 @@ struct LatticeSet {
     int *chunk_prob = nullptr, *chunk_s0 = nullptr, *chunk_s1 = nullptr, *prob_chunk0 = nullptr;
     long long *chunk_tbl = nullptr;
     int *csr_tbl = nullptr, *scan_tot = nullptr;
-    // rows by length class (filled by csr_build): [0, kMedRow) lane-sequential, [kMedRow, kLongRow) one warp
-    // per row, [kLongRow, ..) one CTA per row -- the latter two with the exact ordered scan (filter.cu)
+    // rows by length class (filled by csr_build): [0, kLongRow) lane-sequential, [kLongRow, kHugeRow) one 256-thread
+    // CTA per (row, label), [kHugeRow, ..) one 1024-thread CTA -- the latter two with the exact ordered scan (filter.cu)
     int *row_list_med = nullptr, *row_list_long = nullptr;  // [Vcap] each
-    int *row_counts = nullptr;                              // [2] device: #medium, #long
+    int *row_counts = nullptr;                              // [2] device: #medium, #huge
+    // gran_row[g] = first row whose first entry lies at or after g * kTileGranule (k_splat_tile windows)
+    int *gran_row = nullptr;                                // [NT*D / kTileGranule + 16]
+    int gran_n = 0;
     // filter workspace
     float *valA = nullptr, *valB = nullptr;  // [Vcap*Lmax] blur ping-pong
-    float *prod = nullptr;                   // [NT*D*Lmax] bary*value of every entry, in vertex-sorted order
     int Lmax = 0;
 };
 
-constexpr int kCsrChunkPoints = 4096;
-constexpr int kMedRow = 96;     // rows at least this long leave the lane-sequential kernel
-constexpr int kLongRow = 1024;  // rows at least this long get a whole CTA  // points per chunk of the parallel stable counting sort
+constexpr int kCsrChunkPoints = 4096;  // points per chunk of the parallel stable counting sort
+constexpr int kLongRow = 1024;   // rows at least this long leave the lane-sequential kernel for the exact scan (256 threads)
+constexpr int kHugeRow = 16384;  // rows at least this long are scanned by 1024 threads
+constexpr int kTileGranule = 2048;  // entry granularity of the k_splat_tile windows
 
 struct Batch {
     Ctx *ctx = nullptr;
@@ -85,7 +88,17 @@ struct Ctx {
         void *p = nullptr;
         size_t bytes = 0;
     };
-    Scratch hash_keys[3], hash_first, hash_id, ent_slot, blk_cnt, misc, feat, pinned_in, pinned_out, dev_io;
+    struct BuildScratch {  // lattice-build workspace; one set per concurrent branch
+        Scratch hash_keys[3], hash_first, hash_id, ent_slot, blk_cnt;
+    };
+    BuildScratch bs[2];
+    Scratch misc, feat, pinned_in, pinned_out, dev_io;
+    // fork/join of independent launch sequences (the K lattices of one CRF): `stream` is the main branch,
+    // `aux_stream` the second one.  Inside a graph capture the event edges become parallel graph branches.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int opt_concurrent = 1;
+    int branch = 0;  // 0 = launches go to `stream`, 1 = to `aux_stream` (see AuxScope)
     int *d_status = nullptr;   // device status word (key range overflow etc.)
     int *h_status = nullptr;   // pinned
 };
@@ -114,6 +127,28 @@ struct KernelScope {
     }
 };
 #define LCCRF_KERNEL(ctx, name) ::lccrf::KernelScope _kscope_##__LINE__(ctx, name)
+// fork: the aux branch starts after everything enqueued on the main branch so far; join: main waits for aux
+bool ctx_concurrent(const Ctx *ctx);
+int ctx_fork(Ctx *ctx);
+int ctx_join(Ctx *ctx);
+// launches inside the scope go to the aux branch (no-op when concurrency is off)
+struct AuxScope {
+    Ctx *c;
+    cudaStream_t saved;
+    bool on;
+    explicit AuxScope(Ctx *ctx, bool enable = true) : c(ctx), saved(ctx->stream), on(enable && ctx_concurrent(ctx)) {
+        if (on) {
+            c->stream = c->aux_stream;
+            c->branch = 1;
+        }
+    }
+    ~AuxScope() {
+        if (on) {
+            c->stream = saved;
+            c->branch = 0;
+        }
+    }
+};
 int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero = false);
 void dev_free(Ctx *ctx, void *p);
 
@@ -156,7 +191,7 @@ int feat_image(Ctx *ctx, float *feat, int W, int H, int F, float posdev, const v
 int unary_pack_kf(Ctx *ctx, void *kf_packed /*nKF*80 B*/, const float *pose, const float *intr, const float *bnd, int nKF);
 int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const int *obs_ptr, const void *obs_kf,
                             int obs_kf_bytes, const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
-                            const int *prob_ptr, const int *kf_ptr, int B);
+                            const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max);
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                      const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
                      const float *kf_bounds, float *observs, float *error, float *depth);

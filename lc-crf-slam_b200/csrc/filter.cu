@@ -19,116 +19,112 @@ namespace {
 // ---------------------------------------------------------------- splat
 // Segmented reduction over the vertex-sorted entries (csr.cu).  values[v][l] = (((0 + w0*x0) + w1*x1) + ...)
 // over the row of v in point order, every product and sum individually rounded -- the reference's splat loop
-// (:653-661) bit for bit.  Three kernels:
-//   k_products      prod[e][l] = bary[e] * in[point[e]][l] for every entry, in vertex-sorted order: one fully
-//                   parallel, coalesced pass (the only gather of the splat)
-//   k_splat_staged  rows shorter than kLongRow: a warp owns G = 32/LP consecutive rows (LP = label count rounded up
-//                   to a power of two) = one contiguous slab of prod; the slab is copied to shared memory with wide
-//                   coalesced loads, then lane (row, label) adds its row front to back -- ordered, no DRAM latency
-//                   in the dependent chain
-//   k_splat_scan    rows of kLongRow entries and more: exact parallel scan (below)
-template <int LT>
-__global__ void __launch_bounds__(kThreads)
-k_products(const int2 *__restrict__ ent, const float *__restrict__ in, float *__restrict__ prod, long long E, int L_rt) {
-    const int L = LT > 0 ? LT : L_rt;
-    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= E) return;
-    const int2 t = __ldg(ent + e);
-    const float w = __int_as_float(t.y);
-    if (LT == 2) {
-        const float2 x = __ldg((const float2 *)in + t.x);
-        ((float2 *)prod)[e] = make_float2(__fmul_rn(w, x.x), __fmul_rn(w, x.y));
-    } else if (LT == 1) {
-        prod[e] = __fmul_rn(w, __ldg(in + t.x));
-    } else {
-        for (int l = 0; l < L; l++) prod[e * L + l] = __fmul_rn(w, __ldg(in + (size_t)t.x * L + l));
-    }
-}
+// (:653-661) bit for bit.  Two kernels, both gathering in[point] themselves (no intermediate product array):
+//   k_splat_tile   rows shorter than kLongRow.  A CTA owns a window of the entry list (a few granules of
+//                  kTileGranule entries) = the rows that START inside it.  Phase 1: all threads stream the window's
+//                  entries (coalesced), gather in[point] and park the products in shared memory -- every load is
+//                  independent, so the whole window costs about two memory round trips.  Phase 2: lane (row, label)
+//                  adds its row front to back from shared memory: the ordered FADD chain never waits on DRAM.
+//   k_splat_scan   rows of kLongRow entries and more: exact parallel scan (below), one CTA per (row, label)
+constexpr int kTileFloats = 14336;      // staged products per CTA (56 KB): 3-4 CTAs per SM
+constexpr int kTileRows = 1024;         // rows per staging round
+constexpr int kTileThreads = 256;
+constexpr int kTileBatch = 16;          // entries per thread whose loads are issued before the first use
 
-constexpr int kStageFloats = 2048;  // per warp
-__device__ __forceinline__ int spad(int idx) { return idx + (idx >> 5); }
+// labels staged per pass and window length (in granules) for a given L
+static inline int tile_labels(int L) { return L <= 2 ? L : 4; }
+static inline int tile_granules(int L) { return (kTileFloats / tile_labels(L) - kLongRow) / kTileGranule; }
 
-template <int LP>
-__global__ void __launch_bounds__(kThreads)
-k_splat_staged(const int *__restrict__ row_ptr, const float *__restrict__ prod, float *__restrict__ val,
-               const int *__restrict__ vtotal, int L) {
-    constexpr int G = 32 / LP;
-    extern __shared__ float s_all[];
-    const int V = __ldg(vtotal);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float *s_prod = s_all + (size_t)wid * (kStageFloats + kStageFloats / 32);
-    const int g = lane / LP;
-    const int cap = (kStageFloats - 4) / L;  // entries per staged chunk (4 floats of alignment slack)
-    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * kThreads) >> 5;
-    for (int l0 = 0; l0 < L; l0 += LP) {  // L > 32: several label passes over the same rows
-        const int l = l0 + lane % LP;
-        for (long long rb = (long long)warp * G; rb < V; rb += (long long)nwarps * G) {
-            const int v = (int)rb + g;
-            const int rs = v < V ? __ldg(row_ptr + v) : 0;
-            const int re = v < V ? __ldg(row_ptr + v + 1) : rs;
-            const bool mine = v < V && l < L && (re - rs) < kLongRow;  // longer rows belong to k_splat_scan
-            const int E0 = __shfl_sync(0xffffffffu, rs, 0);
-            const int E1 = __ldg(row_ptr + min((int)rb + G, V));
-            float acc = 0.0f;
-            int gcur = 0;  // row of the group that contains cb (moves forward only)
-            for (int cb = E0; cb < E1;) {
-                int rs_c, re_c;
-                for (;;) {
-                    rs_c = __shfl_sync(0xffffffffu, rs, gcur * LP);
-                    re_c = __shfl_sync(0xffffffffu, re, gcur * LP);
-                    if (re_c > cb || gcur == G - 1) break;
-                    gcur++;
-                }
-                if (re_c - rs_c >= kLongRow && cb >= rs_c && cb < re_c) {  // inside a long row: jump over it
-                    cb = re_c;
-                    continue;
-                }
-                const int ce = min(cb + cap, E1);
-                // phase 1: the slab prod[cb*L, ce*L) -> shared memory with 128-bit loads from the enclosing
-                // 16-byte aligned window, all lanes, every load independent (one memory round trip per chunk)
-                const long long f0 = (long long)cb * L;
-                const long long a0 = f0 & ~3ll;
-                const int shift = (int)(f0 - a0);
-                const int nq = ((ce - cb) * L + shift + 3) >> 2;  // float4 count (prod is padded by 4 floats)
-                {   // nq <= 512: at most 16 float4 per lane, all loaded before the first shared store
-                    float4 x[16];
+template <int LG>  // labels per pass (1, 2 or 4)
+__global__ void __launch_bounds__(kTileThreads)
+k_splat_tile(const int *__restrict__ row_ptr, const int *__restrict__ gran_row, const int2 *__restrict__ ent,
+             const float *__restrict__ in, float *__restrict__ val, int granules_per_tile, int L) {
+    extern __shared__ float s_prod[];          // [entry][LG]
+    __shared__ int s_rp[kTileRows + 1];        // row starts of the current round
+    __shared__ int s_first_long;
+    const int tid = threadIdx.x;
+    const int g0 = blockIdx.x * granules_per_tile;
+    const int v0 = __ldg(gran_row + g0), v1 = __ldg(gran_row + g0 + granules_per_tile);
+    int vcur = v0;
+    while (vcur < v1) {  // rounds: maximal runs of consecutive short rows, at most kTileRows each (usually one round)
+        const int nr_try = min(kTileRows, v1 - vcur);
+        if (tid == 0) s_first_long = nr_try;
+        __syncthreads();
+        for (int r = tid; r <= nr_try; r += kTileThreads) s_rp[r] = __ldg(row_ptr + vcur + r);
+        __syncthreads();
+        for (int r = tid; r < nr_try; r += kTileThreads)
+            if (s_rp[r + 1] - s_rp[r] >= kLongRow) atomicMin(&s_first_long, r);
+        __syncthreads();
+        const int nr = s_first_long;
+        if (nr == 0) {  // a long row: k_splat_scan owns it
+            vcur++;
+            __syncthreads();
+            continue;
+        }
+        const int eb = s_rp[0], cnt = s_rp[nr] - eb;  // cnt < window + kLongRow: the rows start inside the window
+        for (int lb = 0; lb < L; lb += LG) {
+            // phase 1: products of the round's entries -> shared memory
+            for (int i0 = 0; i0 < cnt; i0 += kTileThreads * kTileBatch) {
+                int2 t[kTileBatch];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int q = lane + 32 * j;
-                        if (q < nq) x[j] = __ldg((const float4 *)(prod + a0) + q);
+                for (int q = 0; q < kTileBatch; q++) {
+                    const int i = i0 + q * kTileThreads + tid;
+                    t[q] = i < cnt ? __ldg(ent + eb + i) : make_int2(0, 0);
+                }
+                if (LG == 2) {
+                    float2 x[kTileBatch];
+#pragma unroll
+                    for (int q = 0; q < kTileBatch; q++) {
+                        const int i = i0 + q * kTileThreads + tid;
+                        x[q] = i < cnt ? __ldg((const float2 *)(in + (size_t)t[q].x * L + lb)) : make_float2(0.f, 0.f);
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int q = lane + 32 * j;
-                        if (q < nq) {
-                            const int o = spad(q * 4);
-                            s_prod[o] = x[j].x;
-                            s_prod[o + 1] = x[j].y;
-                            s_prod[o + 2] = x[j].z;
-                            s_prod[o + 3] = x[j].w;
+                    for (int q = 0; q < kTileBatch; q++) {
+                        const int i = i0 + q * kTileThreads + tid;
+                        const float w = __int_as_float(t[q].y);
+                        if (i < cnt) ((float2 *)s_prod)[i] = make_float2(__fmul_rn(w, x[q].x), __fmul_rn(w, x[q].y));
+                    }
+                } else {
+                    float x[kTileBatch][LG];
+#pragma unroll
+                    for (int q = 0; q < kTileBatch; q++) {
+                        const int i = i0 + q * kTileThreads + tid;
+#pragma unroll
+                        for (int j = 0; j < LG; j++)
+                            x[q][j] = (i < cnt && lb + j < L) ? __ldg(in + (size_t)t[q].x * L + lb + j) : 0.0f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < kTileBatch; q++) {
+                        const int i = i0 + q * kTileThreads + tid;
+                        const float w = __int_as_float(t[q].y);
+                        if (i < cnt) {
+#pragma unroll
+                            for (int j = 0; j < LG; j++) s_prod[(size_t)i * LG + j] = __fmul_rn(w, x[q][j]);
                         }
                     }
                 }
-                __syncwarp();
-                // phase 2: ordered accumulation
-                if (mine) {
-                    const int a = max(rs, cb), z = min(re, ce);
-                    int e = a;
-                    for (; e + 8 <= z; e += 8) {  // independent shared loads first, then the ordered chain
-                        float x[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) x[q] = s_prod[spad((e + q - cb) * L + l + shift)];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, x[q]);
-                    }
-                    for (; e < z; e++) acc = __fadd_rn(acc, s_prod[spad((e - cb) * L + l + shift)]);
-                }
-                __syncwarp();
-                cb = ce;
             }
-            if (mine) val[(size_t)v * L + l] = acc;
+            __syncthreads();
+            // phase 2: ordered accumulation, one lane per (row, label)
+            for (int idx = tid; idx < nr * LG; idx += kTileThreads) {
+                const int r = idx / LG, j = idx - r * LG;
+                if (lb + j >= L) continue;
+                const int a = s_rp[r] - eb, z = s_rp[r + 1] - eb;
+                float acc = 0.0f;
+                int e = a;
+                for (; e + 8 <= z; e += 8) {  // independent shared loads first, then the ordered chain
+                    float y[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) y[q] = s_prod[(size_t)(e + q) * LG + j];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, y[q]);
+                }
+                for (; e < z; e++) acc = __fadd_rn(acc, s_prod[(size_t)e * LG + j]);
+                val[(size_t)(vcur + r) * L + lb + j] = acc;
+            }
+            __syncthreads();
         }
+        vcur += nr;
     }
 }
 
@@ -158,31 +154,49 @@ struct ScanShared {
     float bcast[2];
 };
 
-// Exact sequential sum of c over entries [e0, e1) for label l, computed by a group of NW warps; every thread owns
-// IT consecutive entries of each chunk of NW*32*IT.  All threads of the group call this with identical arguments;
-// tid = thread index inside the group.  Returns the same value in every thread.
+// barrier of a team of NW warps (named barrier 1: sub-teams of a CTA may run it while the other warps wait at barrier 0)
+template <int NW>
+__device__ __forceinline__ void team_sync() {
+    if (NW > 1) asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+}
+
+// Exact sequential sum s0 + c[e0] + c[e0+1] + ... (c = bary * in[point], label l) over the entries [e0, e1), computed
+// by a team of NW warps; every thread owns IT consecutive entries of each chunk of NW*32*IT.  All threads of the team
+// call this with identical arguments; tid = thread index inside the team.  Returns the same value in every thread.
 template <int NW, int IT>
-__device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, int L, int l, int tid, ScanShared<NW> &sh) {
+__device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__restrict__ in, int e0, int e1, int L, int l,
+                               int tid, ScanShared<NW> &sh, float s) {
     constexpr int T = NW * 32, CH = T * IT;
     const int lane = tid & 31, wid = tid >> 5;
-    float s = 0.0f;
-    float cn[IT];  // next chunk's contributions, loaded while the current chunk is being scanned
+    const float *x = in + l;
+    // software pipeline over chunks: (wn, xn) = weights and gathered values of the next chunk, en = entries of the
+    // chunk after it; both are in flight while the current chunk is scanned (the multiply happens at consumption,
+    // so no instruction waits on a load before the scan work)
+    float wn[IT], xn[IT];
+    int2 en[IT];
+#pragma unroll
+    for (int k = 0; k < IT; k++) en[k] = e0 + tid * IT + k < e1 ? __ldg(ent + e0 + tid * IT + k) : make_int2(0, 0);
 #pragma unroll
     for (int k = 0; k < IT; k++) {
-        cn[k] = 0.0f;
-        if (e0 + tid * IT + k < e1) cn[k] = __ldg(prod + (size_t)(e0 + tid * IT + k) * L + l);
+        wn[k] = __int_as_float(en[k].y);
+        xn[k] = e0 + tid * IT + k < e1 ? __ldg(x + (size_t)en[k].x * L) : 0.0f;
     }
+#pragma unroll
+    for (int k = 0; k < IT; k++)
+        en[k] = e0 + CH + tid * IT + k < e1 ? __ldg(ent + e0 + CH + tid * IT + k) : make_int2(0, 0);
     for (int cb = e0; cb < e1; cb += CH) {
         float c[IT];
 #pragma unroll
-        for (int k = 0; k < IT; k++) c[k] = cn[k];
+        for (int k = 0; k < IT; k++) c[k] = __fmul_rn(wn[k], xn[k]);
         {
             const int nbase = cb + CH + tid * IT;
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                cn[k] = 0.0f;
-                if (nbase + k < e1) cn[k] = __ldg(prod + (size_t)(nbase + k) * L + l);
+                wn[k] = __int_as_float(en[k].y);
+                xn[k] = nbase + k < e1 ? __ldg(x + (size_t)en[k].x * L) : 0.0f;
             }
+#pragma unroll
+            for (int k = 0; k < IT; k++) en[k] = nbase + CH + k < e1 ? __ldg(ent + nbase + CH + k) : make_int2(0, 0);
         }
         const int n_chunk = min(CH, e1 - cb);
         const int li0 = tid * IT;  // chunk-local index of this thread's first entry
@@ -193,7 +207,7 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
             if (!regular) {
                 // rare path (row start, zero / negative / huge running sums): one real addition at a time,
                 // except that a run of exact zeros is skipped while s == +0
-                if (NW > 1) __syncthreads();
+                team_sync<NW>();
                 if (s == 0.0f) {
                     int first = CH;
 #pragma unroll
@@ -203,11 +217,11 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
                     for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
                     if (NW > 1) {
                         if (lane == 0) sh.first_bad[wid] = first;
-                        __syncthreads();
+                        team_sync<NW>();
                         first = CH;
 #pragma unroll
                         for (int w = 0; w < NW; w++) first = min(first, sh.first_bad[w]);
-                        __syncthreads();
+                        team_sync<NW>();
                     }
                     if (first >= n_chunk) {
                         st = n_chunk;
@@ -222,7 +236,7 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
                 if (NW == 1) cj = __shfl_sync(0xffffffffu, cj, st / IT);
                 else {
                     if (tid == st / IT) sh.bcast[1] = cj;
-                    __syncthreads();
+                    team_sync<NW>();
                     cj = sh.bcast[1];
                 }
                 s = __fadd_rn(s, cj);
@@ -236,32 +250,34 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
             ScanPair tot;
             tot.a0 = tot.a1 = 0;
             int hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+            if (li0 + IT > st && li0 < n_chunk) {  // threads whose entries are already folded in contribute the identity
 #pragma unroll
-            for (int k = 0; k < IT; k++) {
-                if (li0 + k >= st && li0 + k < n_chunk) {
-                    const float q = __fmul_rn(c[k], inv_u);
-                    int ni;
-                    float fr = 0.0f;
-                    if (!(fabsf(q) < 16777216.0f)) {  // also NaN / inf: forces "leaves the binade"
-                        ni = q > 0.0f ? (1 << 24) : -(1 << 24);
-                    } else {
-                        ni = __float2int_rd(q);
-                        fr = __fsub_rn(q, (float)ni);  // exact, in [0, 1)
+                for (int k = 0; k < IT; k++) {
+                    if (li0 + k >= st && li0 + k < n_chunk) {
+                        const float q = __fmul_rn(c[k], inv_u);
+                        int ni;
+                        float fr = 0.0f;
+                        if (!(fabsf(q) < 16777216.0f)) {  // also NaN / inf: forces "leaves the binade"
+                            ni = q > 0.0f ? (1 << 24) : -(1 << 24);
+                        } else {
+                            ni = __float2int_rd(q);
+                            fr = __fsub_rn(q, (float)ni);  // exact, in [0, 1)
+                        }
+                        if (fr != 0.5f) {  // common case: the same increment for either parity
+                            const int inc1 = ni + (fr > 0.5f ? 1 : 0);
+                            tot.a0 += inc1;
+                            tot.a1 += inc1;
+                        } else {           // tie: round half to even
+                            ScanPair a;
+                            a.a0 = ni + (ni & 1);
+                            a.a1 = ni + ((ni + 1) & 1);
+                            tot = scan_combine(tot, a);
+                        }
+                        hi0 = max(hi0, tot.a0);
+                        lo0 = min(lo0, tot.a0);
+                        hi1 = max(hi1, tot.a1);
+                        lo1 = min(lo1, tot.a1);
                     }
-                    if (fr != 0.5f) {  // common case: the same increment for either parity
-                        const int inc1 = ni + (fr > 0.5f ? 1 : 0);
-                        tot.a0 += inc1;
-                        tot.a1 += inc1;
-                    } else {           // tie: round half to even
-                        ScanPair a;
-                        a.a0 = ni + (ni & 1);
-                        a.a1 = ni + ((ni + 1) & 1);
-                        tot = scan_combine(tot, a);
-                    }
-                    hi0 = max(hi0, tot.a0);
-                    lo0 = min(lo0, tot.a0);
-                    hi1 = max(hi1, tot.a1);
-                    lo1 = min(lo1, tot.a1);
                 }
             }
             // exclusive scan of the thread totals in thread order
@@ -279,7 +295,7 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
             if (lane == 0) exc.a0 = exc.a1 = 0;
             if (NW > 1) {
                 if (lane == 31) sh.warp_tot[wid] = inc;
-                __syncthreads();
+                team_sync<NW>();
                 // every warp scans the NW warp totals itself (no second barrier)
                 ScanPair w = sh.warp_tot[lane < NW ? lane : 0];
                 if (lane >= NW) w.a0 = w.a1 = 0;
@@ -306,7 +322,7 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
             } else {
                 if (lane == 0) sh.first_bad[wid] = badmask ? wid * 32 + __ffs(badmask) - 1 : T;
                 if (tid == T - 1) sh.bcast[0] = __fmul_rn((float)m_end, u);
-                __syncthreads();
+                team_sync<NW>();
                 tb = T;
 #pragma unroll
                 for (int w = NW - 1; w >= 0; w--) {
@@ -328,32 +344,58 @@ __device__ float row_sum_exact(const float *__restrict__ prod, int e0, int e1, i
                 if (NW == 1) s = __shfl_sync(0xffffffffu, sq, tb);
                 else {
                     if (tid == tb) sh.bcast[1] = sq;
-                    __syncthreads();
+                    team_sync<NW>();
                     s = sh.bcast[1];
                 }
                 st = min((tb + 1) * IT, n_chunk);
             }
+            // shared words written above are rewritten only after the next team barrier of this loop
         }
     }
     return s;
 }
 
-// one group (warp or CTA) per (row, label) task; rows come from a device-side list
+// One CTA per (row, label) task; rows come from a device-side list.  Binade crossings are densest at the start of a
+// row (the running sum doubles after 1, 2, 4, ... entries) and every crossing costs one re-scan of the rest of the
+// chunk, so the row is summed in stages by growing teams: the first kScanHead1 entries by warp 0 alone (cheap
+// re-scans), up to kScanHead2 by 8 warps, the rest by the whole CTA with its large chunks.
+constexpr int kScanHead1 = 2048, kScanHead2 = 16384;
+
 template <int NW, int IT>
-__global__ void __launch_bounds__(NW * 32 > kThreads ? NW * 32 : kThreads)
-k_splat_scan(const int *__restrict__ row_ptr, const float *__restrict__ prod, float *__restrict__ val,
-             const int *__restrict__ list, const int *__restrict__ count, int L) {
-    constexpr int GROUPS = NW == 1 ? kThreads / 32 : 1;  // groups per CTA
-    __shared__ ScanShared<NW> sh[GROUPS];
+__global__ void __launch_bounds__(NW * 32)
+k_splat_scan(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
+             float *__restrict__ val, const int *__restrict__ list, const int *__restrict__ count, int L) {
+    __shared__ ScanShared<NW> sh;
+    __shared__ ScanShared<8> sh8;
+    __shared__ ScanShared<1> sh1;
+    __shared__ float s_stage;
     const long long n = (long long)__ldg(count) * L;
-    const int gid = NW == 1 ? threadIdx.x >> 5 : 0;
-    const int tid = NW == 1 ? (threadIdx.x & 31) : threadIdx.x;
-    for (long long k = (long long)blockIdx.x * GROUPS + gid; k < n; k += (long long)gridDim.x * GROUPS) {
+    const int tid = threadIdx.x, wid = tid >> 5;
+    for (long long k = blockIdx.x; k < n; k += gridDim.x) {
         const int v = __ldg(list + (int)(k / L)), l = (int)(k % L);
         const int e0 = __ldg(row_ptr + v), e1 = __ldg(row_ptr + v + 1);
-        const float s = row_sum_exact<NW, IT>(prod, e0, e1, L, l, tid, sh[gid]);
+        float s = 0.0f;
+        int pos = min(e0 + kScanHead1, e1);
+        if (wid == 0) {
+            s = row_sum_exact<1, IT>(ent, in, e0, pos, L, l, tid, sh1, 0.0f);
+            if (tid == 0) s_stage = s;
+        }
+        __syncthreads();
+        s = s_stage;
+        if (NW > 8 && pos < e1) {
+            const int h2 = min(e0 + kScanHead2, e1);
+            __syncthreads();  // everybody has read s_stage
+            if (wid < 8) {
+                s = row_sum_exact<8, IT>(ent, in, pos, h2, L, l, tid, sh8, s);
+                if (tid == 0) s_stage = s;
+            }
+            __syncthreads();
+            s = s_stage;
+            pos = h2;
+        }
+        if (pos < e1) s = row_sum_exact<NW, IT>(ent, in, pos, e1, L, l, tid, sh, s);
         if (tid == 0) val[(size_t)v * L + l] = s;
-        if (NW > 1) __syncthreads();
+        __syncthreads();
     }
 }
 
@@ -374,18 +416,44 @@ k_blur(const int2 *__restrict__ nbr_j, const float *__restrict__ src, float *__r
     }
 }
 
-// all D blur passes of one problem inside one CTA (shared-memory ping-pong when the lattice fits, global otherwise):
-// replaces D launch-bound passes when a batch holds several problems or the lattice is small
-constexpr int kBlurFusedFloats = 24576;  // 96 KB
+// all D blur passes of one problem inside one CTA: replaces D launch-bound passes when a batch holds several
+// problems or the lattice is small.  When values (ping-pong) AND the problem's D neighbour tables fit shared memory
+// everything is fetched in one round of independent global loads and the passes run from shared memory; otherwise
+// the values ping-pong in shared memory with neighbour pairs read per pass, or (huge lattices) in global memory.
+constexpr int kBlurFusedBytes = 160 * 1024;
 __global__ void __launch_bounds__(1024)
 k_blur_fused(const int2 *__restrict__ nbr, int Vcap, const int *__restrict__ vbase, float *__restrict__ A,
              float *__restrict__ B, int L, int D) {
     extern __shared__ float s_blur[];
     const int b = blockIdx.x;
     const int vb = __ldg(vbase + b);
-    const int n = (__ldg(vbase + b + 1) - vb) * L;
+    const int nv = __ldg(vbase + b + 1) - vb;
+    const int n = nv * L;
     float *gA = A + (size_t)vb * L, *gB = B + (size_t)vb * L;
-    if (2 * n <= kBlurFusedFloats) {
+    if ((size_t)2 * n * sizeof(float) + (size_t)D * nv * sizeof(int2) <= (size_t)kBlurFusedBytes) {
+        float *src = s_blur, *dst = s_blur + n;
+        int2 *s_nb = (int2 *)(s_blur + 2 * n + ((2 * n) & 1));  // 8-byte aligned
+        for (int t = threadIdx.x; t < n; t += 1024) src[t] = gA[t];
+        for (int t = threadIdx.x; t < D * nv; t += 1024) {
+            const int j = t / nv, v = t - j * nv;
+            s_nb[t] = __ldg(nbr + (size_t)j * Vcap + vb + v);
+        }
+        __syncthreads();
+        for (int j = 0; j < D; j++) {
+            for (int t = threadIdx.x; t < n; t += 1024) {
+                const int v = t / L, l = t - v * L;
+                const int2 nb = s_nb[j * nv + v];
+                const float a = nb.x >= 0 ? src[(nb.x - vb) * L + l] : 0.f;
+                const float c = nb.y >= 0 ? src[(nb.y - vb) * L + l] : 0.f;
+                dst[t] = __fadd_rn(src[t], __fmul_rn(0.5f, __fadd_rn(a, c)));
+            }
+            __syncthreads();
+            float *tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+        for (int t = threadIdx.x; t < n; t += 1024) gB[t] = src[t];
+    } else if ((size_t)2 * n * sizeof(float) <= (size_t)kBlurFusedBytes) {
         float *src = s_blur, *dst = s_blur + n;
         for (int t = threadIdx.x; t < n; t += 1024) src[t] = gA[t];
         __syncthreads();
@@ -470,52 +538,51 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     const int D = ls->D;
     const int *vt = ls->vbase + ls->B;
     float *src = ls->valA, *dst = ls->valB;
-    const long long E = (long long)b.NT * D;
-    if (E > 0) {
-        LCCRF_KERNEL(ctx, "k_products");
-        const int grid = cdiv(E, kThreads);
-        if (L == 1) k_products<1><<<grid, kThreads, 0, st>>>(ls->csr_ent, in_dev, ls->prod, E, L);
-        else if (L == 2) k_products<2><<<grid, kThreads, 0, st>>>(ls->csr_ent, in_dev, ls->prod, E, L);
-        else k_products<0><<<grid, kThreads, 0, st>>>(ls->csr_ent, in_dev, ls->prod, E, L);
-    }
-    {
-        int LP = 1;
-        while (LP < L && LP < 32) LP <<= 1;
-        const int grid = persistent_grid((long long)ls->Vcap * LP, kThreads, 3);
-        const size_t smem = (size_t)(kThreads / 32) * (kStageFloats + kStageFloats / 32) * sizeof(float);
+    if (b.NT > 0) {
+        const int LG = tile_labels(L), gpt = tile_granules(L);
+        const long long E = (long long)b.NT * D;
+        const int ngran = (int)((E + kTileGranule - 1) / kTileGranule);
+        const int grid = (ngran + gpt - 1) / gpt;
+        const size_t smem = (size_t)kTileFloats * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_staged<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        LCCRF_KERNEL(ctx, "k_splat_staged");
-        switch (LP) {
-            case 1: k_splat_staged<1><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
-            case 2: k_splat_staged<2><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
-            case 4: k_splat_staged<4><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
-            case 8: k_splat_staged<8><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
-            case 16: k_splat_staged<16><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
-            default: k_splat_staged<32><<<grid, kThreads, smem, st>>>(ls->row_ptr, ls->prod, src, vt, L); break;
+        LCCRF_KERNEL(ctx, "k_splat_tile");
+        switch (LG) {
+            case 1: k_splat_tile<1><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
+            case 2: k_splat_tile<2><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
+            default: k_splat_tile<4><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
         }
     }
-    {   // long rows: one CTA each, exact ordered scan
-        LCCRF_KERNEL(ctx, "k_splat_scan_cta");
-        k_splat_scan<8, 8><<<kNumSMs * 8, kThreads, 0, st>>>(ls->row_ptr, ls->prod, src, ls->row_list_long, ls->row_counts + 1, L);
+    // long rows: exact ordered scan, one CTA per (row, label): 256 threads for [kLongRow, kHugeRow), 1024 above.
+    // The lists live on the device, so the grids are sized for the worst case a lattice set can hold
+    // (rows of >= kLongRow entries: at most E / kLongRow) and capped at one wave.
+    if (b.NT > 0) {
+        const long long E = (long long)b.NT * D;
+        const long long max_med = (E / kLongRow) * L, max_huge = (E / kHugeRow) * L;
+        if (max_med > 0) {
+            const int grid = (int)(max_med < kNumSMs * 8 ? max_med : kNumSMs * 8);
+            LCCRF_KERNEL(ctx, "k_splat_scan_256");
+            k_splat_scan<8, 8><<<grid, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_med, ls->row_counts, L);
+        }
+        if (max_huge > 0) {
+            const int grid = (int)(max_huge < kNumSMs * 2 ? max_huge : kNumSMs * 2);
+            LCCRF_KERNEL(ctx, "k_splat_scan_1024");
+            k_splat_scan<32, 8><<<grid, 1024, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts + 1, L);
+        }
     }
     if (b.B >= 2 || b.maxN <= 32768) {  // one CTA per problem runs all D passes
         static bool attr_set = false;
         if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_blur_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kBlurFusedFloats * (int)sizeof(float)));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_blur_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurFusedBytes + 16));
             attr_set = true;
         }
         LCCRF_KERNEL(ctx, "k_blur_fused");
-        k_blur_fused<<<b.B, 1024, kBlurFusedFloats * sizeof(float), st>>>(ls->nbr, ls->Vcap, ls->vbase, src, dst, L, D);
+        k_blur_fused<<<b.B, 1024, kBlurFusedBytes + 16, st>>>(ls->nbr, ls->Vcap, ls->vbase, src, dst, L, D);
         *values_out = dst;
         LCCRF_CUDA(cudaGetLastError());
         return LCCRF_OK;

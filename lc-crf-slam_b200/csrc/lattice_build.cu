@@ -415,7 +415,6 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
     if (Lmax > 0) {
         rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * Lmax * sizeof(float));
         rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * Lmax * sizeof(float));
-        rc |= dev_alloc(ctx, (void **)&ls->prod, (nent * Lmax + 8) * sizeof(float));
     }
     rc |= dev_alloc(ctx, (void **)&ls->tab_base, (size_t)(b.B + 1) * sizeof(int));
     if (rc != LCCRF_OK) {
@@ -459,13 +458,11 @@ int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     if (L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "label count exceeds LCCRF_MAX_L");
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
-    dev_free(ctx, ls->prod);
-    ls->valA = ls->valB = ls->prod = nullptr;
+    ls->valA = ls->valB = nullptr;
     ls->Lmax = 0;
     int rc = LCCRF_OK;
     rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * L * sizeof(float));
     rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * L * sizeof(float));
-    rc |= dev_alloc(ctx, (void **)&ls->prod, ((size_t)(ls->NT > 0 ? ls->NT : 1) * ls->D * L + 8) * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
     ls->Lmax = L;
     return LCCRF_OK;
@@ -482,7 +479,6 @@ void lattice_set_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->norm);
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
-    dev_free(ctx, ls->prod);
     dev_free(ctx, ls->tab_base);
     csr_destroy(ctx, ls);
     delete ls;
@@ -492,17 +488,18 @@ int lattice_set_build(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *fea
     const int d = ls->d, D = ls->D;
     const long long slots = ls->tab_slots;
     const int NLEV = num_levels(d);
+    Ctx::BuildScratch &bs = ctx->bs[ctx->branch];
     for (int lev = 0; lev < NLEV; lev++) {
-        LCCRF_TRY(ctx_scratch(ctx, ctx->hash_keys[lev], (size_t)slots * sizeof(uint64_t)));
-        LCCRF_CUDA(cudaMemsetAsync(ctx->hash_keys[lev].p, 0, (size_t)slots * sizeof(uint64_t), ctx->stream));
+        LCCRF_TRY(ctx_scratch(ctx, bs.hash_keys[lev], (size_t)slots * sizeof(uint64_t)));
+        LCCRF_CUDA(cudaMemsetAsync(bs.hash_keys[lev].p, 0, (size_t)slots * sizeof(uint64_t), ctx->stream));
     }
-    LCCRF_TRY(ctx_scratch(ctx, ctx->hash_first, (size_t)slots * sizeof(int)));
-    LCCRF_CUDA(cudaMemsetAsync(ctx->hash_first.p, 0x7f, (size_t)slots * sizeof(int), ctx->stream));
-    LCCRF_TRY(ctx_scratch(ctx, ctx->hash_id, (size_t)slots * sizeof(int)));
+    LCCRF_TRY(ctx_scratch(ctx, bs.hash_first, (size_t)slots * sizeof(int)));
+    LCCRF_CUDA(cudaMemsetAsync(bs.hash_first.p, 0x7f, (size_t)slots * sizeof(int), ctx->stream));
+    LCCRF_TRY(ctx_scratch(ctx, bs.hash_id, (size_t)slots * sizeof(int)));
     const long long S = ((long long)b.NT + b.B) * D;
-    LCCRF_TRY(ctx_scratch(ctx, ctx->ent_slot, (size_t)S * sizeof(int)));
+    LCCRF_TRY(ctx_scratch(ctx, bs.ent_slot, (size_t)S * sizeof(int)));
     const int nblk = cdiv(S, kThreads);
-    LCCRF_TRY(ctx_scratch(ctx, ctx->blk_cnt, (size_t)(nblk + 1) * sizeof(int)));
+    LCCRF_TRY(ctx_scratch(ctx, bs.blk_cnt, (size_t)(nblk + 1) * sizeof(int)));
 
     BuildParams p;
     memset(&p, 0, sizeof(p));
@@ -511,11 +508,11 @@ int lattice_set_build(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *fea
     p.prob_ptr = b.prob_ptr;
     p.tab_base = ls->tab_base;
     p.feat = feat_dev;
-    for (int lev = 0; lev < NLEV; lev++) p.key[lev] = (uint64_t *)ctx->hash_keys[lev].p;
-    p.first = (int *)ctx->hash_first.p;
-    p.tab_id = (int *)ctx->hash_id.p;
-    p.ent_slot = (int *)ctx->ent_slot.p;
-    p.blk_cnt = (int *)ctx->blk_cnt.p;
+    for (int lev = 0; lev < NLEV; lev++) p.key[lev] = (uint64_t *)bs.hash_keys[lev].p;
+    p.first = (int *)bs.hash_first.p;
+    p.tab_id = (int *)bs.hash_id.p;
+    p.ent_slot = (int *)bs.ent_slot.p;
+    p.blk_cnt = (int *)bs.blk_cnt.p;
     p.bary = ls->bary;
     p.offset = ls->offset;
     p.nbr = ls->nbr;

@@ -22,6 +22,16 @@ __device__ __forceinline__ float very_fast_exp(float x) {
     return __fsub_rn(1.0f, __fmul_rn(x, p));
 }
 
+// The reference compares the float argument with DOUBLE thresholds (0.69*2*2*2 etc., densecrf3d.h:60-62).  For a
+// float x and a double c:  (double)x > c  <=>  x > fl(c), fl(c) = the largest float <= c (no float lies strictly
+// between fl(c) and c), so the comparisons run in fp32 with constants the compiler folds.  Dividing by 8, 4, 2 is
+// a multiplication by 0.125, 0.25, 0.5: scaling by a power of two rounds identically either way.
+__device__ __forceinline__ float float_at_or_below(double c) {
+    float t = (float)c;
+    if ((double)t > c) t = __int_as_float(__float_as_int(t) - 1);  // c > 0 here
+    return t;
+}
+
 __device__ __forceinline__ float fast_exp(float x) {
     bool lessZero = true;
     if (x < 0) {
@@ -29,18 +39,19 @@ __device__ __forceinline__ float fast_exp(float x) {
         x = -x;
     }
     if (x > 20) return 0;
+    const float t3 = float_at_or_below(0.69 * 2 * 2 * 2), t2 = float_at_or_below(0.69 * 2 * 2), t1 = float_at_or_below(0.69);
     int mult = 0;
-    while ((double)x > 0.69 * 2 * 2 * 2) {
+    while (x > t3) {
         mult += 3;
-        x = __fdiv_rn(x, 8.0f);
+        x = __fmul_rn(x, 0.125f);
     }
-    while ((double)x > 0.69 * 2 * 2) {
+    while (x > t2) {
         mult += 2;
-        x = __fdiv_rn(x, 4.0f);
+        x = __fmul_rn(x, 0.25f);
     }
-    while ((double)x > 0.69) {
+    while (x > t1) {
         mult++;
-        x = __fdiv_rn(x, 2.0f);
+        x = __fmul_rn(x, 0.5f);
     }
     x = very_fast_exp(x);
     while (mult) {
@@ -248,8 +259,15 @@ int mf_step(Ctx *ctx, Batch &b, float relax) {
     if (b.NT == 0) return LCCRF_OK;
     if (b.L == 2 && !b.lat.empty() && ctx->opt_fused) {
         // splat + blur of every lattice from the same Q, then ONE point pass
+        // (odd lattices on the aux branch: the filters of different lattices are independent)
         const float *vals[LCCRF_MAX_K];
-        for (size_t k = 0; k < b.lat.size(); k++) LCCRF_TRY(filter_splat_blur(ctx, b, b.lat[k], b.cur, 2, &vals[k]));
+        const bool par = b.lat.size() > 1;
+        if (par) LCCRF_TRY(ctx_fork(ctx));
+        for (size_t k = 0; k < b.lat.size(); k++) {
+            AuxScope aux(ctx, par && (k & 1));
+            LCCRF_TRY(filter_splat_blur(ctx, b, b.lat[k], b.cur, 2, &vals[k]));
+        }
+        if (par) LCCRF_TRY(ctx_join(ctx));
         return mf_point_pass_l2(ctx, b, vals, relax, false);
     }
     if (b.lat.empty()) LCCRF_TRY(mf_negate(ctx, b.next, b.unary, (long long)b.NT * b.L));
