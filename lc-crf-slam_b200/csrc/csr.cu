@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(kFillWarpsH * 32) k_csr_fill(CsrParams p) {
 // after g * kTileGranule.  Row v (v == V: the end sentinel, start = E) owns the granule boundaries in
 // (start of row v-1, start of row v]; the sentinel also fills the table's tail.
 __global__ void __launch_bounds__(kThreads)
-k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ med,
-               int *__restrict__ lng, int *__restrict__ counts, int *__restrict__ gran_row, int gran_n) {
+k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ lng,
+               int *__restrict__ counts, int *__restrict__ gran_row, int gran_n) {
     const int V = __ldg(vtotal);
     for (int v = blockIdx.x * kThreads + threadIdx.x; v <= V; v += gridDim.x * kThreads) {
         const int start = __ldg(row_ptr + v);
@@ -263,8 +263,59 @@ k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, 
         for (int g = g_lo; g <= g_hi; g++) gran_row[g] = v;
         if (v == V) break;
         const int len = __ldg(row_ptr + v + 1) - start;
-        if (len >= kHugeRow) lng[atomicAdd(counts + 1, 1)] = v;       // list order is irrelevant: rows are independent
-        else if (len >= kLongRow) med[atomicAdd(counts, 1)] = v;
+        if (len >= kLongRow) lng[atomicAdd(counts, 1)] = v;  // list order is irrelevant: rows are independent
+    }
+}
+
+// chunks of the long rows: long_chunk0 = exclusive scan of ceil(len / kScanChunk) over the long list, chunk_row[c] =
+// list index of the row that owns chunk c, counts[1] = number of chunks.  Single CTA (the list is short).
+__global__ void __launch_bounds__(1024)
+k_long_chunks(const int *__restrict__ row_ptr, const int *__restrict__ lng, int *__restrict__ counts,
+              int *__restrict__ long_chunk0, int *__restrict__ chunk_row) {
+    __shared__ int ws[32];
+    __shared__ int carry_s;
+    const int n = counts[0];
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int start = 0; start < n; start += 1024) {
+        const int i = start + threadIdx.x;
+        int nch = 0;
+        if (i < n) {
+            const int v = lng[i];
+            nch = (__ldg(row_ptr + v + 1) - __ldg(row_ptr + v) + kScanChunk - 1) / kScanChunk;
+        }
+        int x = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) ws[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int t = ws[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            ws[lane] = t;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int base = carry + (wid ? ws[wid - 1] : 0) + x - nch;
+        if (i < n) {
+            long_chunk0[i] = base;
+            for (int c = 0; c < nch; c++) chunk_row[base + c] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + ws[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        long_chunk0[n] = carry_s;
+        counts[1] = carry_s;
     }
 }
 
@@ -301,8 +352,14 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     rc |= dev_alloc(ctx, (void **)&ls->row_ptr, ((size_t)ls->Vcap + 2) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->csr_ent, (size_t)(b.NT > 0 ? b.NT : 1) * D * sizeof(int2));
     rc |= dev_alloc(ctx, (void **)&ls->scan_tot, ((size_t)ls->Vcap / 1024 + 2) * 4);
-    rc |= dev_alloc(ctx, (void **)&ls->row_list_med, ((size_t)ls->Vcap + 1) * 4);
-    rc |= dev_alloc(ctx, (void **)&ls->row_list_long, ((size_t)ls->Vcap + 1) * 4);
+    {   // long rows: at most E / kLongRow of them; their chunks: at most E / kScanChunk full ones + one partial per row
+        const long long E = (long long)b.NT * D;
+        ls->max_long = (int)(E / kLongRow);
+        ls->max_chunks = (int)(E / kScanChunk) + ls->max_long;
+    }
+    rc |= dev_alloc(ctx, (void **)&ls->row_list_long, ((size_t)ls->max_long + 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->long_chunk0, ((size_t)ls->max_long + 2) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->chunk_row, ((size_t)ls->max_chunks + 1) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->row_counts, 2 * 4);
     ls->gran_n = (int)(((long long)b.NT * D) / kTileGranule + 16);
     rc |= dev_alloc(ctx, (void **)&ls->gran_row, (size_t)ls->gran_n * 4);
@@ -329,8 +386,11 @@ void csr_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->row_ptr);
     dev_free(ctx, ls->csr_ent);
     dev_free(ctx, ls->scan_tot);
-    dev_free(ctx, ls->row_list_med);
     dev_free(ctx, ls->row_list_long);
+    dev_free(ctx, ls->long_chunk0);
+    dev_free(ctx, ls->chunk_row);
+    dev_free(ctx, ls->chunk_sum);
+    dev_free(ctx, ls->chunk_rec);
     dev_free(ctx, ls->row_counts);
     dev_free(ctx, ls->gran_row);
 }
@@ -373,7 +433,11 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
         { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<<<p.G, kFillWarpsH * 32, kCursorSmemInts * sizeof(int), st>>>(p); }
     }
     LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 2 * sizeof(int), st));
-    { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_med, ls->row_list_long, ls->row_counts, ls->gran_row, ls->gran_n); }
+    { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_long, ls->row_counts, ls->gran_row, ls->gran_n); }
+    if (ls->max_long > 0) {
+        LCCRF_KERNEL(ctx, "k_long_chunks");
+        k_long_chunks<<<1, 1024, 0, st>>>(ls->row_ptr, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row);
+    }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }

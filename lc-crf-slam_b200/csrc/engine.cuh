@@ -38,10 +38,14 @@ struct LatticeSet {
     int *chunk_prob = nullptr, *chunk_s0 = nullptr, *chunk_s1 = nullptr, *prob_chunk0 = nullptr;
     long long *chunk_tbl = nullptr;
     int *csr_tbl = nullptr, *scan_tot = nullptr;
-    // rows by length class (filled by csr_build): [0, kLongRow) lane-sequential, [kLongRow, kHugeRow) one 256-thread
-    // CTA per (row, label), [kHugeRow, ..) one 1024-thread CTA -- the latter two with the exact ordered scan (filter.cu)
-    int *row_list_med = nullptr, *row_list_long = nullptr;  // [Vcap] each
-    int *row_counts = nullptr;                              // [2] device: #medium, #huge
+    // long rows (>= kLongRow entries; filled by csr_build) and their chunks of kScanChunk entries (filter.cu: speculative scan)
+    int *row_list_long = nullptr;   // [max_long] vertex ids
+    int *row_counts = nullptr;      // [2] device: #long rows, #chunks
+    int *long_chunk0 = nullptr;     // [max_long+1] first chunk of each long row
+    int *chunk_row = nullptr;       // [max_chunks] long-list index of each chunk
+    float *chunk_sum = nullptr;     // [max_chunks*Lmax] unordered chunk sums (per filter call)
+    void *chunk_rec = nullptr;      // [max_chunks*Lmax] ChunkRec (per filter call)
+    int max_long = 0, max_chunks = 0;
     // gran_row[g] = first row whose first entry lies at or after g * kTileGranule (k_splat_tile windows)
     int *gran_row = nullptr;                                // [NT*D / kTileGranule + 16]
     int gran_n = 0;
@@ -51,8 +55,8 @@ struct LatticeSet {
 };
 
 constexpr int kCsrChunkPoints = 4096;  // points per chunk of the parallel stable counting sort
-constexpr int kLongRow = 1024;   // rows at least this long leave the lane-sequential kernel for the exact scan (256 threads)
-constexpr int kHugeRow = 16384;  // rows at least this long are scanned by 1024 threads
+constexpr int kLongRow = 1024;    // rows at least this long leave the staged lane-sequential kernel for the exact scan
+constexpr int kScanChunk = 2048;  // entries per chunk of a long row
 constexpr int kTileGranule = 2048;  // entry granularity of the k_splat_tile windows
 
 struct Batch {

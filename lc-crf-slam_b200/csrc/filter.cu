@@ -9,6 +9,7 @@
 //   k_slice   (:684-694)  out[i] = sum_r (bary*alpha) * values[v_r]  (association of the SSE overload).
 // The mean-field update fuses PottsPotential3D::apply (pairwise3d.h:73-78) into the slice.
 #include <cfloat>
+#include <climits>
 
 #include "engine.cuh"
 
@@ -355,45 +356,297 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__rest
     return s;
 }
 
-// One CTA per (row, label) task; rows come from a device-side list.  Binade crossings are densest at the start of a
-// row (the running sum doubles after 1, 2, 4, ... entries) and every crossing costs one re-scan of the rest of the
-// chunk, so the row is summed in stages by growing teams: the first kScanHead1 entries by warp 0 alone (cheap
-// re-scans), up to kScanHead2 by 8 warps, the rest by the whole CTA with its large chunks.
-constexpr int kScanHead1 = 2048, kScanHead2 = 16384;
+// ---------------------------------------------------------------- long rows: speculative parallel scan
+// A row of 67k entries is still one dependent chain if a single CTA walks it chunk by chunk.  But inside a binade
+// the effect of a whole chunk on the running sum is the pair composite (a_even, a_odd) -- it depends on the running
+// sum only through its binade (the ulp) and its parity.  The binade at the start of every chunk is predictable from
+// plain (unordered) chunk sums, so ALL chunks of ALL long rows are composed in parallel, and the sequential part
+// shrinks to one O(1) step per chunk:
+//   k_scan_sums     per (chunk, label): unordered fp32 sum of the chunk's products            (parallel)
+//   k_scan_compose  per (chunk, label): predicted start sum -> binade E; composite (a0, a1) of the chunk under that
+//                   binade and the range of start values for which no prefix leaves the binade (parallel)
+//   k_scan_walk     per (row, label): walks the chunk records; a record applies iff the true running sum is in
+//                   the predicted binade and inside the record's safe range -- then s <- (m + a_parity) * ulp,
+//                   exactly what the entry-by-entry additions would give.  Otherwise (the chunk that contains a
+//                   binade crossing, a mispredicted binade, the row head) the chunk is summed for real with
+//                   row_sum_exact.  Either way the result is the sequential fp32 sum, bit for bit.
+struct ChunkRec {
+    int E;                   // predicted binade (unbiased exponent of the running sum), INT_MIN = no composite
+    int a0, a1;              // total increment in ulps for an even / odd start mantissa
+    int lo0, hi0, lo1, hi1;  // extreme prefix increments for an even / odd start
+    int pad;
+};
 
-template <int NW, int IT>
-__global__ void __launch_bounds__(NW * 32)
-k_splat_scan(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-             float *__restrict__ val, const int *__restrict__ list, const int *__restrict__ count, int L) {
-    __shared__ ScanShared<NW> sh;
-    __shared__ ScanShared<8> sh8;
-    __shared__ ScanShared<1> sh1;
-    __shared__ float s_stage;
-    const long long n = (long long)__ldg(count) * L;
-    const int tid = threadIdx.x, wid = tid >> 5;
+struct ChunkGeom {
+    int e0, e1;   // entry range of the chunk
+    int first;    // index of the row's first chunk
+    int c;        // this chunk's global index
+};
+
+__device__ __forceinline__ ChunkGeom chunk_geom(int c, const int *__restrict__ row_ptr, const int *__restrict__ list,
+                                                const int *__restrict__ long_chunk0, const int *__restrict__ chunk_row) {
+    ChunkGeom g;
+    const int i = __ldg(chunk_row + c);
+    const int v = __ldg(list + i);
+    g.first = __ldg(long_chunk0 + i);
+    g.c = c;
+    g.e0 = __ldg(row_ptr + v) + (c - g.first) * kScanChunk;
+    g.e1 = min(g.e0 + kScanChunk, __ldg(row_ptr + v + 1));
+    return g;
+}
+
+constexpr int kScanIT = kScanChunk / 256;  // entries per thread of a 256-thread team
+
+__global__ void __launch_bounds__(256)
+k_scan_sums(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
+            const int *__restrict__ list, const int *__restrict__ counts, const int *__restrict__ long_chunk0,
+            const int *__restrict__ chunk_row, float *__restrict__ chunk_sum, int L) {
+    __shared__ float s_w[8];
+    const long long n = (long long)__ldg(counts + 1) * L;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
-        const int v = __ldg(list + (int)(k / L)), l = (int)(k % L);
-        const int e0 = __ldg(row_ptr + v), e1 = __ldg(row_ptr + v + 1);
-        float s = 0.0f;
-        int pos = min(e0 + kScanHead1, e1);
-        if (wid == 0) {
-            s = row_sum_exact<1, IT>(ent, in, e0, pos, L, l, tid, sh1, 0.0f);
-            if (tid == 0) s_stage = s;
+        const int c = (int)(k / L), l = (int)(k % L);
+        const ChunkGeom g = chunk_geom(c, row_ptr, list, long_chunk0, chunk_row);
+        int2 t[kScanIT];
+        float x[kScanIT];
+#pragma unroll
+        for (int q = 0; q < kScanIT; q++) {
+            const int e = g.e0 + q * 256 + tid;
+            t[q] = e < g.e1 ? __ldg(ent + e) : make_int2(0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < kScanIT; q++) {
+            const int e = g.e0 + q * 256 + tid;
+            x[q] = e < g.e1 ? __ldg(in + (size_t)t[q].x * L + l) : 0.0f;
+        }
+        float acc = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kScanIT; q++) acc += __int_as_float(t[q].y) * x[q];  // a prediction: any order will do
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_w[wid] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += s_w[w];
+            chunk_sum[k] = tot;
         }
         __syncthreads();
-        s = s_stage;
-        if (NW > 8 && pos < e1) {
-            const int h2 = min(e0 + kScanHead2, e1);
-            __syncthreads();  // everybody has read s_stage
-            if (wid < 8) {
-                s = row_sum_exact<8, IT>(ent, in, pos, h2, L, l, tid, sh8, s);
-                if (tid == 0) s_stage = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
+               const int *__restrict__ list, const int *__restrict__ counts, const int *__restrict__ long_chunk0,
+               const int *__restrict__ chunk_row, const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec, int L) {
+    constexpr int IT = kScanIT;
+    __shared__ double s_red[8];
+    __shared__ ScanPair s_wtot[8];
+    __shared__ int s_bnd[8][4];
+    __shared__ float s_pred;
+    const long long n = (long long)__ldg(counts + 1) * L;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (long long k = blockIdx.x; k < n; k += gridDim.x) {
+        const int c = (int)(k / L), l = (int)(k % L);
+        const ChunkGeom g = chunk_geom(c, row_ptr, list, long_chunk0, chunk_row);
+        if (c == g.first) continue;  // the row head is always summed for real (k_scan_walk)
+        // entries of this chunk (thread-contiguous: thread t owns entries [t*IT, (t+1)*IT) of the chunk)
+        int2 t[IT];
+        float x[IT];
+#pragma unroll
+        for (int q = 0; q < IT; q++) {
+            const int e = g.e0 + tid * IT + q;
+            t[q] = e < g.e1 ? __ldg(ent + e) : make_int2(0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < IT; q++) {
+            const int e = g.e0 + tid * IT + q;
+            x[q] = e < g.e1 ? __ldg(in + (size_t)t[q].x * L + l) : 0.0f;
+        }
+        // predicted running sum at the start of the chunk = sum of the previous chunks of the row
+        double part = 0.0;
+        for (int j = g.first + tid; j < c; j += 256) part += (double)__ldg(chunk_sum + (size_t)j * L + l);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_red[wid] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += s_red[w];
+            s_pred = (float)tot;
+        }
+        __syncthreads();
+        const float sp = s_pred;
+        const int E = ((__float_as_int(sp) >> 23) & 0xff) - 127;
+        if (!((sp > 0.0f) && E >= -100 && E <= 100)) {  // uniform
+            if (tid == 0) {
+                ChunkRec r;
+                r.E = INT_MIN;
+                r.a0 = r.a1 = r.lo0 = r.hi0 = r.lo1 = r.hi1 = r.pad = 0;
+                rec[k] = r;
             }
             __syncthreads();
-            s = s_stage;
-            pos = h2;
+            continue;
         }
-        if (pos < e1) s = row_sum_exact<NW, IT>(ent, in, pos, e1, L, l, tid, sh, s);
+        const float inv_u = __int_as_float((23 - E + 127) << 23);
+        // thread-local composition (same arithmetic as row_sum_exact)
+        ScanPair tot;
+        tot.a0 = tot.a1 = 0;
+        int hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+#pragma unroll
+        for (int q = 0; q < IT; q++) {
+            if (g.e0 + tid * IT + q < g.e1) {
+                const float cq = __fmul_rn(__int_as_float(t[q].y), x[q]);
+                const float qv = __fmul_rn(cq, inv_u);
+                int ni;
+                float fr = 0.0f;
+                if (!(fabsf(qv) < 16777216.0f)) {
+                    ni = qv > 0.0f ? (1 << 24) : -(1 << 24);
+                } else {
+                    ni = __float2int_rd(qv);
+                    fr = __fsub_rn(qv, (float)ni);
+                }
+                if (fr != 0.5f) {
+                    const int inc1 = ni + (fr > 0.5f ? 1 : 0);
+                    tot.a0 += inc1;
+                    tot.a1 += inc1;
+                } else {
+                    ScanPair a;
+                    a.a0 = ni + (ni & 1);
+                    a.a1 = ni + ((ni + 1) & 1);
+                    tot = scan_combine(tot, a);
+                }
+                hi0 = max(hi0, tot.a0);
+                lo0 = min(lo0, tot.a0);
+                hi1 = max(hi1, tot.a1);
+                lo1 = min(lo1, tot.a1);
+            }
+        }
+        // exclusive scan of the thread composites in thread order
+        ScanPair inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            ScanPair lft;
+            lft.a0 = __shfl_up_sync(0xffffffffu, inc.a0, o);
+            lft.a1 = __shfl_up_sync(0xffffffffu, inc.a1, o);
+            if (lane >= o) inc = scan_combine(lft, inc);
+        }
+        ScanPair exc;
+        exc.a0 = __shfl_up_sync(0xffffffffu, inc.a0, 1);
+        exc.a1 = __shfl_up_sync(0xffffffffu, inc.a1, 1);
+        if (lane == 0) exc.a0 = exc.a1 = 0;
+        if (lane == 31) s_wtot[wid] = inc;
+        __syncthreads();
+        ScanPair w = s_wtot[lane < 8 ? lane : 0];
+        if (lane >= 8) w.a0 = w.a1 = 0;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            ScanPair lft;
+            lft.a0 = __shfl_up_sync(0xffffffffu, w.a0, o);
+            lft.a1 = __shfl_up_sync(0xffffffffu, w.a1, o);
+            if (lane >= o) w = scan_combine(lft, w);
+        }
+        ScanPair wp;
+        wp.a0 = __shfl_sync(0xffffffffu, w.a0, wid > 0 ? wid - 1 : 0);
+        wp.a1 = __shfl_sync(0xffffffffu, w.a1, wid > 0 ? wid - 1 : 0);
+        if (wid > 0) exc = scan_combine(wp, exc);
+        const ScanPair all = {__shfl_sync(0xffffffffu, w.a0, 7), __shfl_sync(0xffffffffu, w.a1, 7)};  // whole chunk
+        // safe range: for a start of parity p this thread begins at offset exc.a_p with parity (p + exc.a_p) & 1
+        int b_lo0 = exc.a0 + ((exc.a0 & 1) ? lo1 : lo0), b_hi0 = exc.a0 + ((exc.a0 & 1) ? hi1 : hi0);
+        int b_lo1 = exc.a1 + ((exc.a1 & 1) ? lo0 : lo1), b_hi1 = exc.a1 + ((exc.a1 & 1) ? hi0 : hi1);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            b_lo0 = min(b_lo0, __shfl_xor_sync(0xffffffffu, b_lo0, o));
+            b_hi0 = max(b_hi0, __shfl_xor_sync(0xffffffffu, b_hi0, o));
+            b_lo1 = min(b_lo1, __shfl_xor_sync(0xffffffffu, b_lo1, o));
+            b_hi1 = max(b_hi1, __shfl_xor_sync(0xffffffffu, b_hi1, o));
+        }
+        if (lane == 0) {
+            s_bnd[wid][0] = b_lo0;
+            s_bnd[wid][1] = b_hi0;
+            s_bnd[wid][2] = b_lo1;
+            s_bnd[wid][3] = b_hi1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ChunkRec r;
+            r.E = E;
+            r.a0 = all.a0;
+            r.a1 = all.a1;
+            r.lo0 = s_bnd[0][0];
+            r.hi0 = s_bnd[0][1];
+            r.lo1 = s_bnd[0][2];
+            r.hi1 = s_bnd[0][3];
+#pragma unroll
+            for (int w8 = 1; w8 < 8; w8++) {
+                r.lo0 = min(r.lo0, s_bnd[w8][0]);
+                r.hi0 = max(r.hi0, s_bnd[w8][1]);
+                r.lo1 = min(r.lo1, s_bnd[w8][2]);
+                r.hi1 = max(r.hi1, s_bnd[w8][3]);
+            }
+            r.pad = 0;
+            rec[k] = r;
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int kWalkBatch = 256;  // chunk records staged per round
+
+__global__ void __launch_bounds__(256)
+k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
+            float *__restrict__ val, const int *__restrict__ list, const int *__restrict__ counts,
+            const int *__restrict__ long_chunk0, const ChunkRec *__restrict__ rec, int L) {
+    __shared__ ScanShared<8> sh;
+    __shared__ ScanShared<1> sh1;
+    __shared__ float s_stage;
+    __shared__ ChunkRec s_rec[kWalkBatch];
+    const long long n = (long long)__ldg(counts) * L;
+    const int tid = threadIdx.x, wid = tid >> 5;
+    for (long long k = blockIdx.x; k < n; k += gridDim.x) {
+        const int i = (int)(k / L), l = (int)(k % L);
+        const int v = __ldg(list + i);
+        const int e0 = __ldg(row_ptr + v), e1 = __ldg(row_ptr + v + 1);
+        const int c0 = __ldg(long_chunk0 + i), nch = __ldg(long_chunk0 + i + 1) - c0;
+        // row head: binade crossings are dense here (the sum doubles after 1, 2, 4, ... entries); one warp sums it
+        // with cheap warp-level re-scans
+        float s = 0.0f;
+        if (wid == 0) {
+            s = row_sum_exact<1, kScanIT>(ent, in, e0, min(e0 + kScanChunk, e1), L, l, tid, sh1, 0.0f);
+            if (tid == 0) s_stage = s;
+        }
+        for (int cb = 1; cb < nch; cb += kWalkBatch) {
+            const int nb = min(kWalkBatch, nch - cb);
+            __syncthreads();  // s_stage visible (first round); previous round's records consumed
+            if (tid < nb) s_rec[tid] = rec[(size_t)(c0 + cb + tid) * L + l];
+            if (cb == 1) s = s_stage;
+            __syncthreads();
+            for (int j = 0; j < nb; j++) {
+                const ChunkRec r = s_rec[j];
+                const int E = ((__float_as_int(s) >> 23) & 0xff) - 127;
+                bool fast = false;
+                if ((s > 0.0f) && E >= -100 && E <= 100 && E == r.E) {
+                    const float u = __int_as_float((E - 23 + 127) << 23);
+                    const float inv_u = __int_as_float((23 - E + 127) << 23);
+                    const int m0 = (int)__fmul_rn(s, inv_u);  // in [2^23, 2^24)
+                    const int lo = (m0 & 1) ? r.lo1 : r.lo0, hi = (m0 & 1) ? r.hi1 : r.hi0;
+                    if (m0 + lo >= (1 << 23) && m0 + hi < (1 << 24)) {
+                        s = __fmul_rn((float)(m0 + ((m0 & 1) ? r.a1 : r.a0)), u);
+                        fast = true;
+                    }
+                }
+                if (!fast) {  // uniform: s and the record are identical in every thread
+                    const int a = e0 + (cb + j) * kScanChunk;
+                    s = row_sum_exact<8, kScanIT>(ent, in, a, min(a + kScanChunk, e1), L, l, tid, sh, s);
+                }
+            }
+        }
+        if (nch <= 1) {
+            __syncthreads();
+            s = s_stage;
+        }
         if (tid == 0) val[(size_t)v * L + l] = s;
         __syncthreads();
     }
@@ -558,22 +811,18 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
             default: k_splat_tile<4><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
         }
     }
-    // long rows: exact ordered scan, one CTA per (row, label): 256 threads for [kLongRow, kHugeRow), 1024 above.
-    // The lists live on the device, so the grids are sized for the worst case a lattice set can hold
-    // (rows of >= kLongRow entries: at most E / kLongRow) and capped at one wave.
-    if (b.NT > 0) {
-        const long long E = (long long)b.NT * D;
-        const long long max_med = (E / kLongRow) * L, max_huge = (E / kHugeRow) * L;
-        if (max_med > 0) {
-            const int grid = (int)(max_med < kNumSMs * 8 ? max_med : kNumSMs * 8);
-            LCCRF_KERNEL(ctx, "k_splat_scan_256");
-            k_splat_scan<8, 8><<<grid, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_med, ls->row_counts, L);
-        }
-        if (max_huge > 0) {
-            const int grid = (int)(max_huge < kNumSMs * 2 ? max_huge : kNumSMs * 2);
-            LCCRF_KERNEL(ctx, "k_splat_scan_1024");
-            k_splat_scan<32, 8><<<grid, 1024, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts + 1, L);
-        }
+    // long rows (>= kLongRow entries): speculative parallel scan.  The lists live on the device, so the grids are
+    // sized for the worst case a lattice set can hold and capped at a few waves (grid-stride inside).
+    if (b.NT > 0 && ls->max_chunks > 0) {
+        const long long maxc = (long long)ls->max_chunks * L, maxr = (long long)ls->max_long * L;
+        const int gc = (int)(maxc < kNumSMs * 16 ? maxc : kNumSMs * 16);
+        const int gr = (int)(maxr < kNumSMs * 8 ? maxr : kNumSMs * 8);
+        { LCCRF_KERNEL(ctx, "k_scan_sums");
+          k_scan_sums<<<gc, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row, ls->chunk_sum, L); }
+        { LCCRF_KERNEL(ctx, "k_scan_compose");
+          k_scan_compose<<<gc, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L); }
+        { LCCRF_KERNEL(ctx, "k_scan_walk");
+          k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, L); }
     }
     if (b.B >= 2 || b.maxN <= 32768) {  // one CTA per problem runs all D passes
         static bool attr_set = false;

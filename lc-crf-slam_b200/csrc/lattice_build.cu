@@ -417,6 +417,14 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
         rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * Lmax * sizeof(float));
     }
     rc |= dev_alloc(ctx, (void **)&ls->tab_base, (size_t)(b.B + 1) * sizeof(int));
+    {
+        const long long E = (long long)b.NT * ls->D;
+        const size_t mc = (size_t)(E / kScanChunk + E / kLongRow) + 1;
+        if (Lmax > 0) {
+            rc |= dev_alloc(ctx, (void **)&ls->chunk_sum, mc * Lmax * sizeof(float));
+            rc |= dev_alloc(ctx, (void **)&ls->chunk_rec, mc * Lmax * 32);
+        }
+    }
     if (rc != LCCRF_OK) {
         lattice_set_destroy(ctx, ls);
         return LCCRF_ERR_CUDA;
@@ -458,9 +466,18 @@ int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     if (L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "label count exceeds LCCRF_MAX_L");
     dev_free(ctx, ls->valA);
     dev_free(ctx, ls->valB);
+    dev_free(ctx, ls->chunk_sum);
+    dev_free(ctx, ls->chunk_rec);
     ls->valA = ls->valB = nullptr;
+    ls->chunk_sum = nullptr;
+    ls->chunk_rec = nullptr;
     ls->Lmax = 0;
     int rc = LCCRF_OK;
+    {
+        const size_t mc = (size_t)ls->max_chunks + 1;
+        rc |= dev_alloc(ctx, (void **)&ls->chunk_sum, mc * L * sizeof(float));
+        rc |= dev_alloc(ctx, (void **)&ls->chunk_rec, mc * L * 32);
+    }
     rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * L * sizeof(float));
     rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * L * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
