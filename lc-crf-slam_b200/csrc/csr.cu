@@ -249,21 +249,26 @@ __global__ void __launch_bounds__(kFillWarpsH * 32) k_csr_fill(CsrParams p) {
     }
 }
 
-// rows by length class + the granule table of k_splat_tile: gran_row[g] = first row whose first entry lies at or
-// after g * kTileGranule.  Row v (v == V: the end sentinel, start = E) owns the granule boundaries in
-// (start of row v-1, start of row v]; the sentinel also fills the table's tail.
+// rows by length class: long rows (>= kLongRow entries) go to the speculative scan; the short ones are grouped
+// into pieces for k_splat_tile -- a piece starts at a short row that is the first row, follows a long row, or is the
+// first to start in its granule of kTileGranule entries.  List order is irrelevant: rows / pieces are independent.
 __global__ void __launch_bounds__(kThreads)
 k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ lng,
-               int *__restrict__ counts, int *__restrict__ gran_row, int gran_n) {
+               int *__restrict__ counts, int *__restrict__ piece_list) {
     const int V = __ldg(vtotal);
-    for (int v = blockIdx.x * kThreads + threadIdx.x; v <= V; v += gridDim.x * kThreads) {
+    for (int v = blockIdx.x * kThreads + threadIdx.x; v < V; v += gridDim.x * kThreads) {
         const int start = __ldg(row_ptr + v);
-        const int g_lo = v == 0 ? 0 : __ldg(row_ptr + v - 1) / kTileGranule + 1;  // first boundary > previous start
-        const int g_hi = v == V ? gran_n - 1 : start / kTileGranule;             // last boundary <= start
-        for (int g = g_lo; g <= g_hi; g++) gran_row[g] = v;
-        if (v == V) break;
         const int len = __ldg(row_ptr + v + 1) - start;
-        if (len >= kLongRow) lng[atomicAdd(counts, 1)] = v;  // list order is irrelevant: rows are independent
+        if (len >= kLongRow) {
+            lng[atomicAdd(counts, 1)] = v;
+        } else {
+            bool first = v == 0;
+            if (!first) {
+                const int pstart = __ldg(row_ptr + v - 1);
+                first = (start - pstart >= kLongRow) || (start / kTileGranule != pstart / kTileGranule);
+            }
+            if (first) piece_list[atomicAdd(counts + 2, 1)] = v;
+        }
     }
 }
 
@@ -360,9 +365,9 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     rc |= dev_alloc(ctx, (void **)&ls->row_list_long, ((size_t)ls->max_long + 1) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->long_chunk0, ((size_t)ls->max_long + 2) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->chunk_row, ((size_t)ls->max_chunks + 1) * 4);
-    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 2 * 4);
-    ls->gran_n = (int)(((long long)b.NT * D) / kTileGranule + 16);
-    rc |= dev_alloc(ctx, (void **)&ls->gran_row, (size_t)ls->gran_n * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 4 * 4);
+    ls->max_pieces = (int)(((long long)b.NT * D) / kTileGranule + ((long long)b.NT * D) / kLongRow + 2);
+    rc |= dev_alloc(ctx, (void **)&ls->piece_list, (size_t)ls->max_pieces * 4);
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
     cudaStream_t st = ctx->stream;
     if (ls->csr_chunks > 0) {
@@ -392,7 +397,7 @@ void csr_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->chunk_sum);
     dev_free(ctx, ls->chunk_rec);
     dev_free(ctx, ls->row_counts);
-    dev_free(ctx, ls->gran_row);
+    dev_free(ctx, ls->piece_list);
 }
 
 int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
@@ -432,8 +437,8 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
         }
         { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<<<p.G, kFillWarpsH * 32, kCursorSmemInts * sizeof(int), st>>>(p); }
     }
-    LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 2 * sizeof(int), st));
-    { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_long, ls->row_counts, ls->gran_row, ls->gran_n); }
+    LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 4 * sizeof(int), st));
+    { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_long, ls->row_counts, ls->piece_list); }
     if (ls->max_long > 0) {
         LCCRF_KERNEL(ctx, "k_long_chunks");
         k_long_chunks<<<1, 1024, 0, st>>>(ls->row_ptr, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row);

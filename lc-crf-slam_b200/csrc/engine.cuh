@@ -40,15 +40,15 @@ struct LatticeSet {
     int *csr_tbl = nullptr, *scan_tot = nullptr;
     // long rows (>= kLongRow entries; filled by csr_build) and their chunks of kScanChunk entries (filter.cu: speculative scan)
     int *row_list_long = nullptr;   // [max_long] vertex ids
-    int *row_counts = nullptr;      // [2] device: #long rows, #chunks
+    int *row_counts = nullptr;      // [4] device: #long rows, #chunks, #pieces
     int *long_chunk0 = nullptr;     // [max_long+1] first chunk of each long row
     int *chunk_row = nullptr;       // [max_chunks] long-list index of each chunk
     float *chunk_sum = nullptr;     // [max_chunks*Lmax] unordered chunk sums (per filter call)
     void *chunk_rec = nullptr;      // [max_chunks*Lmax] ChunkRec (per filter call)
     int max_long = 0, max_chunks = 0;
-    // gran_row[g] = first row whose first entry lies at or after g * kTileGranule (k_splat_tile windows)
-    int *gran_row = nullptr;                                // [NT*D / kTileGranule + 16]
-    int gran_n = 0;
+    // pieces of k_splat_tile: first rows of the maximal runs of short rows that start in one kTileGranule granule
+    int *piece_list = nullptr;      // [max_pieces]
+    int max_pieces = 0;
     // filter workspace
     float *valA = nullptr, *valB = nullptr;  // [Vcap*Lmax] blur ping-pong
     int Lmax = 0;
@@ -57,6 +57,7 @@ struct LatticeSet {
 constexpr int kCsrChunkPoints = 4096;  // points per chunk of the parallel stable counting sort
 constexpr int kLongRow = 1024;    // rows at least this long leave the staged lane-sequential kernel for the exact scan
 constexpr int kScanChunk = 2048;  // entries per chunk of a long row
+constexpr int kChunkRecBytes = 16 + 2 * 24 + 4 * (kScanChunk / 256) * 4;  // sizeof(ChunkRec) of filter.cu
 constexpr int kTileGranule = 2048;  // entry granularity of the k_splat_tile windows
 
 struct Batch {

@@ -21,111 +21,114 @@ namespace {
 // Segmented reduction over the vertex-sorted entries (csr.cu).  values[v][l] = (((0 + w0*x0) + w1*x1) + ...)
 // over the row of v in point order, every product and sum individually rounded -- the reference's splat loop
 // (:653-661) bit for bit.  Two kernels, both gathering in[point] themselves (no intermediate product array):
-//   k_splat_tile   rows shorter than kLongRow.  A CTA owns a window of the entry list (a few granules of
-//                  kTileGranule entries) = the rows that START inside it.  Phase 1: all threads stream the window's
-//                  entries (coalesced), gather in[point] and park the products in shared memory -- every load is
-//                  independent, so the whole window costs about two memory round trips.  Phase 2: lane (row, label)
-//                  adds its row front to back from shared memory: the ordered FADD chain never waits on DRAM.
+//   k_splat_tile   rows shorter than kLongRow.  A CTA owns a piece = a run of consecutive short rows that start in one
+//                  granule of kTileGranule entries.  Phase 1: all threads stream the piece's entries (coalesced),
+//                  gather in[point] and park the products in shared memory -- every load is independent, so the
+//                  piece costs about two memory round trips.  Phase 2: lane (row, label) adds its row front to
+//                  back from shared memory: the ordered FADD chain never waits on DRAM.
 //   k_splat_scan   rows of kLongRow entries and more: exact parallel scan (below), one CTA per (row, label)
-constexpr int kTileFloats = 14336;      // staged products per CTA (56 KB): 3-4 CTAs per SM
 constexpr int kTileRows = 1024;         // rows per staging round
 constexpr int kTileThreads = 256;
-constexpr int kTileBatch = 16;          // entries per thread whose loads are issued before the first use
+constexpr int kTileBatch = 12;          // entries per thread whose loads are issued before the first use
+static_assert(kTileBatch * kTileThreads >= kTileGranule + kLongRow, "one batch covers a piece");
 
-// labels staged per pass and window length (in granules) for a given L
+// labels staged per pass
 static inline int tile_labels(int L) { return L <= 2 ? L : 4; }
-static inline int tile_granules(int L) { return (kTileFloats / tile_labels(L) - kLongRow) / kTileGranule; }
 
+// A piece (csr.cu: k_row_classify) = a maximal run of consecutive short rows whose first entries lie in one
+// granule of kTileGranule entries: at most kTileGranule + kLongRow - 1 entries, any number of rows.
 template <int LG>  // labels per pass (1, 2 or 4)
 __global__ void __launch_bounds__(kTileThreads)
-k_splat_tile(const int *__restrict__ row_ptr, const int *__restrict__ gran_row, const int2 *__restrict__ ent,
-             const float *__restrict__ in, float *__restrict__ val, int granules_per_tile, int L) {
+k_splat_tile(const int *__restrict__ row_ptr, const int *__restrict__ piece_list, const int *__restrict__ counts,
+             const int *__restrict__ vtotal, const int2 *__restrict__ ent, const float *__restrict__ in,
+             float *__restrict__ val, int L) {
     extern __shared__ float s_prod[];          // [entry][LG]
     __shared__ int s_rp[kTileRows + 1];        // row starts of the current round
-    __shared__ int s_first_long;
+    __shared__ int s_first_end;
     const int tid = threadIdx.x;
-    const int g0 = blockIdx.x * granules_per_tile;
-    const int v0 = __ldg(gran_row + g0), v1 = __ldg(gran_row + g0 + granules_per_tile);
-    int vcur = v0;
-    while (vcur < v1) {  // rounds: maximal runs of consecutive short rows, at most kTileRows each (usually one round)
-        const int nr_try = min(kTileRows, v1 - vcur);
-        if (tid == 0) s_first_long = nr_try;
-        __syncthreads();
-        for (int r = tid; r <= nr_try; r += kTileThreads) s_rp[r] = __ldg(row_ptr + vcur + r);
-        __syncthreads();
-        for (int r = tid; r < nr_try; r += kTileThreads)
-            if (s_rp[r + 1] - s_rp[r] >= kLongRow) atomicMin(&s_first_long, r);
-        __syncthreads();
-        const int nr = s_first_long;
-        if (nr == 0) {  // a long row: k_splat_scan owns it
-            vcur++;
+    const int V = __ldg(vtotal);
+    const int npieces = __ldg(counts + 2);
+    for (int pc = blockIdx.x; pc < npieces; pc += gridDim.x) {
+        int vcur = __ldg(piece_list + pc);
+        const int gran = __ldg(row_ptr + vcur) / kTileGranule;
+        for (;;) {  // rounds of at most kTileRows rows (usually one)
+            const int nr_try = min(kTileRows, V - vcur);
+            if (tid == 0) s_first_end = nr_try;
             __syncthreads();
-            continue;
-        }
-        const int eb = s_rp[0], cnt = s_rp[nr] - eb;  // cnt < window + kLongRow: the rows start inside the window
-        for (int lb = 0; lb < L; lb += LG) {
-            // phase 1: products of the round's entries -> shared memory
-            for (int i0 = 0; i0 < cnt; i0 += kTileThreads * kTileBatch) {
-                int2 t[kTileBatch];
-#pragma unroll
-                for (int q = 0; q < kTileBatch; q++) {
-                    const int i = i0 + q * kTileThreads + tid;
-                    t[q] = i < cnt ? __ldg(ent + eb + i) : make_int2(0, 0);
-                }
-                if (LG == 2) {
-                    float2 x[kTileBatch];
+            for (int r = tid; r <= nr_try; r += kTileThreads) s_rp[r] = __ldg(row_ptr + vcur + r);
+            __syncthreads();
+            for (int r = tid; r < nr_try; r += kTileThreads)
+                if (s_rp[r + 1] - s_rp[r] >= kLongRow || s_rp[r] / kTileGranule != gran) atomicMin(&s_first_end, r);
+            __syncthreads();
+            const int nr = s_first_end;
+            if (nr == 0) break;  // (uniform) the piece ended exactly at a round boundary
+            const int eb = s_rp[0], cnt = s_rp[nr] - eb;  // cnt < kTileGranule + kLongRow
+            for (int lb = 0; lb < L; lb += LG) {
+                // phase 1: products of the round's entries -> shared memory, every load independent
+                {
+                    int2 t[kTileBatch];
 #pragma unroll
                     for (int q = 0; q < kTileBatch; q++) {
-                        const int i = i0 + q * kTileThreads + tid;
-                        x[q] = i < cnt ? __ldg((const float2 *)(in + (size_t)t[q].x * L + lb)) : make_float2(0.f, 0.f);
+                        const int i = q * kTileThreads + tid;
+                        t[q] = i < cnt ? __ldg(ent + eb + i) : make_int2(0, 0);
                     }
+                    if (LG == 2) {
+                        float2 x[kTileBatch];
 #pragma unroll
-                    for (int q = 0; q < kTileBatch; q++) {
-                        const int i = i0 + q * kTileThreads + tid;
-                        const float w = __int_as_float(t[q].y);
-                        if (i < cnt) ((float2 *)s_prod)[i] = make_float2(__fmul_rn(w, x[q].x), __fmul_rn(w, x[q].y));
-                    }
-                } else {
-                    float x[kTileBatch][LG];
+                        for (int q = 0; q < kTileBatch; q++) {
+                            const int i = q * kTileThreads + tid;
+                            x[q] = i < cnt ? __ldg((const float2 *)(in + (size_t)t[q].x * L + lb)) : make_float2(0.f, 0.f);
+                        }
 #pragma unroll
-                    for (int q = 0; q < kTileBatch; q++) {
-                        const int i = i0 + q * kTileThreads + tid;
+                        for (int q = 0; q < kTileBatch; q++) {
+                            const int i = q * kTileThreads + tid;
+                            const float w = __int_as_float(t[q].y);
+                            if (i < cnt) ((float2 *)s_prod)[i] = make_float2(__fmul_rn(w, x[q].x), __fmul_rn(w, x[q].y));
+                        }
+                    } else {
+                        float x[kTileBatch][LG];
 #pragma unroll
-                        for (int j = 0; j < LG; j++)
-                            x[q][j] = (i < cnt && lb + j < L) ? __ldg(in + (size_t)t[q].x * L + lb + j) : 0.0f;
-                    }
+                        for (int q = 0; q < kTileBatch; q++) {
+                            const int i = q * kTileThreads + tid;
 #pragma unroll
-                    for (int q = 0; q < kTileBatch; q++) {
-                        const int i = i0 + q * kTileThreads + tid;
-                        const float w = __int_as_float(t[q].y);
-                        if (i < cnt) {
+                            for (int j = 0; j < LG; j++)
+                                x[q][j] = (i < cnt && lb + j < L) ? __ldg(in + (size_t)t[q].x * L + lb + j) : 0.0f;
+                        }
 #pragma unroll
-                            for (int j = 0; j < LG; j++) s_prod[(size_t)i * LG + j] = __fmul_rn(w, x[q][j]);
+                        for (int q = 0; q < kTileBatch; q++) {
+                            const int i = q * kTileThreads + tid;
+                            const float w = __int_as_float(t[q].y);
+                            if (i < cnt) {
+#pragma unroll
+                                for (int j = 0; j < LG; j++) s_prod[(size_t)i * LG + j] = __fmul_rn(w, x[q][j]);
+                            }
                         }
                     }
                 }
-            }
-            __syncthreads();
-            // phase 2: ordered accumulation, one lane per (row, label)
-            for (int idx = tid; idx < nr * LG; idx += kTileThreads) {
-                const int r = idx / LG, j = idx - r * LG;
-                if (lb + j >= L) continue;
-                const int a = s_rp[r] - eb, z = s_rp[r + 1] - eb;
-                float acc = 0.0f;
-                int e = a;
-                for (; e + 8 <= z; e += 8) {  // independent shared loads first, then the ordered chain
-                    float y[8];
+                __syncthreads();
+                // phase 2: ordered accumulation, one lane per (row, label)
+                for (int idx = tid; idx < nr * LG; idx += kTileThreads) {
+                    const int r = idx / LG, j = idx - r * LG;
+                    if (lb + j >= L) continue;
+                    const int a = s_rp[r] - eb, z = s_rp[r + 1] - eb;
+                    float acc = 0.0f;
+                    int e = a;
+                    for (; e + 8 <= z; e += 8) {  // independent shared loads first, then the ordered chain
+                        float y[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) y[q] = s_prod[(size_t)(e + q) * LG + j];
+                        for (int q = 0; q < 8; q++) y[q] = s_prod[(size_t)(e + q) * LG + j];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, y[q]);
+                        for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, y[q]);
+                    }
+                    for (; e < z; e++) acc = __fadd_rn(acc, s_prod[(size_t)e * LG + j]);
+                    val[(size_t)(vcur + r) * L + lb + j] = acc;
                 }
-                for (; e < z; e++) acc = __fadd_rn(acc, s_prod[(size_t)e * LG + j]);
-                val[(size_t)(vcur + r) * L + lb + j] = acc;
+                __syncthreads();
             }
-            __syncthreads();
+            vcur += nr;
+            if (nr < nr_try || vcur >= V) break;  // a boundary (long row / next granule / end) closed the piece
         }
-        vcur += nr;
+        __syncthreads();
     }
 }
 
@@ -370,12 +373,29 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__rest
 //                   exactly what the entry-by-entry additions would give.  Otherwise (the chunk that contains a
 //                   binade crossing, a mispredicted binade, the row head) the chunk is summed for real with
 //                   row_sum_exact.  Either way the result is the sequential fp32 sum, bit for bit.
-struct ChunkRec {
-    int E;                   // predicted binade (unbiased exponent of the running sum), INT_MIN = no composite
+// One record per (chunk, label).  kind:
+//   kRecNone   no composite (irregular prediction): the walk sums the chunk for real
+//   kRecExact  s_exact = the exact running sum at the END of the chunk (row heads: the start value 0 is known)
+//   kRecPlain  composite A covers the whole chunk under binade E
+//   kRecCross  the running sum is predicted to cross from binade E to E+1 inside the chunk: composite A covers the
+//              threads before the crossing window (binade E), win[] holds the kWinEntries products of the window
+//              (added for real by the walk), composite B covers the threads behind it (binade E+1)
+enum { kRecNone = 0, kRecExact = 1, kRecPlain = 2, kRecCross = 3 };
+constexpr int kWinThreads = 4;                     // threads of the compose team covered by the crossing window
+struct Composite {
     int a0, a1;              // total increment in ulps for an even / odd start mantissa
     int lo0, hi0, lo1, hi1;  // extreme prefix increments for an even / odd start
-    int pad;
 };
+struct ChunkRec {
+    int kind;
+    int E;            // predicted binade (unbiased exponent of the running sum) at the start of the chunk
+    float s_exact;
+    int pad;
+    Composite A, B;
+    float win[kWinThreads * (kScanChunk / 256)];
+};
+
+static_assert(sizeof(ChunkRec) == kChunkRecBytes, "engine.cuh: kChunkRecBytes must match ChunkRec");
 
 struct ChunkGeom {
     int e0, e1;   // entry range of the chunk
@@ -436,21 +456,147 @@ k_scan_sums(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
     }
 }
 
+// block-wide composite of the per-thread composites of the threads in [t_lo, t_hi) (others contribute the identity):
+// returns, in every thread, the composite of the whole range and its safe start range.  256 threads.
+struct ComposeShared {
+    ScanPair wtot[8];
+    int bnd[8][4];
+};
+__device__ __forceinline__ Composite block_composite(ScanPair tot, int hi0, int lo0, int hi1, int lo1, bool active,
+                                                     int tid, ComposeShared &sh) {
+    const int lane = tid & 31, wid = tid >> 5;
+    if (!active) {
+        tot.a0 = tot.a1 = 0;
+        hi0 = lo0 = hi1 = lo1 = 0;
+    }
+    ScanPair inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        ScanPair lft;
+        lft.a0 = __shfl_up_sync(0xffffffffu, inc.a0, o);
+        lft.a1 = __shfl_up_sync(0xffffffffu, inc.a1, o);
+        if (lane >= o) inc = scan_combine(lft, inc);
+    }
+    ScanPair exc;
+    exc.a0 = __shfl_up_sync(0xffffffffu, inc.a0, 1);
+    exc.a1 = __shfl_up_sync(0xffffffffu, inc.a1, 1);
+    if (lane == 0) exc.a0 = exc.a1 = 0;
+    __syncthreads();  // previous use of sh is over
+    if (lane == 31) sh.wtot[wid] = inc;
+    __syncthreads();
+    ScanPair w = sh.wtot[lane < 8 ? lane : 0];
+    if (lane >= 8) w.a0 = w.a1 = 0;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        ScanPair lft;
+        lft.a0 = __shfl_up_sync(0xffffffffu, w.a0, o);
+        lft.a1 = __shfl_up_sync(0xffffffffu, w.a1, o);
+        if (lane >= o) w = scan_combine(lft, w);
+    }
+    ScanPair wp;
+    wp.a0 = __shfl_sync(0xffffffffu, w.a0, wid > 0 ? wid - 1 : 0);
+    wp.a1 = __shfl_sync(0xffffffffu, w.a1, wid > 0 ? wid - 1 : 0);
+    if (wid > 0) exc = scan_combine(wp, exc);
+    Composite c;
+    c.a0 = __shfl_sync(0xffffffffu, w.a0, 7);
+    c.a1 = __shfl_sync(0xffffffffu, w.a1, 7);
+    // safe range: for a start of parity p this thread begins at offset exc.a_p with parity (p + exc.a_p) & 1
+    int b_lo0 = exc.a0 + ((exc.a0 & 1) ? lo1 : lo0), b_hi0 = exc.a0 + ((exc.a0 & 1) ? hi1 : hi0);
+    int b_lo1 = exc.a1 + ((exc.a1 & 1) ? lo0 : lo1), b_hi1 = exc.a1 + ((exc.a1 & 1) ? hi0 : hi1);
+    if (!active) {  // identity threads must not widen the range with offsets of ranges they do not belong to
+        b_lo0 = b_lo1 = INT_MAX;
+        b_hi0 = b_hi1 = INT_MIN;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        b_lo0 = min(b_lo0, __shfl_xor_sync(0xffffffffu, b_lo0, o));
+        b_hi0 = max(b_hi0, __shfl_xor_sync(0xffffffffu, b_hi0, o));
+        b_lo1 = min(b_lo1, __shfl_xor_sync(0xffffffffu, b_lo1, o));
+        b_hi1 = max(b_hi1, __shfl_xor_sync(0xffffffffu, b_hi1, o));
+    }
+    if (lane == 0) {
+        sh.bnd[wid][0] = b_lo0;
+        sh.bnd[wid][1] = b_hi0;
+        sh.bnd[wid][2] = b_lo1;
+        sh.bnd[wid][3] = b_hi1;
+    }
+    __syncthreads();
+    c.lo0 = c.lo1 = 0;  // the start itself is a prefix
+    c.hi0 = c.hi1 = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) {
+        c.lo0 = min(c.lo0, sh.bnd[w8][0]);
+        c.hi0 = max(c.hi0, sh.bnd[w8][1]);
+        c.lo1 = min(c.lo1, sh.bnd[w8][2]);
+        c.hi1 = max(c.hi1, sh.bnd[w8][3]);
+    }
+    return c;
+}
+
+// per-thread composite of the products c[0..IT) under the binade with ulp 1/inv_u (same arithmetic as row_sum_exact)
+template <int IT>
+__device__ __forceinline__ void thread_composite(const float *c, int n_valid, float inv_u, ScanPair &tot, int &hi0,
+                                                 int &lo0, int &hi1, int &lo1) {
+    tot.a0 = tot.a1 = 0;
+    hi0 = lo0 = hi1 = lo1 = 0;
+#pragma unroll
+    for (int q = 0; q < IT; q++) {
+        if (q < n_valid) {
+            const float qv = __fmul_rn(c[q], inv_u);
+            int ni;
+            float fr = 0.0f;
+            if (!(fabsf(qv) < 16777216.0f)) {  // also NaN / inf: forces "leaves the binade"
+                ni = qv > 0.0f ? (1 << 24) : -(1 << 24);
+            } else {
+                ni = __float2int_rd(qv);
+                fr = __fsub_rn(qv, (float)ni);  // exact, in [0, 1)
+            }
+            if (fr != 0.5f) {  // common case: the same increment for either parity
+                const int inc1 = ni + (fr > 0.5f ? 1 : 0);
+                tot.a0 += inc1;
+                tot.a1 += inc1;
+            } else {           // tie: round half to even
+                ScanPair a;
+                a.a0 = ni + (ni & 1);
+                a.a1 = ni + ((ni + 1) & 1);
+                tot = scan_combine(tot, a);
+            }
+            hi0 = max(hi0, tot.a0);
+            lo0 = min(lo0, tot.a0);
+            hi1 = max(hi1, tot.a1);
+            lo1 = min(lo1, tot.a1);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
                const int *__restrict__ list, const int *__restrict__ counts, const int *__restrict__ long_chunk0,
                const int *__restrict__ chunk_row, const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec, int L) {
     constexpr int IT = kScanIT;
     __shared__ double s_red[8];
-    __shared__ ScanPair s_wtot[8];
-    __shared__ int s_bnd[8][4];
-    __shared__ float s_pred;
+    __shared__ double s_wpre[8];
+    __shared__ ComposeShared s_cs;
+    __shared__ ScanShared<1> sh1;
+    __shared__ double s_pred;
+    __shared__ int s_tcross;
     const long long n = (long long)__ldg(counts + 1) * L;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
         const int c = (int)(k / L), l = (int)(k % L);
         const ChunkGeom g = chunk_geom(c, row_ptr, list, long_chunk0, chunk_row);
-        if (c == g.first) continue;  // the row head is always summed for real (k_scan_walk)
+        if (c == g.first) {
+            // row head: the start value (0) is known, so the exact sum is computed right here, in parallel with
+            // every other chunk, by one warp with cheap warp-level re-scans (binade crossings are dense at a row start)
+            if (wid == 0) {
+                const float s = row_sum_exact<1, IT>(ent, in, g.e0, g.e1, L, l, tid, sh1, 0.0f);
+                if (tid == 0) {
+                    rec[k].kind = kRecExact;
+                    rec[k].s_exact = s;
+                }
+            }
+            continue;  // (uniform per CTA)
+        }
         // entries of this chunk (thread-contiguous: thread t owns entries [t*IT, (t+1)*IT) of the chunk)
         int2 t[IT];
         float x[IT];
@@ -469,186 +615,158 @@ k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, co
         for (int j = g.first + tid; j < c; j += 256) part += (double)__ldg(chunk_sum + (size_t)j * L + l);
 #pragma unroll
         for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __syncthreads();  // previous task's reads of the shared words are over
         if (lane == 0) s_red[wid] = part;
+        if (tid == 0) s_tcross = 256;
         __syncthreads();
         if (tid == 0) {
             double tot = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; w++) tot += s_red[w];
-            s_pred = (float)tot;
+            s_pred = tot;
         }
+        // products and their thread-local sums (double: a prediction of where the sum crosses the binade)
+        const int n_valid = max(0, min(IT, g.e1 - (g.e0 + tid * IT)));
+        float cq[IT];
+        double lsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < IT; q++) {
+            cq[q] = __fmul_rn(__int_as_float(t[q].y), x[q]);
+            if (q < n_valid) lsum += (double)cq[q];
+        }
+        double incl = lsum;  // inclusive prefix of the thread sums over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_wpre[wid] = incl;
         __syncthreads();
-        const float sp = s_pred;
-        const int E = ((__float_as_int(sp) >> 23) & 0xff) - 127;
-        if (!((sp > 0.0f) && E >= -100 && E <= 100)) {  // uniform
-            if (tid == 0) {
-                ChunkRec r;
-                r.E = INT_MIN;
-                r.a0 = r.a1 = r.lo0 = r.hi0 = r.lo1 = r.hi1 = r.pad = 0;
-                rec[k] = r;
-            }
-            __syncthreads();
+        const double sp = s_pred;
+        double wbase = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+            if (w < wid) wbase += s_wpre[w];
+        const double p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
+        double total = sp;
+#pragma unroll
+        for (int w = 0; w < 8; w++) total += s_wpre[w];  // predicted running sum at the end of the chunk
+        const float spf = (float)sp;
+        const int E = ((__float_as_int(spf) >> 23) & 0xff) - 127;
+        const bool regular = (spf > 0.0f) && E >= -100 && E <= 100;
+        const double top = (double)__int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
+        int kind = kRecNone;
+        if (regular) {
+            if (total < top * (1.0 - 1e-4)) kind = kRecPlain;
+            else if (total < 2.0 * top * (1.0 - 1e-4)) kind = kRecCross;
+        }
+        if (kind == kRecNone) {  // uniform
+            if (tid == 0) rec[k].kind = kRecNone;
             continue;
         }
         const float inv_u = __int_as_float((23 - E + 127) << 23);
-        // thread-local composition (same arithmetic as row_sum_exact)
         ScanPair tot;
-        tot.a0 = tot.a1 = 0;
-        int hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
-#pragma unroll
-        for (int q = 0; q < IT; q++) {
-            if (g.e0 + tid * IT + q < g.e1) {
-                const float cq = __fmul_rn(__int_as_float(t[q].y), x[q]);
-                const float qv = __fmul_rn(cq, inv_u);
-                int ni;
-                float fr = 0.0f;
-                if (!(fabsf(qv) < 16777216.0f)) {
-                    ni = qv > 0.0f ? (1 << 24) : -(1 << 24);
-                } else {
-                    ni = __float2int_rd(qv);
-                    fr = __fsub_rn(qv, (float)ni);
-                }
-                if (fr != 0.5f) {
-                    const int inc1 = ni + (fr > 0.5f ? 1 : 0);
-                    tot.a0 += inc1;
-                    tot.a1 += inc1;
-                } else {
-                    ScanPair a;
-                    a.a0 = ni + (ni & 1);
-                    a.a1 = ni + ((ni + 1) & 1);
-                    tot = scan_combine(tot, a);
-                }
-                hi0 = max(hi0, tot.a0);
-                lo0 = min(lo0, tot.a0);
-                hi1 = max(hi1, tot.a1);
-                lo1 = min(lo1, tot.a1);
+        int hi0, lo0, hi1, lo1;
+        if (kind == kRecPlain) {
+            thread_composite<IT>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
+            const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, true, tid, s_cs);
+            if (tid == 0) {
+                rec[k].kind = kRecPlain;
+                rec[k].E = E;
+                rec[k].A = A;
             }
+            continue;
         }
-        // exclusive scan of the thread composites in thread order
-        ScanPair inc = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            ScanPair lft;
-            lft.a0 = __shfl_up_sync(0xffffffffu, inc.a0, o);
-            lft.a1 = __shfl_up_sync(0xffffffffu, inc.a1, o);
-            if (lane >= o) inc = scan_combine(lft, inc);
-        }
-        ScanPair exc;
-        exc.a0 = __shfl_up_sync(0xffffffffu, inc.a0, 1);
-        exc.a1 = __shfl_up_sync(0xffffffffu, inc.a1, 1);
-        if (lane == 0) exc.a0 = exc.a1 = 0;
-        if (lane == 31) s_wtot[wid] = inc;
+        // crossing: the first thread behind whose entries the predicted sum reaches 2^(E+1) (with a small safety
+        // margin: the true fp32 running sum differs from the prediction by rounding noise only)
+        if (p_end_thread >= top * (1.0 - 2e-5)) atomicMin(&s_tcross, tid);
         __syncthreads();
-        ScanPair w = s_wtot[lane < 8 ? lane : 0];
-        if (lane >= 8) w.a0 = w.a1 = 0;
+        int tw = s_tcross - 1;  // window = threads [tw, tw + kWinThreads)
+        tw = max(0, min(tw, 256 - kWinThreads));
+        const bool inA = tid < tw, inB = tid >= tw + kWinThreads;
+        thread_composite<IT>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
+        const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, inA, tid, s_cs);
+        const Composite Bc = block_composite(tot, hi0, lo0, hi1, lo1, inB, tid, s_cs);
+        if (!inA && !inB) {
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            ScanPair lft;
-            lft.a0 = __shfl_up_sync(0xffffffffu, w.a0, o);
-            lft.a1 = __shfl_up_sync(0xffffffffu, w.a1, o);
-            if (lane >= o) w = scan_combine(lft, w);
+            for (int q = 0; q < IT; q++) rec[k].win[(tid - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;
         }
-        ScanPair wp;
-        wp.a0 = __shfl_sync(0xffffffffu, w.a0, wid > 0 ? wid - 1 : 0);
-        wp.a1 = __shfl_sync(0xffffffffu, w.a1, wid > 0 ? wid - 1 : 0);
-        if (wid > 0) exc = scan_combine(wp, exc);
-        const ScanPair all = {__shfl_sync(0xffffffffu, w.a0, 7), __shfl_sync(0xffffffffu, w.a1, 7)};  // whole chunk
-        // safe range: for a start of parity p this thread begins at offset exc.a_p with parity (p + exc.a_p) & 1
-        int b_lo0 = exc.a0 + ((exc.a0 & 1) ? lo1 : lo0), b_hi0 = exc.a0 + ((exc.a0 & 1) ? hi1 : hi0);
-        int b_lo1 = exc.a1 + ((exc.a1 & 1) ? lo0 : lo1), b_hi1 = exc.a1 + ((exc.a1 & 1) ? hi0 : hi1);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            b_lo0 = min(b_lo0, __shfl_xor_sync(0xffffffffu, b_lo0, o));
-            b_hi0 = max(b_hi0, __shfl_xor_sync(0xffffffffu, b_hi0, o));
-            b_lo1 = min(b_lo1, __shfl_xor_sync(0xffffffffu, b_lo1, o));
-            b_hi1 = max(b_hi1, __shfl_xor_sync(0xffffffffu, b_hi1, o));
-        }
-        if (lane == 0) {
-            s_bnd[wid][0] = b_lo0;
-            s_bnd[wid][1] = b_hi0;
-            s_bnd[wid][2] = b_lo1;
-            s_bnd[wid][3] = b_hi1;
-        }
-        __syncthreads();
         if (tid == 0) {
-            ChunkRec r;
-            r.E = E;
-            r.a0 = all.a0;
-            r.a1 = all.a1;
-            r.lo0 = s_bnd[0][0];
-            r.hi0 = s_bnd[0][1];
-            r.lo1 = s_bnd[0][2];
-            r.hi1 = s_bnd[0][3];
-#pragma unroll
-            for (int w8 = 1; w8 < 8; w8++) {
-                r.lo0 = min(r.lo0, s_bnd[w8][0]);
-                r.hi0 = max(r.hi0, s_bnd[w8][1]);
-                r.lo1 = min(r.lo1, s_bnd[w8][2]);
-                r.hi1 = max(r.hi1, s_bnd[w8][3]);
-            }
-            r.pad = 0;
-            rec[k] = r;
+            rec[k].kind = kRecCross;
+            rec[k].E = E;
+            rec[k].A = A;
+            rec[k].B = Bc;
         }
-        __syncthreads();
     }
 }
 
-constexpr int kWalkBatch = 256;  // chunk records staged per round
+constexpr int kWalkBatch = 32;  // chunk records staged per round
+
+__device__ __forceinline__ bool apply_composite(float &s, int E, const Composite &c) {
+    const int Es = ((__float_as_int(s) >> 23) & 0xff) - 127;
+    if (!((s > 0.0f) && Es == E)) return false;
+    const float u = __int_as_float((E - 23 + 127) << 23);
+    const float inv_u = __int_as_float((23 - E + 127) << 23);
+    const int m0 = (int)__fmul_rn(s, inv_u);  // in [2^23, 2^24)
+    const int lo = (m0 & 1) ? c.lo1 : c.lo0, hi = (m0 & 1) ? c.hi1 : c.hi0;
+    if (!(m0 + lo >= (1 << 23) && m0 + hi < (1 << 24))) return false;
+    s = __fmul_rn((float)(m0 + ((m0 & 1) ? c.a1 : c.a0)), u);
+    return true;
+}
 
 __global__ void __launch_bounds__(256)
 k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
             float *__restrict__ val, const int *__restrict__ list, const int *__restrict__ counts,
             const int *__restrict__ long_chunk0, const ChunkRec *__restrict__ rec, int L) {
     __shared__ ScanShared<8> sh;
-    __shared__ ScanShared<1> sh1;
-    __shared__ float s_stage;
     __shared__ ChunkRec s_rec[kWalkBatch];
     const long long n = (long long)__ldg(counts) * L;
-    const int tid = threadIdx.x, wid = tid >> 5;
+    const int tid = threadIdx.x;
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
         const int i = (int)(k / L), l = (int)(k % L);
         const int v = __ldg(list + i);
         const int e0 = __ldg(row_ptr + v), e1 = __ldg(row_ptr + v + 1);
         const int c0 = __ldg(long_chunk0 + i), nch = __ldg(long_chunk0 + i + 1) - c0;
-        // row head: binade crossings are dense here (the sum doubles after 1, 2, 4, ... entries); one warp sums it
-        // with cheap warp-level re-scans
         float s = 0.0f;
-        if (wid == 0) {
-            s = row_sum_exact<1, kScanIT>(ent, in, e0, min(e0 + kScanChunk, e1), L, l, tid, sh1, 0.0f);
-            if (tid == 0) s_stage = s;
-        }
-        for (int cb = 1; cb < nch; cb += kWalkBatch) {
+        for (int cb = 0; cb < nch; cb += kWalkBatch) {
             const int nb = min(kWalkBatch, nch - cb);
-            __syncthreads();  // s_stage visible (first round); previous round's records consumed
-            if (tid < nb) s_rec[tid] = rec[(size_t)(c0 + cb + tid) * L + l];
-            if (cb == 1) s = s_stage;
+            __syncthreads();  // previous round's records consumed
+            {   // stage the records of this round (word-wise, coalesced)
+                constexpr int W = (int)(sizeof(ChunkRec) / 4);
+                const int *src = (const int *)rec;
+                int *dst = (int *)s_rec;
+                for (int w = tid; w < nb * W; w += 256) {
+                    const int j = w / W, o = w - j * W;
+                    dst[w] = __ldg(src + ((size_t)(c0 + cb + j) * L + l) * W + o);
+                }
+            }
             __syncthreads();
             for (int j = 0; j < nb; j++) {
-                const ChunkRec r = s_rec[j];
-                const int E = ((__float_as_int(s) >> 23) & 0xff) - 127;
-                bool fast = false;
-                if ((s > 0.0f) && E >= -100 && E <= 100 && E == r.E) {
-                    const float u = __int_as_float((E - 23 + 127) << 23);
-                    const float inv_u = __int_as_float((23 - E + 127) << 23);
-                    const int m0 = (int)__fmul_rn(s, inv_u);  // in [2^23, 2^24)
-                    const int lo = (m0 & 1) ? r.lo1 : r.lo0, hi = (m0 & 1) ? r.hi1 : r.hi0;
-                    if (m0 + lo >= (1 << 23) && m0 + hi < (1 << 24)) {
-                        s = __fmul_rn((float)(m0 + ((m0 & 1) ? r.a1 : r.a0)), u);
-                        fast = true;
+                const ChunkRec &r = s_rec[j];
+                bool done = false;
+                if (r.kind == kRecExact) {
+                    s = r.s_exact;  // row head
+                    done = true;
+                } else if (r.kind == kRecPlain) {
+                    done = apply_composite(s, r.E, r.A);
+                } else if (r.kind == kRecCross) {
+                    float t = s;
+                    if (apply_composite(t, r.E, r.A)) {
+#pragma unroll 8
+                        for (int q = 0; q < kWinThreads * kScanIT; q++) t = __fadd_rn(t, r.win[q]);
+                        if (apply_composite(t, r.E + 1, r.B)) {
+                            s = t;
+                            done = true;
+                        }
                     }
                 }
-                if (!fast) {  // uniform: s and the record are identical in every thread
+                if (!done) {  // uniform: s and the record are identical in every thread
                     const int a = e0 + (cb + j) * kScanChunk;
                     s = row_sum_exact<8, kScanIT>(ent, in, a, min(a + kScanChunk, e1), L, l, tid, sh, s);
                 }
             }
         }
-        if (nch <= 1) {
-            __syncthreads();
-            s = s_stage;
-        }
         if (tid == 0) val[(size_t)v * L + l] = s;
-        __syncthreads();
     }
 }
 
@@ -792,23 +910,20 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     const int *vt = ls->vbase + ls->B;
     float *src = ls->valA, *dst = ls->valB;
     if (b.NT > 0) {
-        const int LG = tile_labels(L), gpt = tile_granules(L);
-        const long long E = (long long)b.NT * D;
-        const int ngran = (int)((E + kTileGranule - 1) / kTileGranule);
-        const int grid = (ngran + gpt - 1) / gpt;
-        const size_t smem = (size_t)kTileFloats * sizeof(float);
+        const int LG = tile_labels(L);
+        const int grid = ls->max_pieces < kNumSMs * 8 ? ls->max_pieces : kNumSMs * 8;
+        const size_t smem = (size_t)(kTileGranule + kLongRow) * LG * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((kTileGranule + kLongRow) * 4 * sizeof(float))));
             attr_set = true;
         }
         LCCRF_KERNEL(ctx, "k_splat_tile");
         switch (LG) {
-            case 1: k_splat_tile<1><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
-            case 2: k_splat_tile<2><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
-            default: k_splat_tile<4><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->gran_row, ls->csr_ent, in_dev, src, gpt, L); break;
+            case 1: k_splat_tile<1><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
+            case 2: k_splat_tile<2><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
+            default: k_splat_tile<4><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
         }
     }
     // long rows (>= kLongRow entries): speculative parallel scan.  The lists live on the device, so the grids are

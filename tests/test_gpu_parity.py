@@ -283,6 +283,38 @@ def test_rough_classify(pkg, ctx, oracle):
         assert 0 < lo.sum() < lo.size
 
 
+@pytest.mark.parametrize("case", ["positive", "ties", "mixed_sign", "sparse_zero", "wild"])
+def test_filter_long_rows_bit_exact(pkg, ctx, oracle, case):
+    """Rows of 10^5 entries (all points share a few lattice vertices): the speculative parallel scan
+    (chunk composites, crossing windows, fallbacks) must reproduce the sequential fp32 sums bit for bit --
+    including round-half-even ties, zeros, sign changes and magnitude jumps."""
+    rng = np.random.default_rng({"positive": 1, "ties": 2, "mixed_sign": 3, "sparse_zero": 4, "wild": 5}[case])
+    N = 150001
+    f = np.zeros((N, 2), np.float32)
+    f[:] = rng.normal(0, 0.02, (N, 2))            # one simplex: 3 rows of ~N entries
+    f[::5000] += rng.normal(0, 5, (N // 5000 + 1, 2)).astype(np.float32)   # plus a few short rows
+    far = rng.random(N) < 0.3
+    f[far] += np.float32(7.0)                      # a second cluster: rows of ~45k entries
+    lo, lg = oracle.lattice(f), pkg.Lattice(ctx, f)
+    assert lo["V"] == lg.V
+    for L in (1, 2, 3):
+        if case == "positive":
+            x = rng.random((N, L)).astype(np.float32)
+        elif case == "ties":      # multiples of 2^-10: exact ties whenever the running sum's ulp exceeds 2^-10
+            x = (rng.integers(0, 2048, (N, L)) / 1024.0).astype(np.float32)
+        elif case == "mixed_sign":
+            x = rng.normal(0, 1, (N, L)).astype(np.float32)
+        elif case == "sparse_zero":
+            x = (rng.random((N, L)) * (rng.random((N, L)) < 0.01)).astype(np.float32)
+            x[: N // 3] = 0
+        else:                     # magnitudes from 1e-30 to 1e+20 with zeros and negatives in between
+            x = (10.0 ** rng.uniform(-30, 20, (N, L)) * rng.choice([-1.0, 0.0, 1.0, 1.0], (N, L))).astype(np.float32)
+        yo, yg = oracle.filter(lo, x), lg.filter(x)
+        assert_bit_exact(yg, yo, what="%s L=%d" % (case, L))
+    oracle.lattice_free(lo)
+    lg.close()
+
+
 # ------------------------------------------------------------------ batched frames (C4) and the C3 pipeline
 def test_frames_batch_parity(pkg, ctx, oracle):
     prm_o, prm = oracle_params(), pkg.SlamParams.make()
