@@ -424,6 +424,7 @@ def run_gpu_arm(args):
             roofline = {"kernel": "+".join(members), "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s",
                         "frac": None, "traffic": traffic, "peak_source": peak_src, "share_of_step": shares[top]}
     abytes = F.algorithmic_bytes()
+    scan_diag = [F.debug_counters(0), F.debug_counters(1)]
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
@@ -448,6 +449,7 @@ def run_gpu_arm(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "scan_diagnostics": scan_diag,
         "kernel_shares": shares,
         "kernel_avg_launch_ms": kernel_ms,
         "algorithmic_bytes_per_step": abytes,

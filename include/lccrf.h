@@ -199,6 +199,10 @@ int lccrf_frames_wait(lccrf_frames *fr, int slot);
 /* diagnostics: init labels [NT], unary-derived vectors, per-problem lattice sizes [B*2] */
 int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth,
                            int *V);
+/* diagnostics of lattice set k (0 = appearance, 1 = smoothness) after a run: out8 = {#long rows, #chunks, #pieces,
+ * compose tickets, chunk records applied in O(1), crossing windows applied, chunks summed for real, zero chunks}
+ * (the last four accumulate over the filter calls since the lattice was built) */
+int lccrf_frames_debug_counters(lccrf_frames *fr, int k, int *out8);
 /* algorithmic bytes of one lccrf_frames_run by the SURVEY 8(d) formulas with the actual V (valid after a run) */
 int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_iteration, double *unary);
 

@@ -104,6 +104,7 @@ SYMBOLS = {
     "lccrf_frames_submit": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_wait": (C.c_int, [_vp, C.c_int]),
     "lccrf_frames_get_debug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_debug_counters": (C.c_int, [_vp, C.c_int, _vp]),
     "lccrf_frames_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -414,6 +415,11 @@ class Frames:
         V = np.empty((self.B, 2), dtype=np.int32)
         self.ctx._check(self.ctx.lib.lccrf_frames_get_debug(self.h, _ptr(lab), _ptr(ob), _ptr(er), _ptr(de), _ptr(V)))
         return dict(init_label=lab, observs=ob, error=er, depth=de, V=V)
+
+    def debug_counters(self, k):
+        out = np.zeros(8, dtype=np.int32)
+        self.ctx._check(self.ctx.lib.lccrf_frames_debug_counters(self.h, k, _ptr(out)))
+        return dict(zip(("long_rows", "chunks", "pieces", "tickets", "rec_fast", "rec_cross", "rec_fallback", "rec_zero"), out.tolist()))
 
     def algorithmic_bytes(self):
         t, i, u = C.c_double(), C.c_double(), C.c_double()

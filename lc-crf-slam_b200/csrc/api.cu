@@ -73,6 +73,16 @@ int ctx_join(Ctx *ctx) {
     return LCCRF_OK;
 }
 
+bool uniform_camera(const float *kf_intr, const float *kf_bounds, int nKF, float *cam8) {
+    if (nKF <= 0 || !kf_intr || !kf_bounds) return false;
+    for (int k = 1; k < nKF; k++)
+        if (memcmp(kf_intr + 4 * (size_t)k, kf_intr, 16) != 0 || memcmp(kf_bounds + 4 * (size_t)k, kf_bounds, 16) != 0)
+            return false;
+    memcpy(cam8, kf_intr, 16);
+    memcpy(cam8 + 4, kf_bounds, 16);
+    return true;
+}
+
 static void scratch_release(Ctx *ctx, Ctx::Scratch &s, bool pinned) {
     (void)ctx;
     if (!s.p) return;
@@ -180,6 +190,8 @@ struct FrameInputs {
     bool have_kf_ptr = false;
     int nKF = 0, nKF_cap = 0;
     int kf_slice_max = 0;  // largest per-problem keyframe slice (0 = unknown)
+    bool ucam = false;     // every keyframe has the same intrinsics / image bounds (cam8)
+    float cam8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long nnz = 0, nnz_cap = 0;
     bool have_inputs = false;
     cudaGraphExec_t graph = nullptr;
@@ -761,10 +773,12 @@ int lccrf_map_point_unary(lccrf_ctx *h, int N, const float *xyz, const int *obs_
         LCCRF_CUDA(cudaMemcpyAsync(base + o_bnd, kf_bounds, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
     }
     float *d_obs = (float *)(base + o_out), *d_err = d_obs + N, *d_dep = d_err + N;
+    float cam8[8];
+    const bool ucam = uniform_camera(kf_intr, kf_bounds, nKF, cam8);
     LCCRF_TRY(unary_map_points(ctx, N, (const float *)(base + o_xyz), (const int *)(base + o_ptr),
                                (const int *)(base + o_kf), (const float *)(base + o_uv), nKF,
                                (const float *)(base + o_pose), (const float *)(base + o_intr),
-                               (const float *)(base + o_bnd), d_obs, d_err, d_dep));
+                               (const float *)(base + o_bnd), d_obs, d_err, d_dep, ucam ? cam8 : nullptr));
     LCCRF_CUDA(cudaMemcpyAsync(observs, d_obs, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     LCCRF_CUDA(cudaMemcpyAsync(error, d_err, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     LCCRF_CUDA(cudaMemcpyAsync(depth, d_dep, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
@@ -940,6 +954,13 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
     bool regraph = false;
     if (slice_max != in.kf_slice_max) regraph = true;  // the launch geometry of the unary kernel depends on it
     in.kf_slice_max = slice_max;
+    {   // kernel parameters of the captured graph: a change of camera model needs a new capture
+        float cam8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const bool ucam = nnz > 0 && uniform_camera(kf_intr, kf_bounds, nKF, cam8);
+        if (ucam != in.ucam || memcmp(cam8, in.cam8, sizeof(cam8)) != 0) regraph = true;
+        in.ucam = ucam;
+        memcpy(in.cam8, cam8, sizeof(cam8));
+    }
     if (nnz > in.nnz_cap || !in.obs_kf || in.obs_kf_bytes != obs_kf_bytes) {
         dev_free(ctx, in.obs_kf);
         dev_free(ctx, in.obs_uv);
@@ -1037,7 +1058,8 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
         LCCRF_TRY(unary_pack_kf(ctx, in.kf_packed, in.kf_pose, in.kf_intr, in.kf_bounds, in.nKF));
         LCCRF_TRY(unary_map_points_packed(ctx, NT, in.nKF, in.xyz, in.obs_ptr, in.obs_kf, in.obs_kf_bytes, in.obs_uv,
                                           in.kf_packed, fr->observs, fr->error, fr->depth, b.prob_ptr,
-                                          in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max));
+                                          in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max,
+                                          in.ucam ? in.cam8 : nullptr));
         observs = fr->observs;
         error = fr->error;
         depth = fr->depth;
@@ -1218,6 +1240,16 @@ int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, 
     if (V)
         for (int i = 0; i < fr->b.B; i++)
             for (int k = 0; k < 2; k++) V[2 * i + k] = vb[k][i + 1] - vb[k][i];
+    return LCCRF_OK;
+}
+
+int lccrf_frames_debug_counters(lccrf_frames *fr, int k, int *out8) {
+    if (!fr || !out8) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (k < 0 || k >= (int)fr->b.lat.size()) return fail(LCCRF_ERR_ARG, "lattice index out of range");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    LCCRF_CUDA(cudaMemcpyAsync(out8, fr->b.lat[k]->row_counts, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
     return LCCRF_OK;
 }
 

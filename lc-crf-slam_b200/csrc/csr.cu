@@ -276,7 +276,7 @@ k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, 
 // list index of the row that owns chunk c, counts[1] = number of chunks.  Single CTA (the list is short).
 __global__ void __launch_bounds__(1024)
 k_long_chunks(const int *__restrict__ row_ptr, const int *__restrict__ lng, int *__restrict__ counts,
-              int *__restrict__ long_chunk0, int *__restrict__ chunk_row) {
+              int *__restrict__ long_chunk0, int4 *__restrict__ chunk_desc) {
     __shared__ int ws[32];
     __shared__ int carry_s;
     const int n = counts[0];
@@ -285,10 +285,12 @@ k_long_chunks(const int *__restrict__ row_ptr, const int *__restrict__ lng, int 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int start = 0; start < n; start += 1024) {
         const int i = start + threadIdx.x;
-        int nch = 0;
+        int nch = 0, rs = 0, re = 0;
         if (i < n) {
             const int v = lng[i];
-            nch = (__ldg(row_ptr + v + 1) - __ldg(row_ptr + v) + kScanChunk - 1) / kScanChunk;
+            rs = __ldg(row_ptr + v);
+            re = __ldg(row_ptr + v + 1);
+            nch = (re - rs + kScanChunk - 1) / kScanChunk;
         }
         int x = nch;
 #pragma unroll
@@ -312,7 +314,8 @@ k_long_chunks(const int *__restrict__ row_ptr, const int *__restrict__ lng, int 
         const int base = carry + (wid ? ws[wid - 1] : 0) + x - nch;
         if (i < n) {
             long_chunk0[i] = base;
-            for (int c = 0; c < nch; c++) chunk_row[base + c] = i;
+            for (int c = 0; c < nch; c++)
+                chunk_desc[base + c] = make_int4(rs + c * kScanChunk, min(rs + (c + 1) * kScanChunk, re), base, i);
         }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = carry + ws[31];
@@ -364,8 +367,8 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     }
     rc |= dev_alloc(ctx, (void **)&ls->row_list_long, ((size_t)ls->max_long + 1) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->long_chunk0, ((size_t)ls->max_long + 2) * 4);
-    rc |= dev_alloc(ctx, (void **)&ls->chunk_row, ((size_t)ls->max_chunks + 1) * 4);
-    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 4 * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->chunk_desc, ((size_t)ls->max_chunks + 1) * 16);
+    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 8 * 4);
     ls->max_pieces = (int)(((long long)b.NT * D) / kTileGranule + ((long long)b.NT * D) / kLongRow + 2);
     rc |= dev_alloc(ctx, (void **)&ls->piece_list, (size_t)ls->max_pieces * 4);
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
@@ -393,7 +396,7 @@ void csr_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->scan_tot);
     dev_free(ctx, ls->row_list_long);
     dev_free(ctx, ls->long_chunk0);
-    dev_free(ctx, ls->chunk_row);
+    dev_free(ctx, ls->chunk_desc);
     dev_free(ctx, ls->chunk_sum);
     dev_free(ctx, ls->chunk_rec);
     dev_free(ctx, ls->row_counts);
@@ -437,11 +440,11 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
         }
         { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<<<p.G, kFillWarpsH * 32, kCursorSmemInts * sizeof(int), st>>>(p); }
     }
-    LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 4 * sizeof(int), st));
+    LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 8 * sizeof(int), st));
     { LCCRF_KERNEL(ctx, "k_row_classify"); k_row_classify<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->row_list_long, ls->row_counts, ls->piece_list); }
     if (ls->max_long > 0) {
         LCCRF_KERNEL(ctx, "k_long_chunks");
-        k_long_chunks<<<1, 1024, 0, st>>>(ls->row_ptr, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row);
+        k_long_chunks<<<1, 1024, 0, st>>>(ls->row_ptr, ls->row_list_long, ls->row_counts, ls->long_chunk0, (int4 *)ls->chunk_desc);
     }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;

@@ -40,9 +40,9 @@ struct LatticeSet {
     int *csr_tbl = nullptr, *scan_tot = nullptr;
     // long rows (>= kLongRow entries; filled by csr_build) and their chunks of kScanChunk entries (filter.cu: speculative scan)
     int *row_list_long = nullptr;   // [max_long] vertex ids
-    int *row_counts = nullptr;      // [4] device: #long rows, #chunks, #pieces
+    int *row_counts = nullptr;      // [8] device: #long rows, #chunks, #pieces, compose ticket, 4 walk diagnostics
     int *long_chunk0 = nullptr;     // [max_long+1] first chunk of each long row
-    int *chunk_row = nullptr;       // [max_chunks] long-list index of each chunk
+    void *chunk_desc = nullptr;     // [max_chunks] int4 {first entry, end entry, first chunk of the row, long-list index}
     float *chunk_sum = nullptr;     // [max_chunks*Lmax] unordered chunk sums (per filter call)
     void *chunk_rec = nullptr;      // [max_chunks*Lmax] ChunkRec (per filter call)
     int max_long = 0, max_chunks = 0;
@@ -196,10 +196,13 @@ int feat_image(Ctx *ctx, float *feat, int W, int H, int F, float posdev, const v
 int unary_pack_kf(Ctx *ctx, void *kf_packed /*nKF*80 B*/, const float *pose, const float *intr, const float *bnd, int nKF);
 int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const int *obs_ptr, const void *obs_kf,
                             int obs_kf_bytes, const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
-                            const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max);
+                            const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max, const float *cam8);
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                      const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
-                     const float *kf_bounds, float *observs, float *error, float *depth);
+                     const float *kf_bounds, float *observs, float *error, float *depth, const float *cam8);
+// cam8 (host, 8 floats {fx fy cx cy, minx maxx miny maxy}) when every keyframe has the same intrinsics and image
+// bounds, else nullptr; uniform_camera() decides from the host tables
+bool uniform_camera(const float *kf_intr, const float *kf_bounds, int nKF, float *cam8);
 int unary_classify(Ctx *ctx, int N, const float *observs, const float *error, const float *depth,
                    const double *p4, const lccrf_slam_params &prm, short *label);
 

@@ -380,7 +380,10 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__rest
 //   kRecCross  the running sum is predicted to cross from binade E to E+1 inside the chunk: composite A covers the
 //              threads before the crossing window (binade E), win[] holds the kWinEntries products of the window
 //              (added for real by the walk), composite B covers the threads behind it (binade E+1)
-enum { kRecNone = 0, kRecExact = 1, kRecPlain = 2, kRecCross = 3 };
+//   kRecZero   every product of the chunk is +-0: the chunk leaves any running sum unchanged (a row start is +0 and a
+//              running sum never becomes -0, so adding +-0 is the identity) -- typical for a label whose marginal
+//              hit the fast_exp cut-off on all points of a vertex
+enum { kRecNone = 0, kRecExact = 1, kRecPlain = 2, kRecCross = 3, kRecZero = 4 };
 constexpr int kWinThreads = 4;                     // threads of the compose team covered by the crossing window
 struct Composite {
     int a0, a1;              // total increment in ulps for an even / odd start mantissa
@@ -397,60 +400,62 @@ struct ChunkRec {
 
 static_assert(sizeof(ChunkRec) == kChunkRecBytes, "engine.cuh: kChunkRecBytes must match ChunkRec");
 
-struct ChunkGeom {
-    int e0, e1;   // entry range of the chunk
-    int first;    // index of the row's first chunk
-    int c;        // this chunk's global index
-};
-
-__device__ __forceinline__ ChunkGeom chunk_geom(int c, const int *__restrict__ row_ptr, const int *__restrict__ list,
-                                                const int *__restrict__ long_chunk0, const int *__restrict__ chunk_row) {
-    ChunkGeom g;
-    const int i = __ldg(chunk_row + c);
-    const int v = __ldg(list + i);
-    g.first = __ldg(long_chunk0 + i);
-    g.c = c;
-    g.e0 = __ldg(row_ptr + v) + (c - g.first) * kScanChunk;
-    g.e1 = min(g.e0 + kScanChunk, __ldg(row_ptr + v + 1));
-    return g;
-}
-
+// chunk descriptor (csr.cu: k_long_chunks): {first entry, one past the last entry, index of the row's first chunk,
+// index of the row in the long list}
 constexpr int kScanIT = kScanChunk / 256;  // entries per thread of a 256-thread team
 
+// labels handled per (chunk, label-group) task: the float2 of a point serves both labels of the SLAM CRF
+static inline int scan_labels(int L) { return L >= 2 ? 2 : 1; }
+
+template <int LG>
+__device__ __forceinline__ void gather_labels(const float *__restrict__ in, int pt, int L, int lb, bool valid, float (&x)[LG]) {
+    if (LG == 2 && L == 2) {
+        const float2 v = valid ? __ldg((const float2 *)in + pt) : make_float2(0.f, 0.f);
+        x[0] = v.x;
+        x[LG - 1] = v.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < LG; j++) x[j] = (valid && lb + j < L) ? __ldg(in + (size_t)pt * L + lb + j) : 0.0f;
+    }
+}
+
+template <int LG>
 __global__ void __launch_bounds__(256)
-k_scan_sums(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-            const int *__restrict__ list, const int *__restrict__ counts, const int *__restrict__ long_chunk0,
-            const int *__restrict__ chunk_row, float *__restrict__ chunk_sum, int L) {
-    __shared__ float s_w[8];
-    const long long n = (long long)__ldg(counts + 1) * L;
+k_scan_sums(const int2 *__restrict__ ent, const float *__restrict__ in, int *counts, const int4 *__restrict__ chunk_desc,
+            float *__restrict__ chunk_sum, int L) {
+    __shared__ float s_w[8][LG];
+    const int ngrp = (L + LG - 1) / LG;
+    const long long n = (long long)counts[1] * ngrp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[3] = 0;  // ticket counter of the k_scan_compose launch that follows
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
-        const int c = (int)(k / L), l = (int)(k % L);
-        const ChunkGeom g = chunk_geom(c, row_ptr, list, long_chunk0, chunk_row);
+        const int c = (int)(k / ngrp), lb = (int)(k % ngrp) * LG;
+        const int4 g = __ldg(chunk_desc + c);
         int2 t[kScanIT];
-        float x[kScanIT];
+        float x[kScanIT][LG];
 #pragma unroll
         for (int q = 0; q < kScanIT; q++) {
-            const int e = g.e0 + q * 256 + tid;
-            t[q] = e < g.e1 ? __ldg(ent + e) : make_int2(0, 0);
+            const int e = g.x + q * 256 + tid;
+            t[q] = e < g.y ? __ldg(ent + e) : make_int2(0, 0);
         }
 #pragma unroll
-        for (int q = 0; q < kScanIT; q++) {
-            const int e = g.e0 + q * 256 + tid;
-            x[q] = e < g.e1 ? __ldg(in + (size_t)t[q].x * L + l) : 0.0f;
+        for (int q = 0; q < kScanIT; q++) gather_labels<LG>(in, t[q].x, L, lb, g.x + q * 256 + tid < g.y, x[q]);
+        float acc[LG];
+#pragma unroll
+        for (int j = 0; j < LG; j++) {
+            acc[j] = 0.0f;
+#pragma unroll
+            for (int q = 0; q < kScanIT; q++) acc[j] += __int_as_float(t[q].y) * x[q][j];  // a prediction: any order will do
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            if (lane == 0) s_w[wid][j] = acc[j];
         }
-        float acc = 0.0f;
-#pragma unroll
-        for (int q = 0; q < kScanIT; q++) acc += __int_as_float(t[q].y) * x[q];  // a prediction: any order will do
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_w[wid] = acc;
         __syncthreads();
-        if (tid == 0) {
+        if (tid < LG && lb + tid < L) {
             float tot = 0.0f;
 #pragma unroll
-            for (int w = 0; w < 8; w++) tot += s_w[w];
-            chunk_sum[k] = tot;
+            for (int w = 0; w < 8; w++) tot += s_w[w][tid];
+            chunk_sum[(size_t)c * L + lb + tid] = tot;
         }
         __syncthreads();
     }
@@ -569,133 +574,164 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
     }
 }
 
+struct ComposeScratch {
+    double red[8];
+    double wpre[8];
+    ComposeShared cs;
+    double pred;
+    int tcross;
+};
+
+// composite record of one (chunk, label): cq = this thread's products (thread t owns entries [t*IT, (t+1)*IT) of the
+// chunk), n_valid of them inside the chunk.  Called by all 256 threads (barriers inside).
+template <int IT>
+__device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, const int4 g, int c, int l, int L,
+                                            const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec_out, int tid,
+                                            ComposeScratch &sc) {
+    const int lane = tid & 31, wid = tid >> 5;
+    // predicted running sum at the start of the chunk = sum of the previous chunks of the row
+    double part = 0.0;
+    for (int j = g.z + tid; j < c; j += 256) part += (double)__ldg(chunk_sum + (size_t)j * L + l);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();  // the previous use of the scratch is over
+    if (lane == 0) sc.red[wid] = part;
+    if (tid == 0) sc.tcross = 256;
+    // thread-local sums of the products (double: a prediction of where the sum crosses the binade)
+    double lsum = 0.0;
+    bool my_zero = true;
+#pragma unroll
+    for (int q = 0; q < IT; q++) {
+        if (q < n_valid) lsum += (double)cq[q];
+        my_zero = my_zero && (q >= n_valid || cq[q] == 0.0f);
+    }
+    double incl = lsum;  // inclusive prefix of the thread sums over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) sc.wpre[wid] = incl;
+    if (__syncthreads_and(my_zero)) {  // (uniform) every product is +-0: the chunk is the identity
+        if (tid == 0) rec_out->kind = kRecZero;
+        return;
+    }
+    double sp = 0.0, wbase = 0.0, total = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        sp += sc.red[w];
+        if (w < wid) wbase += sc.wpre[w];
+        total += sc.wpre[w];
+    }
+    const double p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
+    total += sp;                                    // predicted running sum at the end of the chunk
+    const float spf = (float)sp;
+    const int E = ((__float_as_int(spf) >> 23) & 0xff) - 127;
+    const bool regular = (spf > 0.0f) && E >= -100 && E <= 100;
+    const double top = (double)__int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
+    int kind = kRecNone;
+    if (regular) {
+        if (total < top * (1.0 - 1e-4)) kind = kRecPlain;
+        else if (total < 2.0 * top * (1.0 - 1e-4)) kind = kRecCross;
+    }
+    if (kind == kRecNone) {  // (uniform)
+        if (tid == 0) rec_out->kind = kRecNone;
+        return;
+    }
+    const float inv_u = __int_as_float((23 - E + 127) << 23);
+    ScanPair tot;
+    int hi0, lo0, hi1, lo1;
+    if (kind == kRecPlain) {
+        thread_composite<IT>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
+        const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
+        if (tid == 0) {
+            rec_out->kind = kRecPlain;
+            rec_out->E = E;
+            rec_out->A = A;
+        }
+        return;
+    }
+    // crossing: the first thread behind whose entries the predicted sum reaches 2^(E+1) (with a small safety
+    // margin: the true fp32 running sum differs from the prediction by rounding noise only)
+    if (p_end_thread >= top * (1.0 - 2e-5)) atomicMin(&sc.tcross, tid);
+    __syncthreads();
+    int tw = sc.tcross - 1;  // window = threads [tw, tw + kWinThreads)
+    tw = max(0, min(tw, 256 - kWinThreads));
+    const bool inA = tid < tw, inB = tid >= tw + kWinThreads;
+    thread_composite<IT>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
+    const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
+    const Composite Bc = block_composite(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+    if (!inA && !inB) {
+#pragma unroll
+        for (int q = 0; q < IT; q++) rec_out->win[(tid - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;
+    }
+    if (tid == 0) {
+        rec_out->kind = kRecCross;
+        rec_out->E = E;
+        rec_out->A = A;
+        rec_out->B = Bc;
+    }
+}
+
+template <int LG>
 __global__ void __launch_bounds__(256)
 k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-               const int *__restrict__ list, const int *__restrict__ counts, const int *__restrict__ long_chunk0,
-               const int *__restrict__ chunk_row, const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec, int L) {
+               const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
+               const int4 *__restrict__ chunk_desc, const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec, int L) {
     constexpr int IT = kScanIT;
-    __shared__ double s_red[8];
-    __shared__ double s_wpre[8];
-    __shared__ ComposeShared s_cs;
-    __shared__ ScanShared<1> sh1;
-    __shared__ double s_pred;
-    __shared__ int s_tcross;
-    const long long n = (long long)__ldg(counts + 1) * L;
+    __shared__ ComposeScratch s_sc;
+    __shared__ ScanShared<1> sh1[8];
+    __shared__ int s_ticket;
+    const int ngrp = (L + LG - 1) / LG;
+    const long long n = (long long)counts[1] * ngrp;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (long long k = blockIdx.x; k < n; k += gridDim.x) {
-        const int c = (int)(k / L), l = (int)(k % L);
-        const ChunkGeom g = chunk_geom(c, row_ptr, list, long_chunk0, chunk_row);
-        if (c == g.first) {
-            // row head: the start value (0) is known, so the exact sum is computed right here, in parallel with
-            // every other chunk, by one warp with cheap warp-level re-scans (binade crossings are dense at a row start)
-            if (wid == 0) {
-                const float s = row_sum_exact<1, IT>(ent, in, g.e0, g.e1, L, l, tid, sh1, 0.0f);
-                if (tid == 0) {
-                    rec[k].kind = kRecExact;
-                    rec[k].s_exact = s;
-                }
+    // Row heads first: the start value (0) is known, so the exact sum of a row's first chunk is computed right here,
+    // in parallel with everything else, one head per WARP (warp-level re-scans are cheap, and binade crossings are
+    // dense at a row start).  The first CTAs of the grid take the heads, 8 per CTA; they are resident from the start
+    // of the launch, so the long head tasks overlap with all the short composite tasks.
+    {
+        const long long nheads = (long long)counts[0] * L;
+        for (long long hk = (long long)blockIdx.x * 8 + wid; hk < nheads; hk += (long long)gridDim.x * 8) {
+            const int i = (int)(hk / L), l = (int)(hk % L);
+            const int v = __ldg(list + i);
+            const int e0 = __ldg(row_ptr + v), e1 = min(e0 + kScanChunk, __ldg(row_ptr + v + 1));
+            const float s = row_sum_exact<1, IT>(ent, in, e0, e1, L, l, lane, sh1[wid], 0.0f);
+            if (lane == 0) {
+                const size_t k = (size_t)__ldg(long_chunk0 + i) * L + l;
+                rec[k].kind = kRecExact;
+                rec[k].s_exact = s;
             }
-            continue;  // (uniform per CTA)
         }
+    }
+    // all other chunks: dynamic tickets (counts[3], zeroed by k_scan_sums) keep the CTAs that did heads from lagging
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(counts + 3, 1);
+        __syncthreads();
+        const long long k = s_ticket;
+        if (k >= n) break;
+        const int c = (int)(k / ngrp), lb = (int)(k % ngrp) * LG;
+        const int4 g = __ldg(chunk_desc + c);
+        if (c == g.z) continue;  // a row head (done above)
         // entries of this chunk (thread-contiguous: thread t owns entries [t*IT, (t+1)*IT) of the chunk)
         int2 t[IT];
-        float x[IT];
+        float x[IT][LG];
 #pragma unroll
         for (int q = 0; q < IT; q++) {
-            const int e = g.e0 + tid * IT + q;
-            t[q] = e < g.e1 ? __ldg(ent + e) : make_int2(0, 0);
+            const int e = g.x + tid * IT + q;
+            t[q] = e < g.y ? __ldg(ent + e) : make_int2(0, 0);
         }
 #pragma unroll
-        for (int q = 0; q < IT; q++) {
-            const int e = g.e0 + tid * IT + q;
-            x[q] = e < g.e1 ? __ldg(in + (size_t)t[q].x * L + l) : 0.0f;
-        }
-        // predicted running sum at the start of the chunk = sum of the previous chunks of the row
-        double part = 0.0;
-        for (int j = g.first + tid; j < c; j += 256) part += (double)__ldg(chunk_sum + (size_t)j * L + l);
+        for (int q = 0; q < IT; q++) gather_labels<LG>(in, t[q].x, L, lb, g.x + tid * IT + q < g.y, x[q]);
+        const int n_valid = max(0, min(IT, g.y - (g.x + tid * IT)));
 #pragma unroll
-        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        __syncthreads();  // previous task's reads of the shared words are over
-        if (lane == 0) s_red[wid] = part;
-        if (tid == 0) s_tcross = 256;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
+        for (int j = 0; j < LG; j++) {
+            if (lb + j < L) {  // (uniform)
+                float cq[IT];
 #pragma unroll
-            for (int w = 0; w < 8; w++) tot += s_red[w];
-            s_pred = tot;
-        }
-        // products and their thread-local sums (double: a prediction of where the sum crosses the binade)
-        const int n_valid = max(0, min(IT, g.e1 - (g.e0 + tid * IT)));
-        float cq[IT];
-        double lsum = 0.0;
-#pragma unroll
-        for (int q = 0; q < IT; q++) {
-            cq[q] = __fmul_rn(__int_as_float(t[q].y), x[q]);
-            if (q < n_valid) lsum += (double)cq[q];
-        }
-        double incl = lsum;  // inclusive prefix of the thread sums over the block
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) s_wpre[wid] = incl;
-        __syncthreads();
-        const double sp = s_pred;
-        double wbase = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; w++)
-            if (w < wid) wbase += s_wpre[w];
-        const double p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
-        double total = sp;
-#pragma unroll
-        for (int w = 0; w < 8; w++) total += s_wpre[w];  // predicted running sum at the end of the chunk
-        const float spf = (float)sp;
-        const int E = ((__float_as_int(spf) >> 23) & 0xff) - 127;
-        const bool regular = (spf > 0.0f) && E >= -100 && E <= 100;
-        const double top = (double)__int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
-        int kind = kRecNone;
-        if (regular) {
-            if (total < top * (1.0 - 1e-4)) kind = kRecPlain;
-            else if (total < 2.0 * top * (1.0 - 1e-4)) kind = kRecCross;
-        }
-        if (kind == kRecNone) {  // uniform
-            if (tid == 0) rec[k].kind = kRecNone;
-            continue;
-        }
-        const float inv_u = __int_as_float((23 - E + 127) << 23);
-        ScanPair tot;
-        int hi0, lo0, hi1, lo1;
-        if (kind == kRecPlain) {
-            thread_composite<IT>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
-            const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, true, tid, s_cs);
-            if (tid == 0) {
-                rec[k].kind = kRecPlain;
-                rec[k].E = E;
-                rec[k].A = A;
+                for (int q = 0; q < IT; q++) cq[q] = __fmul_rn(__int_as_float(t[q].y), x[q][j]);
+                compose_one<IT>(cq, n_valid, g, c, lb + j, L, chunk_sum, rec + (size_t)c * L + lb + j, tid, s_sc);
             }
-            continue;
-        }
-        // crossing: the first thread behind whose entries the predicted sum reaches 2^(E+1) (with a small safety
-        // margin: the true fp32 running sum differs from the prediction by rounding noise only)
-        if (p_end_thread >= top * (1.0 - 2e-5)) atomicMin(&s_tcross, tid);
-        __syncthreads();
-        int tw = s_tcross - 1;  // window = threads [tw, tw + kWinThreads)
-        tw = max(0, min(tw, 256 - kWinThreads));
-        const bool inA = tid < tw, inB = tid >= tw + kWinThreads;
-        thread_composite<IT>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
-        const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, inA, tid, s_cs);
-        const Composite Bc = block_composite(tot, hi0, lo0, hi1, lo1, inB, tid, s_cs);
-        if (!inA && !inB) {
-#pragma unroll
-            for (int q = 0; q < IT; q++) rec[k].win[(tid - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;
-        }
-        if (tid == 0) {
-            rec[k].kind = kRecCross;
-            rec[k].E = E;
-            rec[k].A = A;
-            rec[k].B = Bc;
         }
     }
 }
@@ -716,11 +752,12 @@ __device__ __forceinline__ bool apply_composite(float &s, int E, const Composite
 
 __global__ void __launch_bounds__(256)
 k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-            float *__restrict__ val, const int *__restrict__ list, const int *__restrict__ counts,
+            float *__restrict__ val, const int *__restrict__ list, int *counts,
             const int *__restrict__ long_chunk0, const ChunkRec *__restrict__ rec, int L) {
     __shared__ ScanShared<8> sh;
     __shared__ ChunkRec s_rec[kWalkBatch];
-    const long long n = (long long)__ldg(counts) * L;
+    const long long n = (long long)counts[0] * L;
+    int n_fast = 0, n_cross = 0, n_fall = 0, n_zero = 0;  // diagnostics (counts[4..7])
     const int tid = threadIdx.x;
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
         const int i = (int)(k / L), l = (int)(k % L);
@@ -747,8 +784,12 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
                 if (r.kind == kRecExact) {
                     s = r.s_exact;  // row head
                     done = true;
+                } else if (r.kind == kRecZero) {
+                    done = true;
+                    n_zero++;
                 } else if (r.kind == kRecPlain) {
                     done = apply_composite(s, r.E, r.A);
+                    n_fast += done;
                 } else if (r.kind == kRecCross) {
                     float t = s;
                     if (apply_composite(t, r.E, r.A)) {
@@ -757,9 +798,11 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
                         if (apply_composite(t, r.E + 1, r.B)) {
                             s = t;
                             done = true;
+                            n_cross++;
                         }
                     }
                 }
+                n_fall += !done;
                 if (!done) {  // uniform: s and the record are identical in every thread
                     const int a = e0 + (cb + j) * kScanChunk;
                     s = row_sum_exact<8, kScanIT>(ent, in, a, min(a + kScanChunk, e1), L, l, tid, sh, s);
@@ -767,6 +810,12 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
             }
         }
         if (tid == 0) val[(size_t)v * L + l] = s;
+    }
+    if (tid == 0 && (n_fast | n_cross | n_fall | n_zero)) {
+        atomicAdd(counts + 4, n_fast);
+        atomicAdd(counts + 5, n_cross);
+        atomicAdd(counts + 6, n_fall);
+        atomicAdd(counts + 7, n_zero);
     }
 }
 
@@ -929,13 +978,20 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     // long rows (>= kLongRow entries): speculative parallel scan.  The lists live on the device, so the grids are
     // sized for the worst case a lattice set can hold and capped at a few waves (grid-stride inside).
     if (b.NT > 0 && ls->max_chunks > 0) {
-        const long long maxc = (long long)ls->max_chunks * L, maxr = (long long)ls->max_long * L;
+        const long long maxc = (long long)ls->max_chunks * ((L + 1) / 2), maxr = (long long)ls->max_long * L;
         const int gc = (int)(maxc < kNumSMs * 16 ? maxc : kNumSMs * 16);
+        const int gk = (int)(maxc < kNumSMs * 3 ? maxc : kNumSMs * 3);  // compose: persistent, one resident wave
         const int gr = (int)(maxr < kNumSMs * 8 ? maxr : kNumSMs * 8);
-        { LCCRF_KERNEL(ctx, "k_scan_sums");
-          k_scan_sums<<<gc, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row, ls->chunk_sum, L); }
-        { LCCRF_KERNEL(ctx, "k_scan_compose");
-          k_scan_compose<<<gc, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, ls->chunk_row, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L); }
+        const int4 *desc = (const int4 *)ls->chunk_desc;
+        if (scan_labels(L) == 1) {
+            { LCCRF_KERNEL(ctx, "k_scan_sums"); k_scan_sums<1><<<gc, 256, 0, st>>>(ls->csr_ent, in_dev, ls->row_counts, desc, ls->chunk_sum, L); }
+            { LCCRF_KERNEL(ctx, "k_scan_compose");
+              k_scan_compose<1><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L); }
+        } else {
+            { LCCRF_KERNEL(ctx, "k_scan_sums"); k_scan_sums<2><<<gc, 256, 0, st>>>(ls->csr_ent, in_dev, ls->row_counts, desc, ls->chunk_sum, L); }
+            { LCCRF_KERNEL(ctx, "k_scan_compose");
+              k_scan_compose<2><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L); }
+        }
         { LCCRF_KERNEL(ctx, "k_scan_walk");
           k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, L); }
     }

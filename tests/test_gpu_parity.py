@@ -271,6 +271,30 @@ def test_map_point_unary_bit_exact(ctx, oracle, N, obs, ragged):
     assert np.array_equal(bits(de), bits(gde))
 
 
+def test_map_point_unary_mixed_cameras(pkg, ctx, oracle):
+    """Keyframes with different intrinsics / image bounds take the per-keyframe path (one shared camera is served
+    from kernel parameters); both must match the restatement bit for bit, stand-alone and inside a frames batch."""
+    snap = synth.map_snapshot(6000, 24, seed=21, ragged=True)
+    snap.kf_intr[::3] = np.array(synth.BONN_INTR, np.float32)
+    snap.kf_bounds[1::4] = np.array([8, 600, 4, 470], np.float32)
+    ob, er, de = oracle.map_point_unary(snap)
+    gob, ger, gde = ctx.map_point_unary(snap)
+    assert np.array_equal(ob, gob) and np.array_equal(bits(er), bits(ger)) and np.array_equal(bits(de), bits(gde))
+    F = pkg.Frames(ctx, [snap.n])
+    F.set_map_inputs(snap.xyz, snap.obs_ptr, snap.obs_kf, snap.obs_uv, snap.kf_pose, snap.kf_intr, snap.kf_bounds, snap.kp2d)
+    F.run(); F.run()
+    d = F.get_debug()
+    assert np.array_equal(bits(er), bits(d["error"])) and np.array_equal(bits(de), bits(d["depth"]))
+    # back to one camera on the same object: the captured graph must be rebuilt with the new kernel parameters
+    snap2 = synth.map_snapshot(6000, 24, seed=22, ragged=True)
+    ob2, er2, de2 = oracle.map_point_unary(snap2)
+    F.set_map_inputs(snap2.xyz, snap2.obs_ptr, snap2.obs_kf, snap2.obs_uv, snap2.kf_pose, snap2.kf_intr, snap2.kf_bounds, snap2.kp2d)
+    F.run(); F.run()
+    d = F.get_debug()
+    assert np.array_equal(bits(er2), bits(d["error"])) and np.array_equal(bits(de2), bits(d["depth"]))
+    F.close()
+
+
 def test_rough_classify(pkg, ctx, oracle):
     prm_o, prm = oracle_params(), pkg.SlamParams.make()
     fr = synth.slam_frame(50000, 21)
