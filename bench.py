@@ -214,8 +214,8 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------- GPU arm
 # Kernels that together implement one stage are timed as a group (one "launch" of the group = one launch of its
-# first kernel): the ordered splat runs as k_splat_tile (short rows) + k_splat_scan_* (long rows) per filter call.
-KERNEL_GROUPS = {"splat": ("k_splat_tile", "k_splat_scan_256", "k_splat_scan_1024")}
+# first kernel): the ordered splat runs as k_splat_tile (short rows) + k_scan_sums/compose/walk (long rows) per filter call.
+KERNEL_GROUPS = {"splat": ("k_splat_tile", "k_scan_sums", "k_scan_compose", "k_scan_walk")}
 
 
 def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, kf_bytes=4, T=5, L=2, D=3, K=2):

@@ -22,6 +22,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-profile > $OUT/ncu_launch_bench.log 2>&1; echo "ncu launches rc=$?"
 echo "== ncu full"
 timeout 1200 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_splat_staged|k_products|k_mf_point_l2|k_map_point_unary|k_embed|k_csr_fill|k_csr_count|k_blur_fused|k_splat_scan|k_neighbours' \
-    -s 160 -c 80 -o $OUT/prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+    -k regex:'k_splat_tile|k_scan_sums|k_scan_compose|k_scan_walk|k_mf_point_l2|k_map_point_unary|k_embed|k_csr_fill|k_csr_count|k_blur_fused|k_neighbours' \
+    -s 160 -c 80 -o /tmp/prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+ncu -i /tmp/prof.ncu-rep --page raw --csv > $OUT/prof_raw.csv 2> $OUT/prof.err; gzip -f $OUT/prof_raw.csv
 ls -la $OUT
