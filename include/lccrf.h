@@ -158,6 +158,35 @@ int lccrf_map_point_unary(lccrf_ctx *ctx, int N, const float *xyz, const int *ob
 int lccrf_rough_classify(lccrf_ctx *ctx, int N, const float *observs, const float *error, const float *depth,
                          const double *p4, const lccrf_slam_params *prm, short *label);
 
+/* ---------------------------------------------------------------- frontend --- */
+/* Replaces Tracking::GetFeature2EpipolarDis   src/Tracking.cc:2030-2047, i.e. per match
+ *   FundamentalMatrixEstimator::symmetricEpipolarDistance
+ *     Thirdparty/graph-cut-ransac-master/include/fundamental_estimator.h:90-127   (double, incl. its y1-for-y2 quirk at :121)
+ *   prob = exp(-(dis-mGcMean)^2 / (2*mGcStdev*mGcStdev))   Tracking.cc:2043.
+ * M matches of `asso`: fid1 [M] feature id in the current frame (may be NULL when only the per-match outputs
+ * are wanted), pt1 [M*2] = mCurrentFrame.mvKeysUn[fid1].pt, pt2 [M*2] = mLastFrame.mvKeysUn[fid2].pt,
+ * F9 = fundModel.descriptor row-major.  Outputs (any may be NULL): dis/prob [M] per match, and dis_by_fid /
+ * prob_by_fid [nFeat], the flat form of mvFeatureMatchDis / mvFeatureMatchProb -- features without a match
+ * read 0.0, the value std::map::operator[] inserts at Tracking.cc:2003.  p4[i] = prob_by_fid[fid of point i]
+ * is what lccrf_rough_classify takes. */
+int lccrf_epipolar_prior(lccrf_ctx *ctx, int M, const int *fid1, const float *pt1, const float *pt2,
+                         const double *F9, float u_gamma, float stdev_gamma, int nFeat, double *dis_by_fid,
+                         double *prob_by_fid, double *dis, double *prob);
+/* Replaces Tracking::BfMatch   src/Tracking.cc:1747-1766:
+ *   cv::BFMatcher(cv::NORM_HAMMING).knnMatch(fl.mDescriptors, fr.mDescriptors, matches, 2) and the ratio test
+ *   match[0].distance < match[1].distance * 0.6 (:1755, evaluated in double).
+ * desc_q [nq*32], desc_t [nt*32]: 256-bit ORB descriptors (rows of the CV_8U x 32 cv::Mat).
+ * match [nq]: asso[q] = train index of the accepted correspondence, -1 = rejected (or nt < 2).
+ * knn (optional) [nq*4]: {d0, i0, d1, i1}, the two nearest train rows; equal distances keep the lower index
+ * first (OpenCV's K-best insertion; pinned against cv2 in tests/golden).  n_match (optional): accepted count. */
+int lccrf_bf_match(lccrf_ctx *ctx, int nq, const uint8_t *desc_q, int nt, const uint8_t *desc_t, double ratio,
+                   int *match, int *knn, int *n_match);
+/* B frame pairs in one launch (sequence replay: frame i against frame i-15, Tracking.cc:266-272): pair b owns
+ * query rows [q_ptr[b], q_ptr[b+1]) and train rows [t_ptr[b], t_ptr[b+1]); indices in match / knn are local
+ * to the pair's train range. */
+int lccrf_bf_match_batch(lccrf_ctx *ctx, int B, const int *q_ptr, const uint8_t *desc_q, const int *t_ptr,
+                         const uint8_t *desc_t, double ratio, int *match, int *knn, int *n_match);
+
 /* ---------------------------------------------------------------- batched frames --------- */
 /* B independent per-frame CRF problems (the body of Tracking::DynamicDetectionWithCRF,
  * src/Tracking.cc:1871-1930, for B frames at once): RroughClassify -> setUnaryEnergyFromLabel ->

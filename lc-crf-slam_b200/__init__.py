@@ -94,6 +94,9 @@ SYMBOLS = {
     "lccrf_exp_and_normalize": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float]),
     "lccrf_map_point_unary": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_rough_classify": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(SlamParams), _vp]),
+    "lccrf_epipolar_prior": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp, _vp]),
+    "lccrf_bf_match": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, _vp, _vp, _ip]),
+    "lccrf_bf_match_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _ip]),
     "lccrf_frames_create": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(SlamParams), _vp, C.POINTER(_vp)]),
     "lccrf_frames_destroy": (None, [_vp]),
     "lccrf_frames_set_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
@@ -227,6 +230,42 @@ class Context:
         self._check(self.lib.lccrf_rough_classify(self.h, observs.size, _ptr(observs), _ptr(error), _ptr(depth),
                                                   _ptr(p4), C.byref(prm), _ptr(lab)))
         return lab
+
+
+    def epipolar_prior(self, fid1, pt1, pt2, F, u_gamma, stdev_gamma, n_feat=0):
+        """GetFeature2EpipolarDis (Tracking.cc:2030-2047): returns (dis[M], prob[M], dis_by_fid[n_feat], prob_by_fid[n_feat])."""
+        pt1, pt2 = _arr(pt1, np.float32), _arr(pt2, np.float32)
+        M = pt1.shape[0]
+        fid = _arr(fid1, np.int32) if fid1 is not None else None
+        F9 = np.ascontiguousarray(F, dtype=np.float64).reshape(9)
+        dis, prob = np.empty(M, np.float64), np.empty(M, np.float64)
+        dbf, pbf = np.empty(n_feat, np.float64), np.empty(n_feat, np.float64)
+        self._check(self.lib.lccrf_epipolar_prior(self.h, M, _ptr(fid), _ptr(pt1), _ptr(pt2), _ptr(F9), u_gamma, stdev_gamma,
+                                                  n_feat, _ptr(dbf) if n_feat and fid is not None else None,
+                                                  _ptr(pbf) if n_feat and fid is not None else None, _ptr(dis), _ptr(prob)))
+        return dis, prob, dbf, pbf
+
+    def bf_match(self, desc_q, desc_t, ratio=0.6, want_knn=True):
+        """BfMatch (Tracking.cc:1747-1766): returns (match[nq], knn[nq,4] or None, n_match)."""
+        dq = np.ascontiguousarray(desc_q, dtype=np.uint8).reshape(-1, 32)
+        dt = np.ascontiguousarray(desc_t, dtype=np.uint8).reshape(-1, 32)
+        match = np.empty(dq.shape[0], np.int32)
+        knn = np.empty((dq.shape[0], 4), np.int32) if want_knn else None
+        n = C.c_int(0)
+        self._check(self.lib.lccrf_bf_match(self.h, dq.shape[0], _ptr(dq), dt.shape[0], _ptr(dt), ratio, _ptr(match),
+                                            _ptr(knn), C.byref(n)))
+        return match, knn, n.value
+
+    def bf_match_batch(self, q_ptr, desc_q, t_ptr, desc_t, ratio=0.6, want_knn=False):
+        q_ptr, t_ptr = _arr(q_ptr, np.int32), _arr(t_ptr, np.int32)
+        dq = np.ascontiguousarray(desc_q, dtype=np.uint8).reshape(-1, 32)
+        dt = np.ascontiguousarray(desc_t, dtype=np.uint8).reshape(-1, 32)
+        match = np.empty(dq.shape[0], np.int32)
+        knn = np.empty((dq.shape[0], 4), np.int32) if want_knn else None
+        n = C.c_int(0)
+        self._check(self.lib.lccrf_bf_match_batch(self.h, q_ptr.size - 1, _ptr(q_ptr), _ptr(dq), _ptr(t_ptr), _ptr(dt), ratio,
+                                                  _ptr(match), _ptr(knn), C.byref(n)))
+        return match, knn, n.value
 
 
 class Lattice:

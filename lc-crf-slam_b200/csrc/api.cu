@@ -811,6 +811,106 @@ int lccrf_rough_classify(lccrf_ctx *h, int N, const float *observs, const float 
     return LCCRF_OK;
 }
 
+// ------------------------------------------------------------------ frontend: epipolar prior, BfMatch
+int lccrf_epipolar_prior(lccrf_ctx *h, int M, const int *fid1, const float *pt1, const float *pt2, const double *F9,
+                         float u_gamma, float stdev_gamma, int nFeat, double *dis_by_fid, double *prob_by_fid,
+                         double *dis, double *prob) {
+    if (!h) return fail(LCCRF_ERR_ARG, "ctx is NULL");
+    if (M < 0 || nFeat < 0) return fail(LCCRF_ERR_ARG, "negative size");
+    if ((dis_by_fid || prob_by_fid) && !fid1 && M > 0) return fail(LCCRF_ERR_ARG, "fid1 is required for the by-feature outputs");
+    if (M > 0 && (!pt1 || !pt2 || !F9)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (fid1)
+        for (int m = 0; m < M; m++)
+            if (fid1[m] < 0 || fid1[m] >= nFeat) return fail(LCCRF_ERR_ARG, "fid1 out of range");
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_fid = take((size_t)M * 4), o_p1 = take((size_t)M * 8), o_p2 = take((size_t)M * 8),
+                 o_dm = take((size_t)M * 8), o_pm = take((size_t)M * 8), o_df = take((size_t)nFeat * 8),
+                 o_pf = take((size_t)nFeat * 8);
+    LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, off + 256));
+    char *base = (char *)ctx->dev_io.p;
+    cudaStream_t st = ctx->stream;
+    if (M > 0) {
+        if (fid1) LCCRF_CUDA(cudaMemcpyAsync(base + o_fid, fid1, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_p1, pt1, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(base + o_p2, pt2, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    }
+    // unmatched features read 0.0, the value std::map<int,double>::operator[] inserts (Tracking.cc:2003)
+    if (nFeat > 0) LCCRF_CUDA(cudaMemsetAsync(base + o_df, 0, (o_pf - o_df) + (size_t)nFeat * 8, st));
+    LCCRF_TRY(epipolar_prior(ctx, M, fid1 ? (const int *)(base + o_fid) : nullptr, (const float *)(base + o_p1),
+                             (const float *)(base + o_p2), F9, u_gamma, stdev_gamma, nFeat,
+                             dis_by_fid ? (double *)(base + o_df) : nullptr, prob_by_fid ? (double *)(base + o_pf) : nullptr,
+                             (double *)(base + o_dm), (double *)(base + o_pm)));
+    if (dis && M > 0) LCCRF_CUDA(cudaMemcpyAsync(dis, base + o_dm, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    if (prob && M > 0) LCCRF_CUDA(cudaMemcpyAsync(prob, base + o_pm, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    if (dis_by_fid && nFeat > 0) LCCRF_CUDA(cudaMemcpyAsync(dis_by_fid, base + o_df, (size_t)nFeat * 8, cudaMemcpyDeviceToHost, st));
+    if (prob_by_fid && nFeat > 0) LCCRF_CUDA(cudaMemcpyAsync(prob_by_fid, base + o_pf, (size_t)nFeat * 8, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));
+    return LCCRF_OK;
+}
+
+int lccrf_bf_match_batch(lccrf_ctx *h, int B, const int *q_ptr, const uint8_t *desc_q, const int *t_ptr,
+                         const uint8_t *desc_t, double ratio, int *match, int *knn, int *n_match) {
+    if (!h) return fail(LCCRF_ERR_ARG, "ctx is NULL");
+    if (B < 0 || B > 65535) return fail(LCCRF_ERR_ARG, "B must be in [0, 65535]");
+    if (n_match) *n_match = 0;
+    if (B == 0) return LCCRF_OK;
+    if (!q_ptr || !t_ptr) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (q_ptr[0] != 0 || t_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "q_ptr / t_ptr must start at 0");
+    int max_nq = 0, max_nt = 0;
+    for (int b = 0; b < B; b++) {
+        const int nq = q_ptr[b + 1] - q_ptr[b], nt = t_ptr[b + 1] - t_ptr[b];
+        if (nq < 0 || nt < 0) return fail(LCCRF_ERR_ARG, "q_ptr / t_ptr must be non-decreasing");
+        if (nq > max_nq) max_nq = nq;
+        if (nt > max_nt) max_nt = nt;
+    }
+    const int NQ = q_ptr[B], NTr = t_ptr[B];
+    if (NQ == 0) return LCCRF_OK;
+    if (!desc_q || (NTr > 0 && !desc_t) || !match) return fail(LCCRF_ERR_ARG, "NULL argument");
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const int S = bf_match_splits(B, max_nq, max_nt);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_qp = take((size_t)(B + 1) * 4), o_tp = take((size_t)(B + 1) * 4), o_dq = take((size_t)NQ * 32),
+                 o_dt = take((size_t)NTr * 32), o_part = take((size_t)NQ * S * 16), o_match = take((size_t)NQ * 4),
+                 o_knn = take((size_t)NQ * 16), o_cnt = take(4);
+    LCCRF_TRY(ctx_scratch(ctx, ctx->dev_io, off + 256));
+    char *base = (char *)ctx->dev_io.p;
+    cudaStream_t st = ctx->stream;
+    LCCRF_CUDA(cudaMemcpyAsync(base + o_qp, q_ptr, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+    LCCRF_CUDA(cudaMemcpyAsync(base + o_tp, t_ptr, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+    LCCRF_CUDA(cudaMemcpyAsync(base + o_dq, desc_q, (size_t)NQ * 32, cudaMemcpyHostToDevice, st));
+    if (NTr > 0) LCCRF_CUDA(cudaMemcpyAsync(base + o_dt, desc_t, (size_t)NTr * 32, cudaMemcpyHostToDevice, st));
+    LCCRF_TRY(bf_match(ctx, B, NQ, max_nq, max_nt, (const int *)(base + o_qp), base + o_dq, (const int *)(base + o_tp),
+                       base + o_dt, ratio, S, base + o_part, (int *)(base + o_match), knn ? (int *)(base + o_knn) : nullptr,
+                       (int *)(base + o_cnt)));
+    LCCRF_CUDA(cudaMemcpyAsync(match, base + o_match, (size_t)NQ * 4, cudaMemcpyDeviceToHost, st));
+    if (knn) LCCRF_CUDA(cudaMemcpyAsync(knn, base + o_knn, (size_t)NQ * 16, cudaMemcpyDeviceToHost, st));
+    int cnt = 0;
+    LCCRF_CUDA(cudaMemcpyAsync(&cnt, base + o_cnt, 4, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));
+    if (n_match) *n_match = cnt;
+    return LCCRF_OK;
+}
+
+int lccrf_bf_match(lccrf_ctx *h, int nq, const uint8_t *desc_q, int nt, const uint8_t *desc_t, double ratio, int *match,
+                   int *knn, int *n_match) {
+    if (nq < 0 || nt < 0) return fail(LCCRF_ERR_ARG, "negative size");
+    const int qp[2] = {0, nq}, tp[2] = {0, nt};
+    return lccrf_bf_match_batch(h, 1, qp, desc_q, tp, desc_t, ratio, match, knn, n_match);
+}
+
 // ------------------------------------------------------------------ batched frames
 int lccrf_frames_create(lccrf_ctx *h, int B, const int *prob_ptr, const lccrf_slam_params *prm,
                         const float *energies3, lccrf_frames **out) {

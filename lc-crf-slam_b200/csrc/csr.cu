@@ -338,10 +338,14 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
         prob_chunk0[i] = (int)chunk_prob.size();
         const int p0 = b.h_prob_ptr[i], p1 = b.h_prob_ptr[i + 1];
         const long long stride = ((long long)(p1 - p0) + 1) * D;  // worst-case vertex count of the problem
-        for (int c = p0; c < p1; c += kCsrChunkPoints) {
+        // the count table is chunks x vertices: image-scale problems (millions of points) take coarser chunks so
+        // that one problem's table stays below 2^30 entries
+        long long cpts = kCsrChunkPoints;
+        while (((long long)(p1 - p0) + cpts - 1) / cpts * stride > (1ll << 30)) cpts *= 2;
+        for (long long c = p0; c < p1; c += cpts) {
             chunk_prob.push_back(i);
-            chunk_s0.push_back(c * D);
-            chunk_s1.push_back((c + kCsrChunkPoints < p1 ? c + kCsrChunkPoints : p1) * D);
+            chunk_s0.push_back((int)(c * D));
+            chunk_s1.push_back((int)((c + cpts < p1 ? c + cpts : p1) * D));
             chunk_tbl.push_back(tbl);
             tbl += stride;
         }

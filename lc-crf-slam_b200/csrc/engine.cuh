@@ -206,4 +206,13 @@ bool uniform_camera(const float *kf_intr, const float *kf_bounds, int nKF, float
 int unary_classify(Ctx *ctx, int N, const float *observs, const float *error, const float *depth,
                    const double *p4, const lccrf_slam_params &prm, short *label);
 
+// frontend (frontend.cu): epipolar prior and brute-force Hamming kNN; all pointers are device pointers
+int epipolar_prior(Ctx *ctx, int M, const int *fid1, const float *pt1, const float *pt2, const double *F9_host,
+                   float u_gamma, float stdev_gamma, int nFeat, double *dis_by_fid, double *prob_by_fid, double *dis_m,
+                   double *prob_m);
+int bf_match_splits(int B, int max_nq, int max_nt);
+int bf_match(Ctx *ctx, int B, int NQ, int max_nq, int max_nt, const int *q_ptr, const void *desc_q, const int *t_ptr,
+             const void *desc_t, double ratio, int S, void *part /*[NQ*S] int4*/, int *match, int *knn /*[NQ*4] or null*/,
+             int *n_match);
+
 }  // namespace lccrf

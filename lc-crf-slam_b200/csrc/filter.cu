@@ -820,19 +820,64 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
 }
 
 // ---------------------------------------------------------------- blur
-// element-parallel over [vertex][label]; persistent grid-stride because V lives on the device
+// One pass new[v] = old[v] + 0.5*(old[n1(v)] + old[n2(v)])  (permutohedral_cpu.h:663-679) for lattices that do not fit
+// one CTA (image-scale V).  HBM stream: per vertex one int2 neighbour pair, the vertex's own labels and the result
+// move as 64/128-bit vectors (labels packed per vertex: float2 for L = 2, float4 groups for L % 4 == 0); the two
+// neighbour gathers hit L1/L2 because vertex ids follow first-touch (scan) order, so lattice neighbours are close
+// in memory.  Each thread keeps kBlurU independent elements in flight (all neighbour pairs and own values are
+// requested before the first dependent gather); persistent grid-stride over a device-resident V.
+constexpr int kBlurU = 4;
+
+template <typename VT> struct BlurVec;
+template <> struct BlurVec<float> {
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float comb(float o, float a, float b) { return __fadd_rn(o, __fmul_rn(0.5f, __fadd_rn(a, b))); }
+};
+template <> struct BlurVec<float2> {
+    static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float2 comb(float2 o, float2 a, float2 b) {
+        return make_float2(BlurVec<float>::comb(o.x, a.x, b.x), BlurVec<float>::comb(o.y, a.y, b.y));
+    }
+};
+template <> struct BlurVec<float4> {
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ float4 comb(float4 o, float4 a, float4 b) {
+        return make_float4(BlurVec<float>::comb(o.x, a.x, b.x), BlurVec<float>::comb(o.y, a.y, b.y),
+                           BlurVec<float>::comb(o.z, a.z, b.z), BlurVec<float>::comb(o.w, a.w, b.w));
+    }
+};
+
+// G = vectors per vertex (L / lanes of VT); element t = v * G + g
+template <typename VT>
 __global__ void __launch_bounds__(kThreads)
-k_blur(const int2 *__restrict__ nbr_j, const float *__restrict__ src, float *__restrict__ dst,
-       const int *__restrict__ vtotal, int L) {
-    const long long total = (long long)__ldg(vtotal) * L;
-    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
-         t += (long long)gridDim.x * kThreads) {
-        const int v = (int)(t / L), l = (int)(t - (long long)v * L);
-        const int2 nb = __ldg(nbr_j + v);
-        const float o = __ldg(src + t);
-        const float a = nb.x >= 0 ? __ldg(src + (size_t)nb.x * L + l) : 0.f;
-        const float b = nb.y >= 0 ? __ldg(src + (size_t)nb.y * L + l) : 0.f;
-        dst[t] = __fadd_rn(o, __fmul_rn(0.5f, __fadd_rn(a, b)));
+k_blur_vec(const int2 *__restrict__ nbr_j, const VT *__restrict__ src, VT *__restrict__ dst,
+           const int *__restrict__ vtotal, int G) {
+    const long long total = (long long)__ldg(vtotal) * G;
+    const long long step = (long long)gridDim.x * kThreads * kBlurU;
+    for (long long base = (long long)blockIdx.x * kThreads * kBlurU + threadIdx.x; base < total; base += step) {
+        int2 nb[kBlurU];
+        VT o[kBlurU];
+        int g[kBlurU];
+#pragma unroll
+        for (int u = 0; u < kBlurU; u++) {
+            const long long t = base + (long long)u * kThreads;
+            nb[u] = make_int2(-1, -1);
+            o[u] = BlurVec<VT>::zero();
+            g[u] = 0;
+            if (t < total) {
+                const int v = G == 1 ? (int)t : (int)(t / G);
+                g[u] = G == 1 ? 0 : (int)(t - (long long)v * G);
+                nb[u] = __ldg(nbr_j + v);
+                o[u] = __ldg(src + t);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBlurU; u++) {
+            const long long t = base + (long long)u * kThreads;
+            const VT a = nb[u].x >= 0 ? __ldg(src + (size_t)nb[u].x * G + g[u]) : BlurVec<VT>::zero();
+            const VT b = nb[u].y >= 0 ? __ldg(src + (size_t)nb[u].y * G + g[u]) : BlurVec<VT>::zero();
+            if (t < total) __stcs(dst + t, BlurVec<VT>::comb(o[u], a, b));
+        }
     }
 }
 
@@ -1007,10 +1052,19 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
         LCCRF_CUDA(cudaGetLastError());
         return LCCRF_OK;
     }
-    const int bgrid = persistent_grid((long long)ls->Vcap * L, kThreads, 8);
+    // vector width: the widest of float4 / float2 / float that divides L (value rows are L floats, 16-byte aligned
+    // bases, so vertex v's row is aligned to the vector whenever the width divides L)
+    const int W = (L % 4 == 0) ? 4 : (L % 2 == 0) ? 2 : 1;
+    const int G = L / W;
+    const int bgrid = persistent_grid(((long long)ls->Vcap * G + kBlurU - 1) / kBlurU, kThreads, 8);
     for (int j = 0; j < D; j++) {
         const int2 *nb = ls->nbr + (size_t)j * ls->Vcap;
-        { LCCRF_KERNEL(ctx, "k_blur"); k_blur<<<bgrid, kThreads, 0, st>>>(nb, src, dst, vt, L); }
+        {
+            LCCRF_KERNEL(ctx, "k_blur");
+            if (W == 4) k_blur_vec<float4><<<bgrid, kThreads, 0, st>>>(nb, (const float4 *)src, (float4 *)dst, vt, G);
+            else if (W == 2) k_blur_vec<float2><<<bgrid, kThreads, 0, st>>>(nb, (const float2 *)src, (float2 *)dst, vt, G);
+            else k_blur_vec<float><<<bgrid, kThreads, 0, st>>>(nb, src, dst, vt, G);
+        }
         float *t = src;
         src = dst;
         dst = t;

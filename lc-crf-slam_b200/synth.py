@@ -175,3 +175,51 @@ def image_problem(w: int, h: int, seed: int, unknown_frac: float = 0.7, n_labels
     lab = np.where(flip, (lab + 1) % n_labels, lab).astype(np.int16)
     lab[rng.random((h, w)) < unknown_frac] = -1
     return img.reshape(-1, 3).copy(), lab.reshape(-1).copy()
+
+
+def orb_frame_pair(nq: int, nt: int, seed: int, match_frac: float = 0.5, flip_bits: int = 20, entropy_bytes: int = 32):
+    """Two frames' ORB descriptor sets (256 bit, rows of a CV_8U x 32 matrix) for BfMatch (Tracking.cc:1747-1766):
+    `match_frac` of the queries are noisy copies (up to `flip_bits` flipped bits) of random train rows, the rest are
+    unrelated.  `entropy_bytes` < 32 zeroes the tail of every descriptor, which makes distance ties common."""
+    rng = np.random.default_rng(seed)
+    dt = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    dq = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    if nt > 0 and nq > 0:
+        sel = np.nonzero(rng.random(nq) < match_frac)[0]
+        src = rng.integers(0, nt, sel.size)
+        dq[sel] = dt[src]
+        for i in sel:
+            nb = int(rng.integers(0, flip_bits + 1))
+            pos = rng.integers(0, 256, nb)
+            np.bitwise_xor.at(dq[i], pos >> 3, (1 << (pos & 7)).astype(np.uint8))
+    if entropy_bytes < 32:
+        dt[:, entropy_bytes:] = 0
+        dq[:, entropy_bytes:] = 0
+    return dq, dt
+
+
+def epipolar_matches(m: int, seed: int, outlier_frac: float = 0.3):
+    """Matched keypoints of two views of static 3-D points plus the fundamental matrix of the pair (double, row-major)
+    for GetFeature2EpipolarDis (Tracking.cc:2030-2047); `outlier_frac` of the matches are displaced (moving points)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = TUM_INTR
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    # consecutive frames: small inter-frame motion (the reference evaluates the second distance with y1 in place of
+    # y2, fundamental_estimator.h:121, which is only harmless when the vertical parallax is small)
+    R = _rot(*(rng.normal(0, 0.004, 3)))
+    t = rng.normal(0, 0.01, 3)
+    X = np.stack([rng.uniform(-1.5, 1.5, m), rng.uniform(-1.0, 1.0, m), rng.uniform(1.0, 5.0, m)], axis=1)
+    x1 = (K @ X.T).T
+    x1 = x1[:, :2] / x1[:, 2:]
+    X2 = (R @ X.T).T + t
+    x2 = (K @ X2.T).T
+    x2 = x2[:, :2] / x2[:, 2:]
+    x1 += rng.normal(0, 0.5, x1.shape)
+    x2 += rng.normal(0, 0.5, x2.shape)
+    out = rng.random(m) < outlier_frac
+    x2[out] += rng.normal(0, 15.0, (int(out.sum()), 2))
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Kinv = np.linalg.inv(K)
+    F = Kinv.T @ tx @ R @ Kinv
+    F = F / np.linalg.norm(F)
+    return x1.astype(np.float32), x2.astype(np.float32), np.ascontiguousarray(F, dtype=np.float64), out

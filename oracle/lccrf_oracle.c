@@ -515,3 +515,79 @@ void orc_slam_crf(int N, const float *observs, const float *error, const float *
     free(feat);
     free(unary);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Frontend feeders: epipolar prior and brute-force descriptor matching
+ * ------------------------------------------------------------------------------------------ */
+
+/* fundamental_estimator.h:90-127 + Tracking.cc:2037-2045 */
+void orc_epipolar_prior(int M, const float *pt1, const float *pt2, const double *F, float u_gamma,
+                        float stdev_gamma, double *dis_out, double *prob_out) {
+    const double f11 = F[0], f12 = F[1], f13 = F[2], f21 = F[3], f22 = F[4], f23 = F[5], f31 = F[6], f32 = F[7],
+                 f33 = F[8]; /* :99-107 */
+    for (int m = 0; m < M; m++) {
+        const double x1 = (double)pt1[2 * m], y1 = (double)pt1[2 * m + 1]; /* Tracking.cc:2037-2039 */
+        const double x2 = (double)pt2[2 * m], y2 = (double)pt2[2 * m + 1];
+        const double l1 = f11 * x2 + f21 * y2 + f31; /* :109-111 */
+        const double l2 = f12 * x2 + f22 * y2 + f32;
+        const double l3 = f13 * x2 + f23 * y2 + f33;
+        const double t1 = f11 * x1 + f12 * y1 + f13; /* :113-115 */
+        const double t2 = f21 * x1 + f22 * y1 + f23;
+        const double t3 = f31 * x1 + f32 * y1 + f33;
+        const double a1 = l1 * x1 + l2 * y1 + l3; /* :117 */
+        const double a2 = sqrt(l1 * l1 + l2 * l2); /* :118 */
+        const double b1 = t1 * x2 + t2 * y1 + t3; /* :120 -- y1 as in the reference */
+        const double b2 = sqrt(t1 * t1 + t2 * t2); /* :121 */
+        const double d1 = a1 / a2, d2 = b1 / b2; /* :123-124 */
+        const double dis = fabs(0.5 * (d1 + d2)); /* :126 */
+        /* Tracking.cc:2043: exp(- (dis-mGcMean)*(dis-mGcMean)/(2*mGcStdev*mGcStdev)), float denominator */
+        const float den = 2 * stdev_gamma * stdev_gamma;
+        const double prob = exp(-(dis - u_gamma) * (dis - u_gamma) / den);
+        if (dis_out) dis_out[m] = dis;
+        if (prob_out) prob_out[m] = prob;
+    }
+}
+
+static int popcount8(unsigned char x) {
+    int c = 0;
+    while (x) {
+        c += x & 1;
+        x >>= 1;
+    }
+    return c;
+}
+
+/* Tracking.cc:1747-1766 */
+int orc_bf_match(int nq, const unsigned char *dq, int nt, const unsigned char *dt, double ratio, int *match,
+                 int *knn) {
+    int accepted = 0;
+    for (int q = 0; q < nq; q++) {
+        int d0 = -1, i0 = -1, d1 = -1, i1 = -1; /* K-best list, K = 2 */
+        for (int t = 0; t < nt; t++) {
+            int d = 0;
+            for (int k = 0; k < 32; k++) d += popcount8((unsigned char)(dq[32 * q + k] ^ dt[32 * t + k]));
+            /* insertion with strict comparisons: an equal distance never displaces an earlier row */
+            if (i0 < 0 || d < d0) {
+                d1 = d0;
+                i1 = i0;
+                d0 = d;
+                i0 = t;
+            } else if (i1 < 0 || d < d1) {
+                d1 = d;
+                i1 = t;
+            }
+        }
+        int m = -1;
+        /* :1755  match.size() == 2 && match[0].distance < match[1].distance * 0.6  (float * double) */
+        if (i1 >= 0 && (double)(float)d0 < (double)(float)d1 * ratio) m = i0;
+        match[q] = m;
+        accepted += m >= 0;
+        if (knn) {
+            knn[4 * q] = d0;
+            knn[4 * q + 1] = i0;
+            knn[4 * q + 2] = d1;
+            knn[4 * q + 3] = i1;
+        }
+    }
+    return accepted;
+}

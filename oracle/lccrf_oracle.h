@@ -92,6 +92,23 @@ void orc_slam_crf(int N, const float *observs, const float *error, const float *
                   const short *init_label, const float *energies, const orc_slam_params *prm,
                   float *Q /*[N*2]*/, short *map /*[N]*/, int *V_out /*[2] or NULL*/);
 
+/* ---- frontend feeders of the CRF ---- */
+/* Tracking::GetFeature2EpipolarDis, src/Tracking.cc:2030-2047, with
+ * FundamentalMatrixEstimator::symmetricEpipolarDistance,
+ * Thirdparty/graph-cut-ransac-master/include/fundamental_estimator.h:90-127 (needs Eigen + OpenCV: not
+ * compilable here -> PARITY UNPINNED, plain double arithmetic restated line by line, including the reference's
+ * use of y1 where y2 is meant at :121).  pt1/pt2 [M*2] float keypoints, F9 row-major.  dis/prob [M]. */
+void orc_epipolar_prior(int M, const float *pt1, const float *pt2, const double *F9, float u_gamma,
+                        float stdev_gamma, double *dis, double *prob);
+/* Tracking::BfMatch, src/Tracking.cc:1747-1766: cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + ratio test.
+ * OpenCV (opencv_features2d, version un-pinned by CMakeLists.txt:33-39) is not in the tree; the published
+ * algorithm is restated (exhaustive Hamming distances, K-best insertion with strict comparisons => ties keep
+ * the lower train index first) and PINNED against cv2 4.13 in this container (tests/golden/golden_frontend.npz,
+ * tests/golden/make_golden_frontend.py).  match [nq] (-1 = rejected), knn [nq*4] {d0,i0,d1,i1} (may be NULL).
+ * Returns the number of accepted matches. */
+int orc_bf_match(int nq, const unsigned char *desc_q, int nt, const unsigned char *desc_t, double ratio,
+                 int *match, int *knn);
+
 #ifdef __cplusplus
 }
 #endif

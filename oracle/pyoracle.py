@@ -90,6 +90,28 @@ class Oracle:
         L.orc_slam_crf.argtypes = [C.c_int, c_float_p, c_float_p, c_float_p, c_short_p, c_float_p,
                                    C.POINTER(_SlamParams), c_float_p, c_short_p, c_int_p]
 
+        L.orc_epipolar_prior.argtypes = [C.c_int, c_float_p, c_float_p, C.c_void_p, C.c_float, C.c_float,
+                                         C.c_void_p, C.c_void_p]
+        L.orc_bf_match.restype = C.c_int
+        L.orc_bf_match.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, c_int_p, c_int_p]
+
+    # -- frontend feeders --
+    def epipolar_prior(self, pt1, pt2, F, u_gamma, stdev_gamma):
+        pt1, pt2 = _f32(pt1), _f32(pt2)
+        F = np.ascontiguousarray(F, dtype=np.float64).reshape(9)
+        M = pt1.shape[0]
+        dis, prob = np.empty(M, dtype=np.float64), np.empty(M, dtype=np.float64)
+        self.lib.orc_epipolar_prior(M, _fp(pt1), _fp(pt2), F.ctypes.data, u_gamma, stdev_gamma, dis.ctypes.data, prob.ctypes.data)
+        return dis, prob
+
+    def bf_match(self, desc_q, desc_t, ratio=0.6):
+        dq = np.ascontiguousarray(desc_q, dtype=np.uint8).reshape(-1, 32)
+        dt = np.ascontiguousarray(desc_t, dtype=np.uint8).reshape(-1, 32)
+        match = np.empty(dq.shape[0], dtype=np.int32)
+        knn = np.empty((dq.shape[0], 4), dtype=np.int32)
+        n = self.lib.orc_bf_match(dq.shape[0], dq.ctypes.data, dt.shape[0], dt.ctypes.data, ratio, _ip(match), _ip(knn))
+        return match, knn, n
+
     # -- lattice --
     def lattice(self, feat: np.ndarray):
         feat = _f32(feat)

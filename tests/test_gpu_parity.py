@@ -106,6 +106,40 @@ def test_filter_parity_and_properties(pkg, ctx, oracle, d, N):
     lg.close()
 
 
+def test_filter_large_lattice_vector_blur(pkg, ctx, oracle):
+    """Lattices beyond one CTA (N > 32768, one problem) take the element-parallel blur: float4 / float2 / float
+    vectors per vertex depending on L.  Every width against the oracle, bit for bit."""
+    W, H = 250, 180
+    f = oracle.features_image(W, H, 2, 1.5)
+    lo = oracle.lattice(f)
+    lg = pkg.Lattice(ctx, f)
+    assert lg.V == lo["V"]
+    rng = np.random.default_rng(99)
+    for L in (1, 2, 3, 4, 6, 8, 12):
+        x = (rng.random((W * H, L)) * 3 - 1).astype(np.float32)
+        assert_bit_exact(lg.filter(x), oracle.filter(lo, x), what="vector blur L=%d" % L)
+    oracle.lattice_free(lo)
+    lg.close()
+
+
+def test_image_crf_c2_full_size(pkg, ctx, oracle):
+    """BASELINE configs[1] (C2) at its full size: 640x480, 2 labels, Gaussian + 5-D bilateral, 10 iterations."""
+    W, H = 640, 480
+    img, lab = synth.image_problem(W, H, 21)
+    en = pkg.label_energies(2, 0.7)
+    unary = oracle.unary_from_label(lab, 2, en[0], np.full(2, en[1], np.float32), np.full(2, en[2], np.float32))
+    Qo, mo, _ = oracle.meanfield(unary, [oracle.features_image(W, H, 2, 3.0), oracle.features_image(W, H, 5, 60.0, img, 20.0)],
+                                 [3.0, 10.0], 10)
+    crf = pkg.DenseCRF(ctx, W * H, 2)
+    crf.setUnaryEnergyFromLabel(lab, energies=en)
+    crf.addPairwiseFromImage(W, H, 3.0, 3.0)
+    crf.addPairwiseFromImage(W, H, 10.0, 60.0, img, 20.0)
+    crf.inference(10, True)
+    assert_bit_exact(crf.getProbability(), Qo, what="C2 full-size marginals")
+    assert np.array_equal(crf.getMap(), mo)
+    crf.close()
+
+
 # ------------------------------------------------------------------ driver pieces
 def test_exp_and_normalize_bit_exact(ctx, oracle):
     rng = np.random.default_rng(3)

@@ -137,3 +137,44 @@ def test_unary_restatement_properties(oracle):
     # points whose projection sits within float rounding of an image bound may legitimately differ
     close = np.isclose(er, err, rtol=2e-4, atol=2e-4) & np.isclose(de, dep, rtol=2e-4, atol=2e-4)
     assert close.mean() > 0.99
+
+
+# ------------------------------------------------------------------ frontend feeders
+def test_bf_match_vs_opencv_golden(oracle):
+    """Tracking::BfMatch restatement against cv::BFMatcher.knnMatch(k=2) outputs captured from OpenCV itself
+    (tests/golden/make_golden_frontend.py): nearest-two lists incl. tie order, and the 0.6 ratio test."""
+    g = np.load(os.path.join(GOLD, "golden_frontend.npz"))
+    for name in ("orb", "ties", "one_train_row", "two_train_rows", "ragged"):
+        match, knn, n = oracle.bf_match(g[name + "_dq"], g[name + "_dt"], 0.6)
+        assert np.array_equal(knn, g[name + "_knn"]), name
+        assert np.array_equal(match, g[name + "_match"]), name
+        assert n == int((g[name + "_match"] >= 0).sum())
+    # empty train / query sets: no correspondences, no crash
+    m, k, n = oracle.bf_match(g["orb_dq"][:5], np.zeros((0, 32), np.uint8))
+    assert (m == -1).all() and n == 0
+    m, k, n = oracle.bf_match(np.zeros((0, 32), np.uint8), g["orb_dt"])
+    assert m.size == 0 and n == 0
+
+
+def test_epipolar_prior_restatement(oracle):
+    """symmetricEpipolarDistance + likelihood (fundamental_estimator.h:90-127, Tracking.cc:2043) against an independent
+    numpy float64 evaluation of the same expressions (numpy rounds every operation, like the -O3 no-FMA build)."""
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    x1, x2, F, out = synth.epipolar_matches(500, 3)
+    dis, prob = oracle.epipolar_prior(x1, x2, F, 0.5, 1.1)
+    a, b = x1.astype(np.float64), x2.astype(np.float64)
+    f = F.reshape(3, 3)
+    l1 = f[0, 0] * b[:, 0] + f[1, 0] * b[:, 1] + f[2, 0]
+    l2 = f[0, 1] * b[:, 0] + f[1, 1] * b[:, 1] + f[2, 1]
+    l3 = f[0, 2] * b[:, 0] + f[1, 2] * b[:, 1] + f[2, 2]
+    t1 = f[0, 0] * a[:, 0] + f[0, 1] * a[:, 1] + f[0, 2]
+    t2 = f[1, 0] * a[:, 0] + f[1, 1] * a[:, 1] + f[1, 2]
+    t3 = f[2, 0] * a[:, 0] + f[2, 1] * a[:, 1] + f[2, 2]
+    d1 = (l1 * a[:, 0] + l2 * a[:, 1] + l3) / np.sqrt(l1 * l1 + l2 * l2)
+    d2 = (t1 * b[:, 0] + t2 * a[:, 1] + t3) / np.sqrt(t1 * t1 + t2 * t2)  # y1, as fundamental_estimator.h:121 has it
+    want = np.abs(0.5 * (d1 + d2))
+    assert np.array_equal(dis.view(np.int64), want.view(np.int64))
+    den = np.float64(np.float32(2) * np.float32(1.1) * np.float32(1.1))
+    wp = np.exp(-(want - np.float64(np.float32(0.5))) * (want - np.float64(np.float32(0.5))) / den)
+    assert np.allclose(prob, wp, rtol=4e-16, atol=0)
+    assert np.median(dis[~out]) < np.median(dis[out])  # displaced matches sit further from their epipolar lines
