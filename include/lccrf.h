@@ -225,6 +225,18 @@ int lccrf_frames_submit_map(lccrf_frames *fr, int slot, const float *xyz, const 
 int lccrf_frames_submit(lccrf_frames *fr, int slot, const float *observs, const float *error, const float *depth,
                         const float *kp2d, short *map_out, float *prob_out);
 int lccrf_frames_wait(lccrf_frames *fr, int slot);
+/* Label application, the hand-off after inference: replaces the scan of res_label in
+ *   Tracking::DynamicDetectionWithCRF   src/Tracking.cc:1945-1955
+ *     for (i < N) if (res_label[i] == 0) { maps.erase(fid); pMP->SetBadFlag(); mvpMapPoints[fid] = NULL; }
+ * by a stable partition of the batch's MAP labels computed on the device: dyn_list holds, problem after problem and
+ * in point order, the points labelled moving (label 0) -- exactly the elements the reference loop acts on, in its
+ * order -- and stat_list the survivors (label 1) that the second PoseOptimization (Tracking.cc:1002) keeps.
+ * Problem b owns dyn_list[dyn_ptr[b] .. dyn_ptr[b+1]) and stat_list[stat_ptr[b] .. stat_ptr[b+1]).  An element is
+ * fid[i] (featureMapAssos[i].fid, [NT]) when fid is given, else the point's index inside its problem.
+ * dyn_ptr / stat_ptr: [B+1]; dyn_list / stat_list: [NT] (only the first dyn_ptr[B] / stat_ptr[B] entries are
+ * written).  Any output may be NULL.  Valid after lccrf_frames_run / lccrf_frames_wait; synchronises. */
+int lccrf_frames_partition(lccrf_frames *fr, const int *fid, int *dyn_ptr, int *dyn_list, int *stat_ptr,
+                           int *stat_list);
 /* diagnostics: init labels [NT], unary-derived vectors, per-problem lattice sizes [B*2] */
 int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth,
                            int *V);
@@ -234,6 +246,40 @@ int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, 
 int lccrf_frames_debug_counters(lccrf_frames *fr, int k, int *out8);
 /* algorithmic bytes of one lccrf_frames_run by the SURVEY 8(d) formulas with the actual V (valid after a run) */
 int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_iteration, double *unary);
+
+/* ---------------------------------------------------------------- snapshot / replay files - */
+/* CRF-input snapshot format (host-only, no device needed).  A file holds, frame after frame, the flat
+ * restatement of what Tracking::DynamicDetectionWithCRF gathers (src/Tracking.cc:1849-1870) and what
+ * ComputeMapPointErrAndObserv dereferences (:1803-1839) -- the lccrf_frames_set_map_inputs layout plus the feature
+ * id of every point (featureMapAssos[i].fid) -- so a TUM/Bonn sequence can be replayed through the CRF without
+ * ORB-SLAM.  Byte layout: lc-crf-slam_b200/csrc/snapshot.cu.  Records are appended and individually checksummed; a
+ * file cut off by a crash still yields every complete frame (lccrf_snapshot_truncated tells). */
+typedef struct lccrf_snapshot_writer lccrf_snapshot_writer;
+typedef struct lccrf_snapshot_reader lccrf_snapshot_reader;
+typedef struct lccrf_snapshot_info {
+    int N, nKF;
+    long long nnz;
+    long long frame_id;  /* mCurrentFrame.mnId */
+    double timestamp;
+    int stored_kf_bytes; /* 2: keyframe indices stored as uint16 (nKF <= 65536), 4: int32 */
+} lccrf_snapshot_info;
+/* append != 0 continues an existing file (created when missing) */
+int lccrf_snapshot_writer_open(const char *path, int append, lccrf_snapshot_writer **out);
+/* one frame; arrays as in lccrf_map_point_unary, kp2d [N*2], fid [N] (NULL = 0..N-1).  Validates the CSR. */
+int lccrf_snapshot_write_frame(lccrf_snapshot_writer *w, long long frame_id, double timestamp, int N, const float *xyz,
+                               const int *obs_ptr, const int *obs_kf, const float *obs_uv, int nKF, const float *kf_pose,
+                               const float *kf_intr, const float *kf_bounds, const float *kp2d, const int *fid);
+int lccrf_snapshot_writer_close(lccrf_snapshot_writer *w);
+int lccrf_snapshot_reader_open(const char *path, lccrf_snapshot_reader **out);
+void lccrf_snapshot_reader_close(lccrf_snapshot_reader *r);
+int lccrf_snapshot_num_frames(const lccrf_snapshot_reader *r);
+int lccrf_snapshot_truncated(const lccrf_snapshot_reader *r);
+int lccrf_snapshot_frame_info(const lccrf_snapshot_reader *r, int i, lccrf_snapshot_info *info);
+/* read frame i into caller buffers sized from frame_info (any pointer may be NULL); obs_kf comes back as int32
+ * (obs_kf_bytes = 4) or uint16 (2, what lccrf_frames_submit_map takes).  Verifies the checksum and the structure
+ * (CSR monotone, keyframe indices in range) and fails with LCCRF_ERR_STATE on a corrupt frame. */
+int lccrf_snapshot_read_frame(lccrf_snapshot_reader *r, int i, float *xyz, int *obs_ptr, void *obs_kf, int obs_kf_bytes,
+                              float *obs_uv, float *kf_pose, float *kf_intr, float *kf_bounds, float *kp2d, int *fid);
 
 #ifdef __cplusplus
 }

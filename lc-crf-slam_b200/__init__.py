@@ -106,9 +106,19 @@ SYMBOLS = {
     "lccrf_frames_submit_map": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_submit": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_wait": (C.c_int, [_vp, C.c_int]),
+    "lccrf_frames_partition": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_get_debug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_debug_counters": (C.c_int, [_vp, C.c_int, _vp]),
     "lccrf_frames_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lccrf_snapshot_writer_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_vp)]),
+    "lccrf_snapshot_write_frame": (C.c_int, [_vp, C.c_longlong, C.c_double, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_snapshot_writer_close": (C.c_int, [_vp]),
+    "lccrf_snapshot_reader_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "lccrf_snapshot_reader_close": (None, [_vp]),
+    "lccrf_snapshot_num_frames": (C.c_int, [_vp]),
+    "lccrf_snapshot_truncated": (C.c_int, [_vp]),
+    "lccrf_snapshot_frame_info": (C.c_int, [_vp, C.c_int, _vp]),
+    "lccrf_snapshot_read_frame": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -448,6 +458,18 @@ class Frames:
     def wait(self, slot):
         self.ctx._check(self.ctx.lib.lccrf_frames_wait(self.h, slot))
 
+    def partition(self, fid=None):
+        """Label application (Tracking.cc:1945-1955): per-problem lists of moving / static points in point order.
+        Returns (dyn_ptr, dyn_list, stat_ptr, stat_list); list elements are fid[i] when fid is given, else the
+        point's index inside its problem."""
+        fid = _arr(fid, np.int32)
+        if fid is not None and fid.size != self.NT:
+            raise LccrfError("fid must have one entry per point")
+        dyn_ptr, stat_ptr = np.empty(self.B + 1, dtype=np.int32), np.empty(self.B + 1, dtype=np.int32)
+        dyn, stat = np.empty(self.NT, dtype=np.int32), np.empty(self.NT, dtype=np.int32)
+        self.ctx._check(self.ctx.lib.lccrf_frames_partition(self.h, _ptr(fid), _ptr(dyn_ptr), _ptr(dyn), _ptr(stat_ptr), _ptr(stat)))
+        return dyn_ptr, dyn[:dyn_ptr[-1]].copy(), stat_ptr, stat[:stat_ptr[-1]].copy()
+
     def get_debug(self):
         lab = np.empty(self.NT, dtype=np.int16)
         ob, er, de = (np.empty(self.NT, dtype=np.float32) for _ in range(3))
@@ -475,3 +497,128 @@ class Frames:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------ snapshot / replay files (host only)
+class SnapshotInfo(C.Structure):
+    _fields_ = [("N", C.c_int), ("nKF", C.c_int), ("nnz", C.c_longlong), ("frame_id", C.c_longlong),
+                ("timestamp", C.c_double), ("stored_kf_bytes", C.c_int)]
+
+
+def _snap_check(lib, rc):
+    if rc != 0:
+        raise LccrfError(f"liblccrf error {rc}: {lib.lccrf_last_error().decode()}")
+
+
+class SnapshotWriter:
+    """Appends CRF-input frames (the lccrf_frames_set_map_inputs layout + feature ids) to an LCCRFSNP file."""
+
+    def __init__(self, path: str, append: bool = False):
+        self.lib = load_library()
+        self.h = _vp()
+        _snap_check(self.lib, self.lib.lccrf_snapshot_writer_open(os.fsencode(path), int(append), C.byref(self.h)))
+
+    def write(self, snap, frame_id: int = 0, timestamp: float = 0.0, fid=None):
+        """snap: any object with xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d (synth.MapSnapshot)."""
+        xyz, ptr, kf, uv = _arr(snap.xyz, np.float32), _arr(snap.obs_ptr, np.int32), _arr(snap.obs_kf, np.int32), _arr(snap.obs_uv, np.float32)
+        pose, intr, bnd, kp = (_arr(a, np.float32) for a in (snap.kf_pose, snap.kf_intr, snap.kf_bounds, snap.kp2d))
+        fid = _arr(fid, np.int32)
+        n = int(xyz.shape[0])
+        if ptr.size != n + 1 or kp.size != 2 * n or (fid is not None and fid.size != n):
+            raise LccrfError("inconsistent snapshot arrays")
+        _snap_check(self.lib, self.lib.lccrf_snapshot_write_frame(
+            self.h, int(frame_id), float(timestamp), n, _ptr(xyz), _ptr(ptr), _ptr(kf), _ptr(uv), int(pose.shape[0]),
+            _ptr(pose), _ptr(intr), _ptr(bnd), _ptr(kp), _ptr(fid)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            h, self.h = self.h, None
+            _snap_check(self.lib, self.lib.lccrf_snapshot_writer_close(h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class SnapshotFrame:
+    """One frame read back from a snapshot file (same attribute names as synth.MapSnapshot)."""
+
+    def __init__(self, info, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d, fid):
+        self.frame_id, self.timestamp = int(info.frame_id), float(info.timestamp)
+        self.xyz, self.obs_ptr, self.obs_kf, self.obs_uv = xyz, obs_ptr, obs_kf, obs_uv
+        self.kf_pose, self.kf_intr, self.kf_bounds, self.kp2d, self.fid = kf_pose, kf_intr, kf_bounds, kp2d, fid
+
+    @property
+    def n(self):
+        return int(self.xyz.shape[0])
+
+    @property
+    def nnz(self):
+        return int(self.obs_kf.shape[0])
+
+
+class SnapshotReader:
+    """Random access to the frames of an LCCRFSNP file; every read verifies checksum and structure."""
+
+    def __init__(self, path: str):
+        self.lib = load_library()
+        self.h = _vp()
+        _snap_check(self.lib, self.lib.lccrf_snapshot_reader_open(os.fsencode(path), C.byref(self.h)))
+
+    def __len__(self):
+        return int(self.lib.lccrf_snapshot_num_frames(self.h))
+
+    @property
+    def truncated(self) -> bool:
+        return bool(self.lib.lccrf_snapshot_truncated(self.h))
+
+    def info(self, i: int) -> SnapshotInfo:
+        inf = SnapshotInfo()
+        _snap_check(self.lib, self.lib.lccrf_snapshot_frame_info(self.h, int(i), C.byref(inf)))
+        return inf
+
+    def read(self, i: int, kf_dtype=np.int32) -> SnapshotFrame:
+        inf = self.info(i)
+        n, nnz, nkf = inf.N, int(inf.nnz), inf.nKF
+        xyz, ptr = np.empty((n, 3), np.float32), np.empty(n + 1, np.int32)
+        kf, uv = np.empty(nnz, kf_dtype), np.empty((nnz, 2), np.float32)
+        pose, intr, bnd = np.empty((nkf, 12), np.float32), np.empty((nkf, 4), np.float32), np.empty((nkf, 4), np.float32)
+        kp, fid = np.empty((n, 2), np.float32), np.empty(n, np.int32)
+        _snap_check(self.lib, self.lib.lccrf_snapshot_read_frame(
+            self.h, int(i), _ptr(xyz), _ptr(ptr), _ptr(kf), int(np.dtype(kf_dtype).itemsize), _ptr(uv), _ptr(pose), _ptr(intr),
+            _ptr(bnd), _ptr(kp), _ptr(fid)))
+        return SnapshotFrame(inf, xyz, ptr, kf, uv, pose, intr, bnd, kp, fid)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lccrf_snapshot_reader_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def concat_frames(frames):
+    """Concatenate map snapshots / snapshot frames into one batch for Frames.set_map_inputs / submit_map: CSR pointers
+    and keyframe indices are rebased, kf_ptr [B+1] names every problem's keyframe slice, fid is carried along."""
+    ptr, kf, eo, ko = [np.zeros(1, np.int64)], [], 0, 0
+    for s in frames:
+        ptr.append(s.obs_ptr[1:].astype(np.int64) + eo)
+        kf.append(s.obs_kf.astype(np.int64) + ko)
+        eo += int(s.obs_kf.shape[0])
+        ko += int(s.kf_pose.shape[0])
+    kf_ptr = np.zeros(len(frames) + 1, dtype=np.int32)
+    np.cumsum([s.kf_pose.shape[0] for s in frames], out=kf_ptr[1:])
+    cat = lambda k, shape: (np.concatenate([getattr(s, k).reshape(shape) for s in frames]) if frames else np.zeros(shape if shape[0] != -1 else (0,) + shape[1:], np.float32))
+    out = dict(xyz=cat("xyz", (-1, 3)), obs_ptr=np.concatenate(ptr).astype(np.int32),
+               obs_kf=(np.concatenate(kf) if kf else np.zeros(0)).astype(np.int32), obs_uv=cat("obs_uv", (-1, 2)),
+               kf_pose=cat("kf_pose", (-1, 12)), kf_intr=cat("kf_intr", (-1, 4)), kf_bounds=cat("kf_bounds", (-1, 4)),
+               kp2d=cat("kp2d", (-1, 2)), kf_ptr=kf_ptr)
+    if frames and all(getattr(s, "fid", None) is not None for s in frames):
+        out["fid"] = np.concatenate([s.fid for s in frames]).astype(np.int32)
+    return out

@@ -213,6 +213,7 @@ struct lccrf_frames {
     FrameInputs in[2];
     int last_slot = 0;
     bool ran = false;
+    int *part = nullptr;  // label application workspace: dyn_ptr, stat_ptr [B+1], dyn_list, stat_list, fid [NT], tiles
 };
 
 extern "C" {
@@ -994,6 +995,7 @@ void lccrf_frames_destroy(lccrf_frames *fr) {
     dev_free(ctx, fr->feat2);
     dev_free(ctx, fr->label);
     dev_free(ctx, fr->d_en);
+    dev_free(ctx, fr->part);
     delete fr;
 }
 
@@ -1340,6 +1342,35 @@ int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, 
     if (V)
         for (int i = 0; i < fr->b.B; i++)
             for (int k = 0; k < 2; k++) V[2 * i + k] = vb[k][i + 1] - vb[k][i];
+    return LCCRF_OK;
+}
+
+// label application (Tracking.cc:1945-1955): stable partition of the batch's MAP labels
+int lccrf_frames_partition(lccrf_frames *fr, const int *fid, int *dyn_ptr, int *dyn_list, int *stat_ptr, int *stat_list) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_partition before frames_run");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const int NT = fr->b.NT, B = fr->b.B;
+    const size_t nB = (size_t)(B + 1), nT = (size_t)(NT > 0 ? NT : 1);
+    if (!fr->part)
+        LCCRF_TRY(dev_alloc(ctx, (void **)&fr->part, (2 * nB + 3 * nT) * sizeof(int) + label_partition_scratch_bytes(NT)));
+    int *d_dyn_ptr = fr->part, *d_stat_ptr = d_dyn_ptr + nB, *d_dyn = d_stat_ptr + nB, *d_stat = d_dyn + nT,
+        *d_fid = d_stat + nT, *d_scratch = d_fid + nT;
+    cudaStream_t st = ctx->stream;
+    if (fid && NT) LCCRF_CUDA(cudaMemcpyAsync(d_fid, fid, (size_t)NT * 4, cudaMemcpyHostToDevice, st));
+    LCCRF_TRY(label_partition(ctx, fr->b.map, NT, fr->b.prob_ptr, B, fid ? d_fid : nullptr, d_scratch, d_dyn_ptr, d_dyn,
+                              d_stat_ptr, d_stat));
+    std::vector<int> hp(2 * nB);
+    LCCRF_CUDA(cudaMemcpyAsync(hp.data(), d_dyn_ptr, 2 * nB * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));
+    const int n_dyn = hp[B], n_stat = hp[nB + B];
+    if (n_dyn < 0 || n_stat < 0 || n_dyn + n_stat != NT) return fail(LCCRF_ERR_STATE, "label partition is inconsistent");
+    if (dyn_ptr) memcpy(dyn_ptr, hp.data(), nB * sizeof(int));
+    if (stat_ptr) memcpy(stat_ptr, hp.data() + nB, nB * sizeof(int));
+    if (dyn_list && n_dyn) LCCRF_CUDA(cudaMemcpyAsync(dyn_list, d_dyn, (size_t)n_dyn * 4, cudaMemcpyDeviceToHost, st));
+    if (stat_list && n_stat) LCCRF_CUDA(cudaMemcpyAsync(stat_list, d_stat, (size_t)n_stat * 4, cudaMemcpyDeviceToHost, st));
+    LCCRF_CUDA(cudaStreamSynchronize(st));
     return LCCRF_OK;
 }
 

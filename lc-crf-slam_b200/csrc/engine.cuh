@@ -206,6 +206,11 @@ bool uniform_camera(const float *kf_intr, const float *kf_bounds, int nKF, float
 int unary_classify(Ctx *ctx, int N, const float *observs, const float *error, const float *depth,
                    const double *p4, const lccrf_slam_params &prm, short *label);
 
+// label application (apply.cu): stable partition of MAP labels into moving / static lists; all device pointers
+size_t label_partition_scratch_bytes(int NT);
+int label_partition(Ctx *ctx, const short *map, int NT, const int *prob_ptr, int B, const int *fid, int *scratch,
+                    int *dyn_ptr, int *dyn_list, int *stat_ptr, int *stat_list);
+
 // frontend (frontend.cu): epipolar prior and brute-force Hamming kNN; all pointers are device pointers
 int epipolar_prior(Ctx *ctx, int M, const int *fid1, const float *pt1, const float *pt2, const double *F9_host,
                    float u_gamma, float stdev_gamma, int nFeat, double *dis_by_fid, double *prob_by_fid, double *dis_m,

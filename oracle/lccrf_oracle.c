@@ -591,3 +591,16 @@ int orc_bf_match(int nq, const unsigned char *dq, int nt, const unsigned char *d
     }
     return accepted;
 }
+
+/* Tracking.cc:1945-1955: the loop that acts on every point labelled moving.  One problem; `dyn` receives, in loop
+ * order, the element the loop body touches for each res_label[i] == 0 (fid = featureMapAssos[i].fid, or i itself
+ * when fid is NULL), `stat` the points the loop leaves alone.  Returns the number of moving points. */
+int orc_label_partition(int N, const short *res_label, const int *fid, int *dyn, int *stat) {
+    int nd = 0, ns = 0;
+    for (int i = 0; i < N; i++) {          /* :1946 */
+        const int v = fid ? fid[i] : i;    /* :1948 */
+        if (res_label[i] == 0) dyn[nd++] = v; /* :1949-1954 */
+        else stat[ns++] = v;
+    }
+    return nd;
+}

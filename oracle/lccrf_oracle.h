@@ -109,6 +109,9 @@ void orc_epipolar_prior(int M, const float *pt1, const float *pt2, const double 
 int orc_bf_match(int nq, const unsigned char *desc_q, int nt, const unsigned char *desc_t, double ratio,
                  int *match, int *knn);
 
+/* Tracking.cc:1945-1955 label application: ordered lists of moving (label 0) and static points of one problem */
+int orc_label_partition(int N, const short *res_label, const int *fid, int *dyn, int *stat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,16 @@ class Oracle:
         L.orc_bf_match.restype = C.c_int
         L.orc_bf_match.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, c_int_p, c_int_p]
 
+    # -- label application (Tracking.cc:1945-1955) --
+    def label_partition(self, res_label, fid=None):
+        lab = np.ascontiguousarray(res_label, dtype=np.int16)
+        f = None if fid is None else np.ascontiguousarray(fid, dtype=np.int32)
+        dyn, stat = np.empty(lab.size, dtype=np.int32), np.empty(lab.size, dtype=np.int32)
+        self.lib.orc_label_partition.restype = C.c_int
+        self.lib.orc_label_partition.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        nd = self.lib.orc_label_partition(lab.size, lab.ctypes.data, None if f is None else f.ctypes.data, dyn.ctypes.data, stat.ctypes.data)
+        return dyn[:nd].copy(), stat[:lab.size - nd].copy()
+
     # -- frontend feeders --
     def epipolar_prior(self, pt1, pt2, F, u_gamma, stdev_gamma):
         pt1, pt2 = _f32(pt1), _f32(pt2)

@@ -403,6 +403,42 @@ def test_frames_batch_parity(pkg, ctx, oracle):
     F.close()
 
 
+def test_frames_label_partition(pkg, ctx, oracle):
+    """Label application (Tracking.cc:1945-1955): the device's stable partition of the MAP labels lists, per problem
+    and in point order, exactly the elements the reference loop acts on -- with feature ids and with local indices;
+    empty problems (leading, inner, trailing) and tile-crossing problems included."""
+    prm = pkg.SlamParams.make()
+    sizes = [0, 0, 1, 3000, 0, 2047, 2048, 2049, 5000, 1, 0, 0]
+    frames = [synth.slam_frame(n, seed=300 + i) for i, n in enumerate(sizes)]
+    F = pkg.Frames(ctx, sizes, prm)
+    with pytest.raises(pkg.LccrfError):
+        F.partition()  # before a run
+    cat = lambda k: np.concatenate([getattr(f, k) for f in frames])
+    F.set_inputs(cat("observs"), cat("error"), cat("depth"), cat("kp2d"))
+    F.run()
+    mp, _ = F.get_outputs()
+    assert 0 < int((mp == 0).sum()) < mp.size  # both classes present
+    rng = np.random.default_rng(3)
+    fid = np.concatenate([rng.permutation(4 * n)[:n] for n in sizes]).astype(np.int32)
+    for f in (None, fid):
+        dp, dl, sp, sl = F.partition(f)
+        assert dp[0] == 0 and sp[0] == 0 and dp[-1] + sp[-1] == mp.size
+        o = 0
+        for b, n in enumerate(sizes):
+            d_ref, s_ref = oracle.label_partition(mp[o:o + n], None if f is None else f[o:o + n])
+            assert np.array_equal(dl[dp[b]:dp[b + 1]], d_ref), b
+            assert np.array_equal(sl[sp[b]:sp[b + 1]], s_ref), b
+            o += n
+    F.close()
+    # a batch of nothing
+    F0 = pkg.Frames(ctx, [0, 0], prm)
+    F0.set_inputs(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 2), np.float32))
+    F0.run()
+    dp, dl, sp, sl = F0.partition()
+    assert dp.tolist() == [0, 0, 0] and sp.tolist() == [0, 0, 0] and dl.size == 0 and sl.size == 0
+    F0.close()
+
+
 def test_frames_from_map_snapshot_c3_small(pkg, ctx, oracle):
     """C3 pipeline at reduced size: unary from the map snapshot -> classify -> CRF, all on the device."""
     prm_o, prm = oracle_params(), pkg.SlamParams.make()

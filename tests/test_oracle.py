@@ -178,3 +178,16 @@ def test_epipolar_prior_restatement(oracle):
     wp = np.exp(-(want - np.float64(np.float32(0.5))) * (want - np.float64(np.float32(0.5))) / den)
     assert np.allclose(prob, wp, rtol=4e-16, atol=0)
     assert np.median(dis[~out]) < np.median(dis[out])  # displaced matches sit further from their epipolar lines
+
+
+def test_label_partition_restatement(oracle):
+    """Tracking.cc:1945-1955: the loop acts on exactly the label-0 points, in point order."""
+    rng = np.random.default_rng(9)
+    lab = (rng.random(1000) < 0.7).astype(np.int16)
+    fid = rng.permutation(5000)[:1000].astype(np.int32)
+    d, s = oracle.label_partition(lab)
+    assert np.array_equal(d, np.nonzero(lab == 0)[0]) and np.array_equal(s, np.nonzero(lab != 0)[0])
+    d, s = oracle.label_partition(lab, fid)
+    assert np.array_equal(d, fid[lab == 0]) and np.array_equal(s, fid[lab != 0])
+    d, s = oracle.label_partition(np.zeros(0, np.int16))
+    assert d.size == 0 and s.size == 0
