@@ -62,6 +62,9 @@ WORKLOADS = {
 }
 
 
+KP_STRIDE = 32768  # keypoint slots per keyframe of the resident table (C3: ~24k observations per keyframe)
+
+
 def make_problems(workload: str, batch: int, seed0: int):
     """Seeded synthetic problems.  Returns a list of MapSnapshot (c3) or SlamFrame (c1/c4)."""
     synth = importlib.import_module("lc-crf-slam_b200.synth")
@@ -282,6 +285,7 @@ def blur_measurements(pkg, ctx, peak):
 def run_gpu_arm(args):
     import torch
     pkg = importlib.import_module("lc-crf-slam_b200")
+    synth_mod = importlib.import_module("lc-crf-slam_b200.synth")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -310,6 +314,20 @@ def run_gpu_arm(args):
     keep = []
     if args.workload == "c3":
         cat = concat_snapshots(problems)
+        # the same observations as (keyframe, feature index) pairs + per-keyframe keypoint rows; obs_uv is replaced by
+        # its consistent flat form so that the device-resident runs and both end-to-end paths work on ONE problem set
+        fids, tabs, uvs, ko = [], [], [], 0
+        for i, p in enumerate(problems):
+            fid, tab, uvc = synth_mod.index_observations(p.obs_kf, p.obs_uv, p.kf_pose.shape[0], seed=77 + i, stride=KP_STRIDE)
+            fids.append(np.stack([p.obs_kf + ko, fid], axis=1).astype(np.uint16))
+            tabs.append(tab)
+            uvs.append(uvc)
+            ko += p.kf_pose.shape[0]
+        assert ko <= 65536
+        cat["obs_uv"] = np.concatenate(uvs)
+        cat["obs_ref"] = np.concatenate(fids)
+        kp_table = np.concatenate(tabs)
+        del fids, tabs, uvs
         host = {}
         for k, v in cat.items():
             host[k], t = pinned(v)
@@ -366,43 +384,71 @@ def run_gpu_arm(args):
         o2m, o2p = torch.empty(NT, dtype=torch.int16).pin_memory(), torch.empty((NT, 2), dtype=torch.float32).pin_memory()
         keep += [o2m, o2p]
         outs.append((o2m.numpy(), o2p.numpy()))
+        e2e_mode = "direct per-frame vectors"
         if args.workload == "c3":
             if nKF <= 65536:  # compact snapshot: uint16 keyframe indices
                 host["obs_kf"], t = pinned(host["obs_kf"].astype(np.uint16))
                 keep.append(t)
-            h2d = sum(int(v.nbytes) for v in host.values())
+            h2d_flat = sum(int(v.nbytes) for k, v in host.items() if k not in ("obs_ref",))
 
-            def submit(slot):
+            def submit_flat(slot):
                 F.submit_map(slot, host["xyz"], host["obs_ptr"], host["obs_kf"], host["obs_uv"], host["kf_pose"],
                              host["kf_intr"], host["kf_bounds"], host["kp2d"], host["kf_ptr"], *outs[slot])
+            # headline end-to-end path: observations as (keyframe, feature index) pairs -- the reference's own
+            # MapPoint::mObservations entries -- against keyframe keypoint arrays that are uploaded ONCE, when a
+            # keyframe is inserted (KeyFrame::mvKeysUn never changes afterwards; the reference's CPU path likewise
+            # reads them from the resident KeyFrame objects, not from per-frame inputs).  Everything that changes
+            # from frame to frame (points, observation lists, keyframe poses, keypoints of the frame) is copied
+            # from pinned host memory every step.
+            F.set_keyframe_keypoints(kp_table)
+            kp_table_bytes = int(kp_table.nbytes)
+            del kp_table
+            h2d = sum(int(host[k].nbytes) for k in ("xyz", "obs_ptr", "obs_ref", "kf_pose", "kf_intr", "kf_bounds", "kp2d", "kf_ptr"))
+            e2e_mode = ("indexed observations (uint16 keyframe, uint16 feature index) + resident keyframe keypoint "
+                        "table (%.0f MB, uploaded once at keyframe insertion, not per step)" % (kp_table_bytes / 1e6))
+
+            def submit(slot):
+                F.submit_map_indexed(slot, host["xyz"], host["obs_ptr"], host["obs_ref"], host["kf_pose"],
+                                     host["kf_intr"], host["kf_bounds"], host["kp2d"], host["kf_ptr"], *outs[slot])
         else:
+            submit_flat, h2d_flat = None, 0
+
             def submit(slot):
                 F.submit(slot, host["observs"], host["error"], host["depth"], host["kp2d"], *outs[slot])
 
-        def e2e_loop(n):
+        def e2e_loop(n, sub):
             for i in range(n):
                 if i >= 2:
                     F.wait(i & 1)
-                submit(i & 1)
+                sub(i & 1)
             F.wait(0)
             F.wait(1)
-        e2e_loop(4)
+
+        def e2e_time(sub, n):
+            e2e_loop(4, sub)
+            barrier()
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            e2e_loop(n, sub)
+            e1.record(stream)
+            barrier()
+            return max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+        F.get_outputs(out_map, out_prob)  # results of the device-resident runs: both end-to-end paths must deliver them
         ref_map, ref_prob = out_map.copy(), out_prob.copy()
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        e2e_loop(args.steps)
-        e1.record(stream)
-        barrier()
-        ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
-        clocks = sampler.stop() if sampler else None
+        ms_e2e = e2e_time(submit, args.steps)
         for m_, p_ in outs[:min(2, args.steps)]:  # both slots delivered the same (deterministic) results
             assert np.array_equal(m_, ref_map) and np.array_equal(p_.view(np.int32), ref_prob.view(np.int32))
-    t_dev = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        # the same steps with the complete flat snapshot (every observed keypoint travels with its observation)
+        n_flat = min(args.steps, 20)
+        ms_flat = e2e_time(submit_flat, n_flat) * args.steps / n_flat if submit_flat else 0.0
+        clocks = sampler.stop() if sampler else None
+        for m_, p_ in outs[:min(2, args.steps)]:
+            assert np.array_equal(m_, ref_map) and np.array_equal(p_.view(np.int32), ref_prob.view(np.int32))
+    t_dev = torch.tensor([ms, ms_e2e, ms_flat], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)  # max over ranks
-    ms, ms_e2e = (float(x) for x in t_dev.tolist())
+    ms, ms_e2e, ms_flat = (float(x) for x in t_dev.tolist())
     total_problems = world * batch * args.steps
     value = total_problems / (ms * 1e-3)
     e2e_value = total_problems / (ms_e2e * 1e-3)
@@ -493,7 +539,11 @@ def run_gpu_arm(args):
                    "sharding": "independent problems per rank, no collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "inputs": e2e_mode},
+        "e2e_full_snapshot": None if not ms_flat else {
+            "value": total_problems / (ms_flat * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_flat,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms_flat / args.steps,
+            "inputs": "flat snapshot: every observation carries its keypoint (uint16 keyframe index + float2), nothing resident"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "blur": blur,

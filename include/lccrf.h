@@ -222,6 +222,25 @@ int lccrf_frames_submit_map(lccrf_frames *fr, int slot, const float *xyz, const 
                             int obs_kf_bytes, const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
                             const float *kf_bounds, const float *kp2d, const int *kf_ptr, short *map_out,
                             float *prob_out);
+/* Resident keyframe keypoints + indexed observations.  In the reference an observation is the pair
+ * (KeyFrame*, feature index) of MapPoint::mObservations (std::map<KeyFrame*, size_t>, include/MapPoint.h:115); the
+ * observed keypoint is looked up as pKF->mvKeysUn[idx].pt (src/Tracking.cc:1831), a per-keyframe array that never
+ * changes once the keyframe exists (include/KeyFrame.h:164).  This entry keeps those arrays resident in HBM:
+ * keyframes [kf_first, kf_first + kf_count) get kp_uv [kf_count][stride][2] (undistorted keypoints, rows padded to
+ * `stride` = the extractor's feature budget); the table grows as keyframes are inserted, earlier rows stay.
+ * Synchronises; not to be called while a submission is in flight. */
+int lccrf_frames_set_keyframe_keypoints(lccrf_frames *fr, int kf_first, int kf_count, int stride, const float *kp_uv);
+/* lccrf_frames_set_map_inputs / lccrf_frames_submit_map with indexed observations: obs_ref [nnz][2] holds
+ * {keyframe index, feature index} as uint16 pairs (index_bytes = 2: nKF and stride <= 65536) or int32 pairs
+ * (index_bytes = 4); the keypoint of observation e is kp_table[obs_ref[e].kf][obs_ref[e].fid].  4 instead of 10 bytes
+ * per observation cross PCIe.  Feature indices must be < stride (not checked: host-side O(nnz) work). */
+int lccrf_frames_set_map_inputs_indexed(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const void *obs_ref,
+                                        int index_bytes, int nKF, const float *kf_pose, const float *kf_intr,
+                                        const float *kf_bounds, const float *kp2d, const int *kf_ptr);
+int lccrf_frames_submit_map_indexed(lccrf_frames *fr, int slot, const float *xyz, const int *obs_ptr, const void *obs_ref,
+                                    int index_bytes, int nKF, const float *kf_pose, const float *kf_intr,
+                                    const float *kf_bounds, const float *kp2d, const int *kf_ptr, short *map_out,
+                                    float *prob_out);
 int lccrf_frames_submit(lccrf_frames *fr, int slot, const float *observs, const float *error, const float *depth,
                         const float *kp2d, short *map_out, float *prob_out);
 int lccrf_frames_wait(lccrf_frames *fr, int slot);

@@ -104,6 +104,9 @@ SYMBOLS = {
     "lccrf_frames_run": (C.c_int, [_vp]),
     "lccrf_frames_get_outputs": (C.c_int, [_vp, _vp, _vp]),
     "lccrf_frames_submit_map": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_set_keyframe_keypoints": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "lccrf_frames_set_map_inputs_indexed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_submit_map_indexed": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_submit": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_wait": (C.c_int, [_vp, C.c_int]),
     "lccrf_frames_partition": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -449,6 +452,32 @@ class Frames:
         assert obs_kf.dtype in (np.int32, np.uint16)
         self.ctx._check(self.ctx.lib.lccrf_frames_submit_map(
             self.h, slot, _ptr(xyz), _ptr(obs_ptr), _ptr(obs_kf), kb, _ptr(obs_uv), kf_pose.shape[0], _ptr(kf_pose),
+            _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d), _ptr(kf_ptr), _ptr(map_out), _ptr(prob_out)))
+
+    def set_keyframe_keypoints(self, kp_table, kf_first=0):
+        """Resident keyframe keypoints (KeyFrame::mvKeysUn): kp_table [n_kf][stride][2] float32 for keyframes
+        [kf_first, kf_first + n_kf).  Uploaded once per keyframe, not per step."""
+        kp_table = _arr(kp_table, np.float32)
+        assert kp_table.ndim == 3 and kp_table.shape[2] == 2
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_keyframe_keypoints(self.h, kf_first, kp_table.shape[0], kp_table.shape[1], _ptr(kp_table)))
+
+    def set_map_inputs_indexed(self, xyz, obs_ptr, obs_ref, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr=None):
+        """set_map_inputs with {keyframe, feature index} pairs (obs_ref [nnz][2], uint16 or int32) instead of
+        (obs_kf, obs_uv): keypoints come from the resident table."""
+        xyz, kf_pose, kf_intr, kf_bounds, kp2d = (_arr(x, np.float32) for x in (xyz, kf_pose, kf_intr, kf_bounds, kp2d))
+        obs_ptr, kf_ptr = _arr(obs_ptr, np.int32), _arr(kf_ptr, np.int32)
+        obs_ref = np.ascontiguousarray(obs_ref)
+        assert obs_ref.dtype in (np.int32, np.uint16) and obs_ref.ndim == 2 and obs_ref.shape[1] == 2
+        self._keep = [xyz, obs_ptr, obs_ref, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr]
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_map_inputs_indexed(
+            self.h, _ptr(xyz), _ptr(obs_ptr), _ptr(obs_ref), obs_ref.dtype.itemsize, kf_pose.shape[0], _ptr(kf_pose),
+            _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d), _ptr(kf_ptr)))
+
+    def submit_map_indexed(self, slot, xyz, obs_ptr, obs_ref, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr, map_out, prob_out):
+        """Pipelined step through HOST buffers with indexed observations (4 bytes per observation with uint16 pairs)."""
+        assert obs_ref.dtype in (np.int32, np.uint16) and obs_ref.ndim == 2 and obs_ref.shape[1] == 2
+        self.ctx._check(self.ctx.lib.lccrf_frames_submit_map_indexed(
+            self.h, slot, _ptr(xyz), _ptr(obs_ptr), _ptr(obs_ref), obs_ref.dtype.itemsize, kf_pose.shape[0], _ptr(kf_pose),
             _ptr(kf_intr), _ptr(kf_bounds), _ptr(kp2d), _ptr(kf_ptr), _ptr(map_out), _ptr(prob_out)))
 
     def submit(self, slot, observs, error, depth, kp2d, map_out, prob_out):

@@ -193,9 +193,10 @@ struct FrameInputs {
     bool ucam = false;     // every keyframe has the same intrinsics / image bounds (cam8)
     float cam8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long nnz = 0, nnz_cap = 0;
+    bool indexed = false;  // obs_kf holds {keyframe, feature index} pairs; keypoints come from lccrf_frames::kp_tab
     bool have_inputs = false;
     cudaGraphExec_t graph = nullptr;
-    uint64_t graph_launches = 0, graph_gen = 0;
+    uint64_t graph_launches = 0, graph_gen = 0, kp_gen = 0;
     cudaEvent_t up_done = nullptr, run_done = nullptr, out_done = nullptr;
     int *h_status = nullptr;  // pinned copy of the device status word taken after this slot's run
     bool in_flight = false;
@@ -214,6 +215,10 @@ struct lccrf_frames {
     int last_slot = 0;
     bool ran = false;
     int *part = nullptr;  // label application workspace: dyn_ptr, stat_ptr [B+1], dyn_list, stat_list, fid [NT], tiles
+    // resident keyframe keypoints (KeyFrame::mvKeysUn, immutable per keyframe): [kp_cap][kp_stride] float2
+    float *kp_tab = nullptr;
+    int kp_cap = 0, kp_stride = 0;
+    uint64_t kp_gen = 0;  // bumped when the table moves (captured graphs hold its address)
 };
 
 extern "C" {
@@ -996,6 +1001,7 @@ void lccrf_frames_destroy(lccrf_frames *fr) {
     dev_free(ctx, fr->label);
     dev_free(ctx, fr->d_en);
     dev_free(ctx, fr->part);
+    dev_free(ctx, fr->kp_tab);
     delete fr;
 }
 
@@ -1031,15 +1037,21 @@ static int frames_upload_direct(lccrf_frames *fr, FrameInputs &in, cudaStream_t 
 // validate + upload a map snapshot of one step into input set `in` on stream `st`
 static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st, const float *xyz, const int *obs_ptr,
                              const void *obs_kf, int obs_kf_bytes, const float *obs_uv, int nKF, const float *kf_pose,
-                             const float *kf_intr, const float *kf_bounds, const float *kp2d, const int *kf_ptr) {
+                             const float *kf_intr, const float *kf_bounds, const float *kp2d, const int *kf_ptr,
+                             bool indexed = false) {
     Ctx *ctx = fr->ctx;
     const int NT = fr->b.NT;
     if (obs_kf_bytes != 4 && obs_kf_bytes != 2) return fail(LCCRF_ERR_ARG, "obs_kf_bytes must be 4 (int32) or 2 (uint16)");
     if (obs_kf_bytes == 2 && nKF > 65536) return fail(LCCRF_ERR_ARG, "uint16 keyframe indices need nKF <= 65536");
+    if (indexed) {
+        if (!fr->kp_tab) return fail(LCCRF_ERR_STATE, "indexed observations need lccrf_frames_set_keyframe_keypoints first");
+        if (nKF > fr->kp_cap) return fail(LCCRF_ERR_ARG, "nKF exceeds the keyframes of the resident keypoint table");
+        if (obs_kf_bytes == 2 && fr->kp_stride > 65536) return fail(LCCRF_ERR_ARG, "uint16 feature indices need stride <= 65536");
+    }
     if (NT > 0 && (!xyz || !obs_ptr || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
     const long long nnz = NT > 0 ? obs_ptr[NT] : 0;
     if (NT > 0 && obs_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "obs_ptr must start at 0");
-    if (nnz > 0 && (!obs_kf || !obs_uv || !kf_pose || !kf_intr || !kf_bounds || nKF <= 0))
+    if (nnz > 0 && (!obs_kf || (!obs_uv && !indexed) || !kf_pose || !kf_intr || !kf_bounds || nKF <= 0))
         return fail(LCCRF_ERR_ARG, "NULL argument");
     // Tracking.cc:1858: points without observations never reach the CRF -- the caller drops them
     // (obs_ptr is host data, so this is a host-side structural check, not device work)
@@ -1063,17 +1075,20 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
         in.ucam = ucam;
         memcpy(in.cam8, cam8, sizeof(cam8));
     }
-    if (nnz > in.nnz_cap || !in.obs_kf || in.obs_kf_bytes != obs_kf_bytes) {
+    if (nnz > in.nnz_cap || !in.obs_kf || in.obs_kf_bytes != obs_kf_bytes || in.indexed != indexed) {
         dev_free(ctx, in.obs_kf);
         dev_free(ctx, in.obs_uv);
         in.obs_kf = nullptr;
         in.obs_uv = nullptr;
         const long long cap = nnz > in.nnz_cap ? nnz : in.nnz_cap;
-        LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_kf, (size_t)(cap ? cap : 1) * 4));
-        LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_uv, (size_t)(cap ? cap : 1) * 8));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_kf, (size_t)(cap ? cap : 1) * 8));  // up to an int32 {kf, fid} pair
+        if (!indexed) LCCRF_TRY(dev_alloc(ctx, (void **)&in.obs_uv, (size_t)(cap ? cap : 1) * 8));
         in.nnz_cap = cap;
         regraph = true;
     }
+    if (indexed && in.kp_gen != fr->kp_gen) regraph = true;  // the captured graph holds the table's address and stride
+    in.kp_gen = fr->kp_gen;
+    in.indexed = indexed;
     if (nKF > in.nKF_cap || !in.kf_pose) {
         dev_free(ctx, in.kf_pose);
         dev_free(ctx, in.kf_intr);
@@ -1113,8 +1128,8 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
         LCCRF_CUDA(cudaMemcpyAsync(in.kp2d, kp2d, (size_t)NT * 8, cudaMemcpyHostToDevice, st));
     }
     if (nnz > 0) {
-        LCCRF_CUDA(cudaMemcpyAsync(in.obs_kf, obs_kf, (size_t)nnz * obs_kf_bytes, cudaMemcpyHostToDevice, st));
-        LCCRF_CUDA(cudaMemcpyAsync(in.obs_uv, obs_uv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.obs_kf, obs_kf, (size_t)nnz * obs_kf_bytes * (indexed ? 2 : 1), cudaMemcpyHostToDevice, st));
+        if (!indexed) LCCRF_CUDA(cudaMemcpyAsync(in.obs_uv, obs_uv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
         LCCRF_CUDA(cudaMemcpyAsync(in.kf_pose, kf_pose, (size_t)nKF * 48, cudaMemcpyHostToDevice, st));
         LCCRF_CUDA(cudaMemcpyAsync(in.kf_intr, kf_intr, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
         LCCRF_CUDA(cudaMemcpyAsync(in.kf_bounds, kf_bounds, (size_t)nKF * 16, cudaMemcpyHostToDevice, st));
@@ -1161,7 +1176,7 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
         LCCRF_TRY(unary_map_points_packed(ctx, NT, in.nKF, in.xyz, in.obs_ptr, in.obs_kf, in.obs_kf_bytes, in.obs_uv,
                                           in.kf_packed, fr->observs, fr->error, fr->depth, b.prob_ptr,
                                           in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max,
-                                          in.ucam ? in.cam8 : nullptr));
+                                          in.ucam ? in.cam8 : nullptr, in.indexed ? fr->kp_tab : nullptr, fr->kp_stride));
         observs = fr->observs;
         error = fr->error;
         depth = fr->depth;
@@ -1291,6 +1306,61 @@ int lccrf_frames_submit_map(lccrf_frames *fr, int slot, const float *xyz, const 
     LCCRF_TRY(frames_submit_prologue(fr, slot, &in));
     LCCRF_TRY(frames_upload_map(fr, *in, fr->ctx->copy_stream, xyz, obs_ptr, obs_kf, obs_kf_bytes, obs_uv, nKF, kf_pose,
                                 kf_intr, kf_bounds, kp2d, kf_ptr));
+    return frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
+}
+
+// ---- resident keyframe keypoints + indexed observations ----
+int lccrf_frames_set_keyframe_keypoints(lccrf_frames *fr, int kf_first, int kf_count, int stride, const float *kp_uv) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (kf_first < 0 || kf_count < 0 || stride <= 0) return fail(LCCRF_ERR_ARG, "bad keyframe range or stride");
+    if (kf_count > 0 && !kp_uv) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (fr->kp_tab && stride != fr->kp_stride) return fail(LCCRF_ERR_ARG, "stride differs from the resident table's");
+    for (int s = 0; s < 2; s++)
+        if (fr->in[s].in_flight) return fail(LCCRF_ERR_STATE, "a submission is in flight: call lccrf_frames_wait first");
+    Ctx *ctx = fr->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    const long long need = (long long)kf_first + kf_count;
+    if (need > 0x7fffffffLL) return fail(LCCRF_ERR_ARG, "too many keyframes");
+    if (!fr->kp_tab || need > fr->kp_cap) {
+        long long cap = fr->kp_cap ? 2LL * fr->kp_cap : 0;
+        if (cap < need) cap = need;
+        if (cap < 1) cap = 1;
+        float *nt = nullptr;
+        LCCRF_TRY(dev_alloc(ctx, (void **)&nt, (size_t)cap * stride * 8, true));
+        if (fr->kp_tab)
+            LCCRF_CUDA(cudaMemcpyAsync(nt, fr->kp_tab, (size_t)fr->kp_cap * stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        dev_free(ctx, fr->kp_tab);
+        fr->kp_tab = nt;
+        fr->kp_cap = (int)cap;
+        fr->kp_stride = stride;
+        fr->kp_gen++;
+    }
+    if (kf_count > 0)
+        LCCRF_CUDA(cudaMemcpyAsync(fr->kp_tab + (size_t)kf_first * stride * 2, kp_uv, (size_t)kf_count * stride * 8,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    // rare call (keyframe insertion): synchronise so that the host buffer is free on return and the copy stream of
+    // the pipelined submissions sees the table
+    LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LCCRF_OK;
+}
+
+int lccrf_frames_set_map_inputs_indexed(lccrf_frames *fr, const float *xyz, const int *obs_ptr, const void *obs_ref,
+                                        int index_bytes, int nKF, const float *kf_pose, const float *kf_intr,
+                                        const float *kf_bounds, const float *kp2d, const int *kf_ptr) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
+    return frames_upload_map(fr, fr->in[0], fr->ctx->stream, xyz, obs_ptr, obs_ref, index_bytes, nullptr, nKF, kf_pose,
+                             kf_intr, kf_bounds, kp2d, kf_ptr, true);
+}
+
+int lccrf_frames_submit_map_indexed(lccrf_frames *fr, int slot, const float *xyz, const int *obs_ptr, const void *obs_ref,
+                                    int index_bytes, int nKF, const float *kf_pose, const float *kf_intr,
+                                    const float *kf_bounds, const float *kp2d, const int *kf_ptr, short *map_out,
+                                    float *prob_out) {
+    FrameInputs *in = nullptr;
+    LCCRF_TRY(frames_submit_prologue(fr, slot, &in));
+    LCCRF_TRY(frames_upload_map(fr, *in, fr->ctx->copy_stream, xyz, obs_ptr, obs_ref, index_bytes, nullptr, nKF, kf_pose,
+                                kf_intr, kf_bounds, kp2d, kf_ptr, true));
     return frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
 }
 

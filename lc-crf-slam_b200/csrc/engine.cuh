@@ -196,7 +196,10 @@ int feat_image(Ctx *ctx, float *feat, int W, int H, int F, float posdev, const v
 int unary_pack_kf(Ctx *ctx, void *kf_packed /*nKF*80 B*/, const float *pose, const float *intr, const float *bnd, int nKF);
 int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const int *obs_ptr, const void *obs_kf,
                             int obs_kf_bytes, const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
-                            const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max, const float *cam8);
+                            const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max, const float *cam8,
+                            const float *kp_tab, int kp_stride);
+// kp_tab != nullptr: indexed observations -- obs_kf holds {keyframe, feature index} pairs (uint16 pairs when
+// obs_kf_bytes == 2, int32 pairs when 4), obs_uv is unused and the observed keypoint is kp_tab[kf*kp_stride + fid]
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                      const float *obs_uv, int nKF, const float *kf_pose, const float *kf_intr,
                      const float *kf_bounds, float *observs, float *error, float *depth, const float *cam8);

@@ -158,6 +158,35 @@ def map_snapshot(n: int, obs_per_point: int, seed: int, n_kf: int = 256, intr=TU
                        kf_pose, kf_intr, kf_bounds, xy.astype(np.float32), dyn)
 
 
+def index_observations(obs_kf, obs_uv, n_kf: int, seed: int, stride: int | None = None, stride_max: int = 32768):
+    """Restate a snapshot's observations the way the reference stores them: (keyframe, feature index) pairs
+    (MapPoint::mObservations, MapPoint.h:115) plus one keypoint array per keyframe (KeyFrame::mvKeysUn).
+    Returns (obs_fid int32 [nnz], kp_table float32 [n_kf][stride][2], obs_uv_consistent float32 [nnz][2]).
+    Feature indices are scattered over the keyframe's row (a multiplicative permutation with a random per-keyframe
+    offset), i.e. uncorrelated with map-point order, as in a real keyframe.  A keyframe referenced by more than
+    `stride` observations re-uses keypoints (first occurrence defines the keypoint); obs_uv_consistent = kp_table[kf, fid]
+    is the flat restatement of exactly the same problem (equal to obs_uv wherever no keypoint is re-used)."""
+    obs_kf = np.asarray(obs_kf, dtype=np.int64)
+    obs_uv = np.asarray(obs_uv, dtype=np.float32)
+    nnz = obs_kf.size
+    cnt = np.bincount(obs_kf, minlength=n_kf)
+    if stride is None:
+        need = int(min(cnt.max() if nnz else 1, stride_max))
+        stride = 1 << max(int(np.ceil(np.log2(max(need, 1)))), 0)
+    assert stride & (stride - 1) == 0, "stride must be a power of two (the permutation is multiplicative mod stride)"
+    order = np.argsort(obs_kf, kind="stable")
+    start = np.zeros(n_kf + 1, dtype=np.int64)
+    np.cumsum(cnt, out=start[1:])
+    rank = np.empty(nnz, dtype=np.int64)
+    rank[order] = np.arange(nnz) - start[obs_kf[order]]
+    rng = np.random.default_rng(seed)
+    off = rng.integers(0, stride, n_kf)
+    fid = ((rank % stride) * 40503 + off[obs_kf]) % stride  # 40503 is odd: a bijection modulo a power of two
+    table = np.zeros((n_kf, stride, 2), dtype=np.float32)
+    table[obs_kf[::-1], fid[::-1]] = obs_uv[::-1]            # last write wins -> reversed: the first occurrence wins
+    return fid.astype(np.int32), table, table[obs_kf, fid]
+
+
 def image_problem(w: int, h: int, seed: int, unknown_frac: float = 0.7, n_labels: int = 2):
     """C2: smooth blobs + N(0,10) noise uint8 RGB image, noisy fg/bg labels, `unknown_frac` unknown (-1)."""
     rng = np.random.default_rng(seed)

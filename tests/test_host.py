@@ -87,3 +87,21 @@ def test_gloo_world2_sharding(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert "OK" in outs[0][0]
+
+
+def test_index_observations_restates_the_same_problem():
+    """(keyframe, feature index) pairs + per-keyframe keypoint rows reproduce the flat observations; with a stride
+    smaller than a keyframe's observation count keypoints are re-used and the consistent flat form says so."""
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    s = synth.map_snapshot(2000, 12, seed=4, n_kf=32, ragged=True)
+    fid, table, uvc = synth.index_observations(s.obs_kf, s.obs_uv, 32, seed=1)
+    assert table.shape[0] == 32 and table.shape[1] & (table.shape[1] - 1) == 0 and table.shape[2] == 2
+    assert fid.min() >= 0 and fid.max() < table.shape[1]
+    assert np.array_equal(table[s.obs_kf, fid], s.obs_uv) and np.array_equal(uvc, s.obs_uv)
+    pairs = np.stack([s.obs_kf, fid], axis=1)
+    assert np.unique(pairs, axis=0).shape[0] == pairs.shape[0]  # one keypoint per observation
+    fid2, table2, uvc2 = synth.index_observations(s.obs_kf, s.obs_uv, 32, seed=1, stride=16)
+    assert table2.shape == (32, 16, 2) and fid2.max() < 16
+    assert np.array_equal(table2[s.obs_kf, fid2], uvc2) and not np.array_equal(uvc2, s.obs_uv)
+    first = np.unique(np.stack([s.obs_kf, fid2], axis=1), axis=0, return_index=True)[1]
+    assert np.array_equal(uvc2[first], s.obs_uv[first])  # the first occurrence defines the keypoint
