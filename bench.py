@@ -190,17 +190,19 @@ def run_reference_arm(args):
         return  # rank 0 alone runs and prints the reference arm
     cores = os.cpu_count() or 1
     desc, dbatch, n, obs = WORKLOADS[args.workload]
-    # bounded sample: one problem per host thread per step (c3: ~0.1-0.2 s of CPU work per problem)
-    per_step = cores if args.workload != "c4" else 4 * cores
+    # bounded sample: two problems per host thread per step (c3: ~0.1 s of CPU work per problem), so that a step keeps
+    # every core busy and the pool start-up is amortised
+    per_step = 2 * cores if args.workload != "c4" else 8 * cores
     base = make_problems(args.workload, min(per_step, 4), seed0=1000)
     problems = [base[i % len(base)] for i in range(per_step)]
-    for _ in range(args.warmup):
-        time_cpu(args.workload, problems[:cores], cores)
-    t0 = time.perf_counter()
-    kind = "port"
-    for _ in range(args.steps):
-        _, kind, _ = time_cpu(args.workload, problems, cores)
-    dt = time.perf_counter() - t0
+    run, kind = cpu_problem_runner(args.workload)
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for _ in range(max(args.warmup, 1)):
+            list(ex.map(run, problems))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            list(ex.map(run, problems))
+        dt = time.perf_counter() - t0
     value = args.steps * per_step / dt
     sample = "%d problems per step on %d host threads; CRF = %s, unary = oracle port (Tracking.cc is not compilable)" % (
         per_step, cores, "reference headers compiled in place (oracle/_ref)" if kind == "reference" else "oracle port")
