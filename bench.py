@@ -56,7 +56,7 @@ def parse_args():
 
 WORKLOADS = {
     # name: (description, default batch, points, observations per point)
-    "c3": ("C3: long-term unary + CRF, N=100k map points x 64 keyframe observations, L=2, K=2 (d=2,2), T=5", 16, 100000, 64),
+    "c3": ("C3: long-term unary + CRF, N=100k map points x 64 keyframe observations, L=2, K=2 (d=2,2), T=5", 32, 100000, 64),
     "c1": ("C1: per-frame CRF, N=3000 points, L=2, K=2 (d=2,2), T=5 (reference's own CPU-runnable case)", 1, 3000, 0),
     "c4": ("C4: 1024 independent per-frame CRFs of N~U[4000,6000] points in one launch sequence", 1024, 5000, 0),
 }
@@ -69,8 +69,9 @@ def make_problems(workload: str, batch: int, seed0: int):
     """Seeded synthetic problems.  Returns a list of MapSnapshot (c3) or SlamFrame (c1/c4)."""
     synth = importlib.import_module("lc-crf-slam_b200.synth")
     _, _, n, obs = WORKLOADS[workload]
-    if workload == "c3":
-        return [synth.map_snapshot(n, obs, seed=seed0 + i) for i in range(batch)]
+    if workload == "c3":  # seeded per problem, so the pool only changes the wall time of the set-up
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            return list(ex.map(lambda i: synth.map_snapshot(n, obs, seed=seed0 + i), range(batch)))
     if workload == "c1":
         return [synth.slam_frame(n, seed=seed0 + i) for i in range(batch)]
     rng = np.random.default_rng(seed0)
@@ -319,12 +320,15 @@ def run_gpu_arm(args):
         # the same observations as (keyframe, feature index) pairs + per-keyframe keypoint rows; obs_uv is replaced by
         # its consistent flat form so that the device-resident runs and both end-to-end paths work on ONE problem set
         fids, tabs, uvs, ko = [], [], [], 0
-        for i, p in enumerate(problems):
-            fid, tab, uvc = synth_mod.index_observations(p.obs_kf, p.obs_uv, p.kf_pose.shape[0], seed=77 + i, stride=KP_STRIDE)
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            indexed = list(ex.map(lambda ip: synth_mod.index_observations(ip[1].obs_kf, ip[1].obs_uv, ip[1].kf_pose.shape[0],
+                                                                          seed=77 + ip[0], stride=KP_STRIDE), enumerate(problems)))
+        for p, (fid, tab, uvc) in zip(problems, indexed):
             fids.append(np.stack([p.obs_kf + ko, fid], axis=1).astype(np.uint16))
             tabs.append(tab)
             uvs.append(uvc)
             ko += p.kf_pose.shape[0]
+        del indexed
         assert ko <= 65536
         cat["obs_uv"] = np.concatenate(uvs)
         cat["obs_ref"] = np.concatenate(fids)
@@ -537,7 +541,10 @@ def run_gpu_arm(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "problems_per_step_per_gpu": batch, "points_per_step_per_gpu": NT,
-                   "l2_policy": "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (abytes["total"] / 1e6),
+                   "l2_policy": ("inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (abytes["total"] / 1e6))
+                                if abytes["total"] > 126e6 else
+                                ("working set %.1f MB per step fits the 126 MB L2 and is NOT flushed between steps: "
+                                 "cache-resident latency figure, not a headline configuration" % (abytes["total"] / 1e6)),
                    "sharding": "independent problems per rank, no collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -158,6 +158,33 @@ struct MfArgs {
     MfLat lat[LCCRF_MAX_K];
 };
 
+// expAndNormalize for two labels (densecrf3d.h:71-98) + optional buildMap (:137-151).  The label holding the maximum
+// has the argument n - mx = +-0 (finite inputs) and fast_exp(+-0) is exactly 1.0f (very_fast_exp(0) = 1, 1/1 = 1), so the
+// range-reduction loops of fast_exp run once per point, for the other label only; a non-zero argument of the maximum
+// (inf - inf = NaN) still takes the full path, so the result is the reference's in every case.
+__device__ __forceinline__ void softmax2_store(float n0, float n1, float2 *__restrict__ cur, short *__restrict__ map,
+                                               int i, float relax) {
+    const bool m0 = !(n0 < n1);  // mx = n0; if (mx < n1) mx = n1
+    const float mx = m0 ? n0 : n1;
+    const float a0 = __fsub_rn(n0, mx), a1 = __fsub_rn(n1, mx);
+    const float am = m0 ? a0 : a1, ao = m0 ? a1 : a0;
+    const float eo = fast_exp(ao);
+    float em = 1.0f;
+    if (!(am == 0.0f)) em = fast_exp(am);
+    float v0 = m0 ? em : eo, v1 = m0 ? eo : em;
+    const float tt = __fadd_rn(__fadd_rn(0.0f, v0), v1);
+    v0 = __fdiv_rn(v0, tt);
+    v1 = __fdiv_rn(v1, tt);
+    if (relax != 1.0f) {
+        const float2 old = cur[i];
+        const float om = __fsub_rn(1.0f, relax);
+        v0 = __fadd_rn(__fmul_rn(om, old.x), __fmul_rn(relax, v0));
+        v1 = __fadd_rn(__fmul_rn(om, old.y), __fmul_rn(relax, v1));
+    }
+    cur[i] = make_float2(v0, v1);
+    if (map) map[i] = (v0 < v1) ? 1 : 0;  // buildMap: strict <, first maximum wins
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_mf_point_l2(MfArgs a, const float2 *__restrict__ unary, float2 *__restrict__ cur, short *__restrict__ map, int NT,
               float relax) {
@@ -179,21 +206,61 @@ k_mf_point_l2(MfArgs a, const float2 *__restrict__ unary, float2 *__restrict__ c
         n0 = __fadd_rn(n0, __fmul_rn(wn, s0));
         n1 = __fadd_rn(n1, __fmul_rn(wn, s1));
     }
-    // expAndNormalize(current_, next_, 1.0, relax)
-    float mx = n0;
-    if (mx < n1) mx = n1;
-    float v0 = fast_exp(__fsub_rn(n0, mx)), v1 = fast_exp(__fsub_rn(n1, mx));
-    const float tt = __fadd_rn(__fadd_rn(0.0f, v0), v1);
-    v0 = __fdiv_rn(v0, tt);
-    v1 = __fdiv_rn(v1, tt);
-    if (relax != 1.0f) {
-        const float2 old = cur[i];
-        const float om = __fsub_rn(1.0f, relax);
-        v0 = __fadd_rn(__fmul_rn(om, old.x), __fmul_rn(relax, v0));
-        v1 = __fadd_rn(__fmul_rn(om, old.y), __fmul_rn(relax, v1));
+    softmax2_store(n0, n1, cur, map, i, relax);
+}
+
+// the SLAM / image shapes: two lattices with compile-time vertex counts per point.  Same operations in the same
+// order as the generic kernel, but every index, weight and vertex value is requested before the first use
+// (6 + 6 + 6 independent loads per point instead of a dependent load per loop trip) and nothing loops at run time.
+template <int D0, int D1>
+__global__ void __launch_bounds__(kThreads)
+k_mf_point_l2_k2(MfArgs a, const float2 *__restrict__ unary, float2 *__restrict__ cur, short *__restrict__ map, int NT,
+                 float relax) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= NT) return;
+    int id0[D0], id1[D1];
+    float w0[D0], w1[D1];
+#pragma unroll
+    for (int r = 0; r < D0; r++) id0[r] = __ldg(a.lat[0].offset + (size_t)i * D0 + r);
+#pragma unroll
+    for (int r = 0; r < D1; r++) id1[r] = __ldg(a.lat[1].offset + (size_t)i * D1 + r);
+#pragma unroll
+    for (int r = 0; r < D0; r++) w0[r] = __ldg(a.lat[0].bary + (size_t)i * D0 + r);
+#pragma unroll
+    for (int r = 0; r < D1; r++) w1[r] = __ldg(a.lat[1].bary + (size_t)i * D1 + r);
+    const float2 u = __ldg(unary + i);
+    const float nm0 = __ldg(a.lat[0].norm + i), nm1 = __ldg(a.lat[1].norm + i);
+    float2 v0[D0], v1[D1];
+#pragma unroll
+    for (int r = 0; r < D0; r++) v0[r] = __ldg(a.lat[0].val + id0[r]);
+#pragma unroll
+    for (int r = 0; r < D1; r++) v1[r] = __ldg(a.lat[1].val + id1[r]);
+    float n0 = -u.x, n1 = -u.y;
+    {
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int r = 0; r < D0; r++) {
+            const float wa = __fmul_rn(w0[r], a.lat[0].alpha);
+            s0 = __fadd_rn(s0, __fmul_rn(wa, v0[r].x));
+            s1 = __fadd_rn(s1, __fmul_rn(wa, v0[r].y));
+        }
+        const float wn = __fmul_rn(a.lat[0].w, nm0);
+        n0 = __fadd_rn(n0, __fmul_rn(wn, s0));
+        n1 = __fadd_rn(n1, __fmul_rn(wn, s1));
     }
-    cur[i] = make_float2(v0, v1);
-    if (map) map[i] = (v0 < v1) ? 1 : 0;  // buildMap: strict <, first maximum wins
+    {
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int r = 0; r < D1; r++) {
+            const float wa = __fmul_rn(w1[r], a.lat[1].alpha);
+            s0 = __fadd_rn(s0, __fmul_rn(wa, v1[r].x));
+            s1 = __fadd_rn(s1, __fmul_rn(wa, v1[r].y));
+        }
+        const float wn = __fmul_rn(a.lat[1].w, nm1);
+        n0 = __fadd_rn(n0, __fmul_rn(wn, s0));
+        n1 = __fadd_rn(n1, __fmul_rn(wn, s1));
+    }
+    softmax2_store(n0, n1, cur, map, i, relax);
 }
 
 }  // namespace
@@ -213,8 +280,14 @@ int mf_point_pass_l2(Ctx *ctx, Batch &b, const float *const *values, float relax
         a.lat[k].D = ls->D;
     }
     LCCRF_KERNEL(ctx, "k_mf_point_l2");
-    k_mf_point_l2<<<cdiv(b.NT, kThreads), kThreads, 0, ctx->stream>>>(a, (const float2 *)b.unary, (float2 *)b.cur,
-                                                                       with_map ? b.map : nullptr, b.NT, relax);
+    const int grid = cdiv(b.NT, kThreads);
+    short *mp = with_map ? b.map : nullptr;
+    if (a.K == 2 && a.lat[0].D == 3 && a.lat[1].D == 3)        // SLAM: appearance + smoothness, both 2-D features
+        k_mf_point_l2_k2<3, 3><<<grid, kThreads, 0, ctx->stream>>>(a, (const float2 *)b.unary, (float2 *)b.cur, mp, b.NT, relax);
+    else if (a.K == 2 && a.lat[0].D == 3 && a.lat[1].D == 6)   // image: Gaussian (x, y) + bilateral (x, y, r, g, b)
+        k_mf_point_l2_k2<3, 6><<<grid, kThreads, 0, ctx->stream>>>(a, (const float2 *)b.unary, (float2 *)b.cur, mp, b.NT, relax);
+    else
+        k_mf_point_l2<<<grid, kThreads, 0, ctx->stream>>>(a, (const float2 *)b.unary, (float2 *)b.cur, mp, b.NT, relax);
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }
