@@ -193,9 +193,13 @@ def test_slam_crf_golden_reference(pkg, ctx):
 def test_generic_labels_dims_relax_and_stepwise(pkg, ctx, oracle):
     rng = np.random.default_rng(5)
     N = 1500
-    for L, dims in ((3, (2, 3)), (4, (5,)), (21, (2,)), (2, ())):
+    # L = 2 with lattices goes through the fused point pass: generic kernel (K = 1, K = 3) and the two-lattice
+    # specialisations (D = 3,3 and D = 3,6), each also with relax != 1
+    for L, dims in ((3, (2, 3)), (4, (5,)), (21, (2,)), (2, ()), (2, (2,)), (2, (2, 2)), (2, (2, 5)), (2, (3, 2, 4))):
         feats = [tie_features(rng, N, d, 2.0) for d in dims]
         unary = rng.random((N, L)).astype(np.float32) * 3
+        if L == 2:
+            unary[::40, 1] = unary[::40, 0]  # label ties at the start (strict-< MAP rule, zero softmax arguments)
         w = [3.0 + k for k in range(len(dims))]
         for relax in (1.0, 0.5):
             Qo, mo, _ = oracle.meanfield(unary, feats, w, 4, relax)
@@ -211,6 +215,27 @@ def test_generic_labels_dims_relax_and_stepwise(pkg, ctx, oracle):
             assert_bit_exact(crf.getProbability(), Qo, what="L=%d dims=%s relax=%g" % (L, dims, relax))
             assert np.array_equal(crf.getMap(), mo)
             crf.close()
+
+
+def test_two_label_symmetric_problem_ties_everywhere(pkg, ctx, oracle):
+    """Equal energies for both labels at every point: every message is label-symmetric, so both softmax arguments are
+    exactly zero at every point and every iteration (the tie path of the fused point pass); MAP must be label 0
+    everywhere (strict <, densecrf3d.h:143-148)."""
+    rng = np.random.default_rng(12)
+    N = 3001
+    e = rng.random(N).astype(np.float32) * 2
+    unary = np.stack([e, e], axis=1)
+    feats = [tie_features(rng, N, 2, 2.0), tie_features(rng, N, 2, 6.0)]
+    Qo, mo, _ = oracle.meanfield(unary, feats, [10.0, 30.0], 5)
+    crf = pkg.DenseCRF(ctx, N, 2)
+    crf.setUnaryEnergy(unary)
+    for f, wk in zip(feats, (10.0, 30.0)):
+        crf.addPairwiseEnergy(f, wk)
+    crf.inference(5, True)
+    assert_bit_exact(crf.getProbability(), Qo)
+    assert np.array_equal(crf.getProbability(), np.full((N, 2), 0.5, np.float32))
+    assert np.array_equal(crf.getMap(), mo) and not crf.getMap().any()
+    crf.close()
 
 
 def test_unary_entry_poke_and_unknown_labels(pkg, ctx, oracle):
