@@ -320,7 +320,10 @@ def test_image_crf_c2_small(pkg, ctx, oracle):
 
 
 # ------------------------------------------------------------------ long-term unary
-@pytest.mark.parametrize("N,obs,ragged", [(1, 1, False), (31, 3, True), (5000, 64, True), (20000, 64, False), (300, 2500, True)])
+# uniform observation counts >= 16 take the round layout of the unary kernel (70, 100: partial last round; 16: one round;
+# 20: not well filled -> chunk layout); ragged or short lists take the chunk layout
+@pytest.mark.parametrize("N,obs,ragged", [(1, 1, False), (31, 3, True), (5000, 64, True), (20000, 64, False), (300, 2500, True),
+                                          (3000, 70, False), (640, 16, False), (1000, 100, False), (2050, 20, False), (64, 4096, False)])
 def test_map_point_unary_bit_exact(ctx, oracle, N, obs, ragged):
     snap = synth.map_snapshot(N, obs, seed=N + obs, ragged=ragged)
     ob, er, de = oracle.map_point_unary(snap)
