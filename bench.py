@@ -505,7 +505,10 @@ def run_gpu_arm(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the last ncu --set full capture
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top)
+            tj = json.load(open(tpath))
+            traffic = tj.get(top)
+            if traffic is not None and tj.get("_captured_points_per_step"):
+                traffic = traffic * NT / float(tj["_captured_points_per_step"])  # DRAM traffic is linear in the batch
         members = KERNEL_GROUPS.get(top, (top,))
         if ab is not None:
             per_launch_ms = tms / cnt
