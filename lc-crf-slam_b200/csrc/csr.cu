@@ -436,12 +436,7 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     { LCCRF_KERNEL(ctx, "k_scan_tot"); k_scan_tot<<<1, 1024, 0, st>>>(ls->scan_tot, vt); }
     { LCCRF_KERNEL(ctx, "k_scan_add"); k_scan_add<<<sgrid, 1024, 0, st>>>(ls->row_ptr, vt, ls->scan_tot); }
     if (p.G > 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_csr_fill, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kCursorSmemInts * (int)sizeof(int)));
-            attr_set = true;
-        }
+        LCCRF_TRY(ensure_dyn_smem(ctx, k_csr_fill, kCursorSmemInts * (int)sizeof(int)));
         { LCCRF_KERNEL(ctx, "k_csr_fill"); k_csr_fill<<<p.G, kFillWarpsH * 32, kCursorSmemInts * sizeof(int), st>>>(p); }
     }
     LCCRF_CUDA(cudaMemsetAsync(ls->row_counts, 0, 8 * sizeof(int), st));

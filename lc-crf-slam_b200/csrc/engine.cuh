@@ -104,6 +104,9 @@ struct Ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_concurrent = 1;
     int branch = 0;  // 0 = launches go to `stream`, 1 = to `aux_stream` (see AuxScope)
+    // kernels whose opt-in dynamic shared memory limit has been raised on this context's device (function attributes
+    // are per device, and a context belongs to one host thread: no process-wide flag)
+    std::vector<const void *> smem_attr_done;
     int *d_status = nullptr;   // device status word (key range overflow etc.)
     int *h_status = nullptr;   // pinned
 };
@@ -154,6 +157,18 @@ struct AuxScope {
         }
     }
 };
+// raise a kernel's dynamic shared memory limit once per context (first launch; outside any graph capture because every
+// captured sequence is run once uncaptured first)
+template <typename Kernel>
+inline int ensure_dyn_smem(Ctx *ctx, Kernel *kernel, int bytes) {
+    const void *key = (const void *)kernel;
+    for (const void *k : ctx->smem_attr_done)
+        if (k == key) return LCCRF_OK;
+    LCCRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->smem_attr_done.push_back(key);
+    return LCCRF_OK;
+}
+
 int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero = false);
 void dev_free(Ctx *ctx, void *p);
 

@@ -1007,12 +1007,7 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
         const int LG = tile_labels(L);
         const int grid = ls->max_pieces < kNumSMs * 8 ? ls->max_pieces : kNumSMs * 8;
         const size_t smem = (size_t)(kTileGranule + kLongRow) * LG * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_splat_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((kTileGranule + kLongRow) * 4 * sizeof(float))));
-            attr_set = true;
-        }
+        LCCRF_TRY(ensure_dyn_smem(ctx, k_splat_tile<4>, (int)((kTileGranule + kLongRow) * 4 * sizeof(float))));
         LCCRF_KERNEL(ctx, "k_splat_tile");
         switch (LG) {
             case 1: k_splat_tile<1><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
@@ -1041,11 +1036,7 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
           k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, L); }
     }
     if (b.B >= 2 || b.maxN <= 32768) {  // one CTA per problem runs all D passes
-        static bool attr_set = false;
-        if (!attr_set) {
-            LCCRF_CUDA(cudaFuncSetAttribute(k_blur_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurFusedBytes + 16));
-            attr_set = true;
-        }
+        LCCRF_TRY(ensure_dyn_smem(ctx, k_blur_fused, kBlurFusedBytes + 16));
         LCCRF_KERNEL(ctx, "k_blur_fused");
         k_blur_fused<<<b.B, 1024, kBlurFusedBytes + 16, st>>>(ls->nbr, ls->Vcap, ls->vbase, src, dst, L, D);
         *values_out = dst;
