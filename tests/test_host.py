@@ -105,3 +105,29 @@ def test_index_observations_restates_the_same_problem():
     assert np.array_equal(table2[s.obs_kf, fid2], uvc2) and not np.array_equal(uvc2, s.obs_uv)
     first = np.unique(np.stack([s.obs_kf, fid2], axis=1), axis=0, return_index=True)[1]
     assert np.array_equal(uvc2[first], s.obs_uv[first])  # the first occurrence defines the keypoint
+
+
+def test_bench_reference_arm_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints ONE JSON line with the
+    contract keys; here on the small C1 workload so that it finishes in seconds."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "crf_problems_per_s" and d["unit"] == "problems/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("C1")
+
+
+def test_bench_reference_arm_other_ranks_stay_silent():
+    import subprocess
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                        "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
