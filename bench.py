@@ -532,8 +532,9 @@ def run_gpu_arm(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        sample = [problems[i % len(problems)] for i in range(cores if args.workload != "c4" else 4 * cores)]
-        reps = 8 if args.workload == "c3" else 64  # ~10-30 s of CPU work in total
+        # the reference arm's step: two problems per host thread per pass keep every core busy (c4: eight)
+        sample = [problems[i % len(problems)] for i in range(2 * cores if args.workload != "c4" else 8 * cores)]
+        reps = 4 if args.workload == "c3" else 32  # ~10-30 s of CPU work in total
         v, kind, dt = time_cpu(args.workload, sample, cores, repeats=reps)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "%d problems on %d host threads in %.1f s; CRF = %s, unary = oracle port" % (
