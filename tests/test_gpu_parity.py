@@ -333,6 +333,17 @@ def test_map_point_unary_bit_exact(ctx, oracle, N, obs, ragged):
     assert np.array_equal(bits(de), bits(gde))
 
 
+@pytest.mark.parametrize("name", ["ragged", "uniform64", "uniform70", "mixed_cameras"])
+def test_map_point_unary_vs_opencv_golden(ctx, name):
+    """The CUDA unary against the committed cv2.gemm-based evaluation of Tracking.cc:1803-1839
+    (tests/golden/golden_unary.npz, made by tests/golden/make_golden_unary.py): bit-identical."""
+    from util import golden_unary_case
+    s, ob, er, de = golden_unary_case(name)
+    gob, ger, gde = ctx.map_point_unary(s)
+    assert np.array_equal(ob, gob)
+    assert np.array_equal(bits(er), bits(ger)) and np.array_equal(bits(de), bits(gde))
+
+
 def test_map_point_unary_mixed_cameras(pkg, ctx, oracle):
     """Keyframes with different intrinsics / image bounds take the per-keyframe path (one shared camera is served
     from kernel parameters); both must match the restatement bit for bit, stand-alone and inside a frames batch."""

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from util import bits, tie_features
+from util import bits, golden_unary_case, tie_features
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 synth = importlib.import_module("lc-crf-slam_b200.synth")
@@ -114,7 +114,7 @@ def test_fast_exp_properties(oracle):
 
 
 def test_unary_restatement_properties(oracle):
-    """The unary has no reference fixture (parity unpinned); check its defining properties."""
+    """Defining properties of the unary restatement (its arithmetic is pinned by test_unary_vs_opencv_golden)."""
     snap = synth.map_snapshot(400, 16, seed=9, ragged=True)
     ob, er, de = oracle.map_point_unary(snap)
     cnt = np.diff(snap.obs_ptr)
@@ -140,6 +140,20 @@ def test_unary_restatement_properties(oracle):
 
 
 # ------------------------------------------------------------------ frontend feeders
+UNARY_CASES = ("ragged", "uniform64", "uniform70", "mixed_cameras")
+
+
+@pytest.mark.parametrize("name", UNARY_CASES)
+def test_unary_vs_opencv_golden(oracle, name):
+    """Tracking::ComputeMapPointErrAndObserv restatement against a statement-by-statement evaluation whose matrix
+    product is the real cv::gemm (tests/golden/make_golden_unary.py): bit-identical observs / error / depth."""
+    s, ob, er, de = golden_unary_case(name)
+    o_ob, o_er, o_de = oracle.map_point_unary(s)
+    assert np.array_equal(o_ob, ob)
+    assert np.array_equal(bits(o_er), bits(er)) and np.array_equal(bits(o_de), bits(de))
+    assert (er > 0).any() and np.isfinite(er).all()
+
+
 def test_bf_match_vs_opencv_golden(oracle):
     """Tracking::BfMatch restatement against cv::BFMatcher.knnMatch(k=2) outputs captured from OpenCV itself
     (tests/golden/make_golden_frontend.py): nearest-two lists incl. tie order, and the 0.6 ratio test."""

@@ -54,3 +54,15 @@ def tie_features(rng, N, d, scale=3.0):
         f[::7] = np.round(f[::7])
         f[::11] = np.round(f[::11] * 2) / 2
     return f
+
+
+def golden_unary_case(name):
+    """One case of tests/golden/golden_unary.npz (made by tests/golden/make_golden_unary.py with the real cv2.gemm):
+    returns (MapSnapshot, observs, error, depth)."""
+    import importlib
+    import os
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_unary.npz"))
+    keys = ("xyz", "obs_ptr", "obs_kf", "obs_uv", "kf_pose", "kf_intr", "kf_bounds", "kp2d")
+    s = synth.MapSnapshot(*(g[name + "_" + k] for k in keys), np.zeros(g[name + "_xyz"].shape[0], bool))
+    return s, g[name + "_observs"], g[name + "_error"], g[name + "_depth"]
