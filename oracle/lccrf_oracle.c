@@ -420,8 +420,9 @@ void orc_features_image(float *feat, int W, int H, int F, float posdev, const un
 
 /* ------------------------------------------------------------------------------------------
  * Tracking::ComputeMapPointErrAndObserv, src/Tracking.cc:1803-1839, on flat arrays.
- * PARITY UNPINNED (see header).  Rcw*x3Dw+tcw (:1818) is OpenCV gemm, restated as the
- * sequential fp32 expression ((r0*x0 + r1*x1) + r2*x2) + t  (SURVEY.md 8a U1 probe).
+ * Rcw*x3Dw+tcw (:1818) is OpenCV gemm, restated as the sequential fp32 expression
+ * ((r0*x0 + r1*x1) + r2*x2) + t; pinned bit for bit by the cv::gemm-based fixture
+ * tests/golden/golden_unary.npz (see header); observation order = CSR order.
  * ------------------------------------------------------------------------------------------ */
 void orc_map_point_unary(int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                          const float *obs_uv, const float *kf_pose, const float *kf_intr,

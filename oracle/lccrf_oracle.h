@@ -12,10 +12,16 @@
  *     oracle/Makefile from /root/reference/Thirdparty/DenseCRF/include) and against
  *     the reference's one golden vector (examples/res1_cpu.ppm, committed as
  *     tests/golden/golden_im1.npz by tests/golden/make_golden.py).
- *   - long-term unary (Tracking.cc:1803-1839, 1961-2013): PARITY UNPINNED.  Tracking.cc
- *     needs OpenCV C++/Eigen/Pangolin/g2o and cannot be compiled here; the reference has
- *     no test or fixture for it, and its own summation order is the pointer order of a
- *     std::map<KeyFrame*,size_t>.  The restatement fixes observation order = CSR order.
+ *   - long-term unary (Tracking.cc:1803-1839, 1961-2013): Tracking.cc needs OpenCV
+ *     C++/Eigen/Pangolin/g2o and cannot be compiled here, and the reference has no test or
+ *     fixture for it.  PINNED TO THE REFERENCE'S THIRD-PARTY ARITHMETIC instead: the
+ *     committed fixture tests/golden/golden_unary.npz (tests/golden/make_golden_unary.py)
+ *     evaluates :1803-1839 statement by statement with Rcw*x3Dw+tcw computed by the real
+ *     cv::gemm (cv2 4.13) and every scalar in its declared C++ type; this restatement
+ *     reproduces it bit for bit (tests/test_oracle.py::test_unary_vs_opencv_golden).
+ *     UNPINNED remains the summation order: the reference walks a
+ *     std::map<KeyFrame*,size_t> (pointer order, not reproducible); the restatement fixes
+ *     observation order = CSR order.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  Arithmetic is IEEE fp32 with each operation individually rounded
@@ -65,7 +71,7 @@ void orc_features_div2(float *feat /*[N*2]*/, const float *a, const float *b, in
 void orc_features_image(float *feat /*[W*H*F]*/, int W, int H, int F, float posdev,
                         const unsigned char *img_u8, const float *img_f32, float featuredev);
 
-/* ---- long-term unary (src/Tracking.cc:1803-1839) : PARITY UNPINNED ---- */
+/* ---- long-term unary (src/Tracking.cc:1803-1839) : pinned by tests/golden/golden_unary.npz (cv::gemm), see header ---- */
 void orc_map_point_unary(int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
                          const float *obs_uv, const float *kf_pose /*[nKF][12] R|t rows*/,
                          const float *kf_intr /*[nKF][4] fx fy cx cy*/,
