@@ -1206,6 +1206,10 @@ static int frames_run_slot(lccrf_frames *fr, FrameInputs &in) {
         return LCCRF_OK;
     }
     if (in.graph && in.graph_gen != ctx->scratch_gen) frame_inputs_drop_graph(in);  // a scratch buffer moved since capture
+    if (in.indexed && in.kp_gen != fr->kp_gen) {  // the keypoint table moved (keyframes inserted) since this slot was captured
+        frame_inputs_drop_graph(in);
+        in.kp_gen = fr->kp_gen;
+    }
     if (!in.graph) {
         // make sure every scratch buffer has its final size before capture (no allocation inside the graph)
         const uint64_t l0 = ctx->launches;
