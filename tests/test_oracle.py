@@ -205,3 +205,38 @@ def test_label_partition_restatement(oracle):
     assert np.array_equal(d, fid[lab == 0]) and np.array_equal(s, fid[lab != 0])
     d, s = oracle.label_partition(np.zeros(0, np.int16))
     assert d.size == 0 and s.size == 0
+
+
+def test_random_crf_shapes_vs_compiled_reference(oracle, ref):
+    """Randomised sweep (hypothesis, fixed seed): point counts incl. 0 and every N % 4 residue, labels, kernels,
+    feature dimensions and scales, weights, iterations, relax, unary-from-label with unknown (-1) labels -- oracle
+    marginals and MAP bit-identical to the unmodified reference headers compiled in place."""
+    from hypothesis import given, settings, strategies as st, HealthCheck, seed
+
+    @seed(20241)
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), database=None)
+    @given(st.data())
+    def run(data):
+        N = data.draw(st.one_of(st.integers(0, 9), st.integers(10, 700)), label="N")
+        L = data.draw(st.sampled_from([2, 3, 4]), label="L")
+        dims = data.draw(st.lists(st.sampled_from([2, 3, 5]), min_size=1, max_size=3), label="dims")
+        iters = data.draw(st.integers(1, 4), label="iters")
+        relax = data.draw(st.sampled_from([1.0, 0.5, 0.3]), label="relax")
+        rs = data.draw(st.integers(0, 2 ** 31 - 1), label="seed")
+        rng = np.random.default_rng(rs)
+        feats = [tie_features(rng, N, d, float(rng.uniform(0.5, 8.0))) for d in dims]
+        w = rng.uniform(0.5, 30.0, len(dims)).astype(np.float32)
+        if data.draw(st.booleans(), label="from_label"):
+            conf = float(data.draw(st.sampled_from([0.55, 0.7, 0.9]), label="conf"))
+            lab = rng.integers(-1, L, N).astype(np.int16)
+            en = ref.label_energies(L, conf)
+            unary = oracle.unary_from_label(lab, L, en[0], np.full(L, en[1], np.float32), np.full(L, en[2], np.float32))
+            Qr, mr = ref.crf3d(L, feats, w, iters, label=lab, conf=conf, relax=relax)
+        else:
+            unary = (rng.random((N, L)) * 4).astype(np.float32)
+            Qr, mr = ref.crf3d(L, feats, w, iters, unary=unary, relax=relax)
+        Qo, mo, _ = oracle.meanfield(unary, feats, w, iters, relax)
+        assert np.array_equal(bits(Qo), bits(Qr))
+        assert np.array_equal(mo, mr)
+
+    run()
