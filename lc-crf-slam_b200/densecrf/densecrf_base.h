@@ -44,7 +44,7 @@ inline lccrf_ctx *context() {
 }
 }  // namespace lccrf_detail
 
-// Define various pair wise weight (compatibility) models.
+// Plugin interface of the mean-field driver (densecrf_base.h:12-19): a potential adds its message onto `out_values`.
 class PairwisePotential {
 protected:
     int N_;
@@ -59,12 +59,12 @@ public:
 
 class DenseCRF {
 protected:
-    // Number of variables (and, in the subclasses, labels)
+    // point count; the label count M_ is fixed by the subclass template (lccrfCreate)
     int N_;
     // Host views, materialised lazily: only the plugin path and the getters touch them
     float *unary_, *current_, *next_, *tmp_;
     short *map_;
-    // Store all pairwise potentials (owned)
+    // potentials handed over by addPairwiseEnergy; deleted by the destructor (densecrf_base.h:41-45)
     std::vector<PairwisePotential *> pairwise_;
 
     lccrf_crf *crf_ = nullptr;  // device-side state
@@ -93,7 +93,7 @@ public:
     template <int M>
     static DenseCRF *Create(int N);  // declared for source compatibility; the reference's has no body either
 
-    // Add your own favorite pairwise potential (ownership is transferred to this class)
+    // takes ownership (densecrf_base.h:53-54); a built-in potential moves onto the device here
     void addPairwiseEnergy(PairwisePotential *potential) {
         pairwise_.push_back(potential);
         if (!potential->lccrfAttach(crf_, M_)) all_on_device_ = false;
@@ -103,7 +103,7 @@ public:
     virtual void setUnaryEnergyFromLabel(const short *label, float *confidences) = 0;
     virtual void setUnaryEnergyFromLabel(const short *label, float confidence = 0.5) = 0;
 
-    // Run inference; all returned values are managed by the class
+    // densecrf_base.h:65-73; getMap() / getProbability() stay valid until destruction (class-owned host arrays)
     virtual void inference(int n_iterations, bool with_map = false, float relax = 1.0) {
         if (all_on_device_) {
             lccrf_detail::check(lccrf_crf_inference(crf_, n_iterations, with_map ? 1 : 0, relax), "lccrf_crf_inference");
@@ -116,7 +116,7 @@ public:
     short *getMap() const { return const_cast<short *>(lccrf_crf_map(crf_)); }
     float *getProbability() const { return const_cast<float *>(lccrf_crf_prob(crf_)); }
 
-    // Step by step inference
+    // stepwise API (densecrf_base.h:78-91)
     virtual void startInference() { lccrf_detail::check(lccrf_crf_start(crf_), "lccrf_crf_start"); }
 
     virtual void stepInference(float relax = 1.0) {
