@@ -131,3 +131,41 @@ def test_bench_reference_arm_other_ranks_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
                         "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_unary_fast_sqrt_window_argument():
+    """The unary kernel's straight-line path (csrc/unary.cu observe_fast) takes (float)sqrt(s) from one double Newton
+    step on an fp32 rsqrt seed and trusts it unless the low 29 mantissa bits of the result lie within 2^13 ulps of a
+    float rounding boundary.  Model of that arithmetic with a seed that is WORSE than the hardware's (relative error
+    up to 2^-21 instead of <= 2^-22; the window holds up to 2^-20.5): wherever the window test passes, the result
+    equals the reference's (float)sqrt(double) bit for bit -- on random inputs and on inputs constructed next to
+    rounding boundaries (squares of float midpoints, nudged by a few double ulps)."""
+    rng = np.random.default_rng(42)
+    n = 2_000_000
+    mant = rng.random(n) + 1.0
+    s = mant * np.exp2(rng.integers(-58, 58, n).astype(np.float64))
+    # adversarial: squares of float midpoints, nudged by a few double ulps either way
+    f = (rng.random(n // 4).astype(np.float32) + np.float32(1)) * np.exp2(rng.integers(-20, 20, n // 4)).astype(np.float32)
+    mid = (f.astype(np.float64) + np.nextafter(f, np.float32(np.inf)).astype(np.float64)) * 0.5
+    adv = mid * mid
+    for k in (-3, -1, 0, 1, 3):
+        t = adv.copy()
+        for _ in range(abs(k)):
+            t = np.nextafter(t, np.inf if k > 0 else 0.0)
+        s = np.concatenate([s, t])
+    want = np.sqrt(s).astype(np.float32)                        # reference: double sqrt, then rounded to float
+    sf = s.astype(np.float32)
+    worst_flagged = 0.0
+    for delta in (-2.0 ** -21, -2.0 ** -22, 0.0, 2.0 ** -22, 2.0 ** -21, None):
+        d = rng.uniform(-2.0 ** -21, 2.0 ** -21, s.size) if delta is None else delta
+        rs = ((1.0 / np.sqrt(sf.astype(np.float64))) * (1.0 + d)).astype(np.float32)   # rsqrt.approx stand-in
+        g = (sf * rs).astype(np.float64)                         # __fmul_rn(sf, rs): fp32 product
+        h = (np.float32(0.5) * rs).astype(np.float64)
+        e2 = s - g * g                                           # fma(-g, g, s): g*g is exact (24-bit g), one rounding
+        y = (e2.astype(np.longdouble) * h.astype(np.longdouble) + g.astype(np.longdouble)).astype(np.float64)  # fma(e2, h, g)
+        low = (y.view(np.uint64) & np.uint64(0x1fffffff)).astype(np.int64)
+        amb = ((low - 0x0fffe000) & 0xffffffff) < 0x4000          # the kernel's unsigned 32-bit window test
+        ok = y.astype(np.float32) == want
+        assert ok[~amb].all(), "fast sqrt disagrees outside the ambiguity window (delta=%r)" % (delta,)
+        worst_flagged = max(worst_flagged, float(amb[:n].mean()))
+    assert worst_flagged < 2.0 ** -13  # the library fallback stays rare (expected 2^-15 on random inputs)
