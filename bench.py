@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lccrf", choices=["lccrf", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c2"])
     ap.add_argument("--batch", type=int, default=0, help="problems per step per GPU (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -59,7 +59,9 @@ WORKLOADS = {
     "c3": ("C3: long-term unary + CRF, N=100k map points x 64 keyframe observations, L=2, K=2 (d=2,2), T=5", 32, 100000, 64),
     "c1": ("C1: per-frame CRF, N=3000 points, L=2, K=2 (d=2,2), T=5 (reference's own CPU-runnable case)", 1, 3000, 0),
     "c4": ("C4: 1024 independent per-frame CRFs of N~U[4000,6000] points in one launch sequence", 1024, 5000, 0),
+    "c2": ("C2: full-image DenseCRF 640x480, L=2, Gaussian (sigma 3) + 5-D bilateral (sigma 60 / 20), T=10", 4, 640 * 480, 0),
 }
+C2 = dict(W=640, H=480, conf=0.7, w_g=3.0, sd_g=3.0, w_b=10.0, sd_b=60.0, sd_rgb=20.0, iters=10)  # example_cpu.cpp:86-98
 
 
 KP_STRIDE = 32768  # keypoint slots per keyframe of the resident table (C3: ~24k observations per keyframe)
@@ -74,6 +76,8 @@ def make_problems(workload: str, batch: int, seed0: int):
             return list(ex.map(lambda i: synth.map_snapshot(n, obs, seed=seed0 + i), range(batch)))
     if workload == "c1":
         return [synth.slam_frame(n, seed=seed0 + i) for i in range(batch)]
+    if workload == "c2":  # (uint8 RGB image [W*H,3], labels [W*H] with 70% unknown)
+        return [synth.image_problem(C2["W"], C2["H"], seed0 + i) for i in range(batch)]
     rng = np.random.default_rng(seed0)
     sizes = rng.integers(4000, 6001, batch)
     return [synth.slam_frame(int(s), seed=seed0 + 1 + i, dyn_frac=float(rng.uniform(0.15, 0.3))) for i, s in enumerate(sizes)]
@@ -156,7 +160,21 @@ def cpu_problem_runner(workload):
     prm = slam_params(**synth.SLAM_PARAMS)
     en = pkg.label_energies(2, prm.confidence)
 
+    def run_image(p):
+        img, lab = p
+        if r is not None:
+            r.image_crf(C2["W"], C2["H"], 2, lab, C2["conf"], C2["w_g"], C2["sd_g"], C2["w_b"], C2["sd_b"], img, C2["sd_rgb"],
+                        C2["iters"], want_q=False)
+        else:
+            e = pkg.label_energies(2, C2["conf"])
+            unary = o.unary_from_label(lab, 2, e[0], np.full(2, e[1], np.float32), np.full(2, e[2], np.float32))
+            o.meanfield(unary, [o.features_image(C2["W"], C2["H"], 2, C2["sd_g"]),
+                                o.features_image(C2["W"], C2["H"], 5, C2["sd_b"], img, C2["sd_rgb"])],
+                        [C2["w_g"], C2["w_b"]], C2["iters"])
+
     def run(p):
+        if workload == "c2":
+            return run_image(p)
         if workload == "c3":
             ob, er, de = o.map_point_unary(p)
             kp = p.kp2d
@@ -205,8 +223,9 @@ def run_reference_arm(args):
             list(ex.map(run, problems))
         dt = time.perf_counter() - t0
     value = args.steps * per_step / dt
-    sample = "%d problems per step on %d host threads; CRF = %s, unary = oracle port (Tracking.cc is not compilable)" % (
-        per_step, cores, "reference headers compiled in place (oracle/_ref)" if kind == "reference" else "oracle port")
+    sample = "%d problems per step on %d host threads; CRF = %s%s" % (
+        per_step, cores, "reference headers compiled in place (oracle/_ref)" if kind == "reference" else "oracle port",
+        "" if args.workload == "c2" else ", unary = oracle port (Tracking.cc is not compilable)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -285,7 +304,144 @@ def blur_measurements(pkg, ctx, peak):
     return out
 
 
+def run_gpu_arm_image(args):
+    """C2 (BASELINE configs[1]): the per-object API -- exactly the calls DenseCRFCPU<2> + PottsPotentialCPU::FromImage
+    forward to (examples/example_cpu.cpp:80-98: create, setUnaryEnergyFromLabel, two FromImage potentials, inference(10,
+    true), getMap) -- once per image and step, host buffers in and host results out.  This path has no device-resident
+    input variant, so `value` and `e2e` time the SAME calls: `value` by CUDA events on the launching stream, `e2e` by the
+    host clock around them (object construction, lattice builds, H2D of labels + image, D2H of marginals + MAP)."""
+    import torch
+    pkg = importlib.import_module("lc-crf-slam_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    desc, dbatch, n, _ = WORKLOADS["c2"]
+    batch = args.batch or dbatch
+    W, H, L, T = C2["W"], C2["H"], 2, C2["iters"]
+    problems = make_problems("c2", batch, seed0=1000 + 100000 * rank)
+    stream = torch.cuda.Stream()
+    ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
+    en = pkg.label_energies(L, C2["conf"])
+    maps = [None] * batch
+    V = [0, 0]
+
+    def step():
+        for i, (img, lab) in enumerate(problems):
+            crf = pkg.DenseCRF(ctx, W * H, L)
+            crf.setUnaryEnergyFromLabel(lab, energies=en)
+            crf.addPairwiseFromImage(W, H, C2["w_g"], C2["sd_g"])
+            crf.addPairwiseFromImage(W, H, C2["w_b"], C2["sd_b"], img, C2["sd_rgb"])
+            crf.inference(T, True)
+            maps[i] = crf.getMap().copy()
+            if i == 0:
+                V[0], V[1] = crf.potts_vertices(0), crf.potts_vertices(1)
+            crf.close()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        ref_maps = [m.copy() for m in maps]
+        l0 = ctx.kernel_launches
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        ms = ev0.elapsed_time(ev1)
+        launches = ctx.kernel_launches - l0
+        clocks = sampler.stop() if sampler else None
+        assert all(np.array_equal(a, b) for a, b in zip(maps, ref_maps))  # deterministic
+    t_dev = torch.tensor([ms, max(ms, wall_ms)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = (float(x) for x in t_dev.tolist())
+    total = world * batch * args.steps
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    N = W * H
+    D = (3, 6)
+    roofline = shares = kernel_ms = None
+    if not args.no_profile:
+        with torch.cuda.stream(stream):
+            ctx.set_option("profile", 1)
+            ctx.profile_report()
+            step()
+            rep = ctx.profile_report()
+            ctx.set_option("profile", 0)
+        tot = sum(v[1] for v in rep.values()) or 1.0
+        shares = {k: round(v[1] / tot, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+        kernel_ms = {k: round(v[1] / max(v[0], 1), 5) for k, v in rep.items()}
+        # algorithmic bytes per launch (SURVEY 8d), averaged over the launches of one problem
+        blur_launches = sum(D) * (T + 1)
+        ab = {"k_blur": sum(D[k] * V[k] * ((8 * L + 8) * T + 16) for k in range(2)) / blur_launches,
+              "k_mf_point_l2": N * (sum(D) * 8 + 2 * 4 + 2 * L * 4) + sum(V) * L * 4}
+        top = next(iter(shares))
+        cnt, tms = rep[top]
+        ach = ab[top] / (tms / cnt * 1e-3) / 1e9 if top in ab else None
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ab.get(top), "avg_launch_ms": tms / cnt, "share_of_step": shares[top],
+                    "achieved_gbs_all_kernels": {k: round(ab[k] / (rep[k][1] / rep[k][0] * 1e-3) / 1e9, 1) for k in ab if k in rep},
+                    "note": "per-kernel CUDA events on the launching stream; lattice working sets (V = %d, %d vertices) fit "
+                            "the 126 MB L2" % (V[0], V[1])}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        sample = [problems[i % len(problems)] for i in range(2 * cores)]
+        v, kind, dt = time_cpu("c2", sample, cores, repeats=2)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d problems on %d host threads in %.1f s; %s" % (
+                   2 * len(sample), cores, dt, "reference headers compiled in place (DenseCRFCPU<2>, FromImage)" if kind == "reference" else "oracle port")}
+    bytes_in, bytes_out = batch * N * (2 + 3), batch * N * (2 + 4 * L)
+    line = {
+        "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "problems_per_step_per_gpu": batch, "points_per_step_per_gpu": batch * N,
+                   "l2_policy": "per-image working set (~60 MB of lattice arrays) fits the 126 MB L2 and is NOT flushed: every step "
+                                "builds its lattices from fresh host inputs, so nothing is reused across steps",
+                   "sharding": "independent images per rank, no collective",
+                   "timing": "value: CUDA events on the launching stream; e2e: host clock around the same calls"},
+        "clocks": clocks,
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+                "ms_per_step": ms_e2e / args.steps, "inputs": "labels (int16) + RGB image (uint8) per image, pageable host arrays"},
+        "gpu_launches": int(launches), "roofline": roofline, "kernel_shares": shares, "kernel_avg_launch_ms": kernel_ms,
+        "lattice_vertices": V, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_gpu_arm(args):
+    if args.workload == "c2":
+        return run_gpu_arm_image(args)
     import torch
     pkg = importlib.import_module("lc-crf-slam_b200")
     synth_mod = importlib.import_module("lc-crf-slam_b200.synth")
