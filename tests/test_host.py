@@ -169,3 +169,95 @@ def test_unary_fast_sqrt_window_argument():
         assert ok[~amb].all(), "fast sqrt disagrees outside the ambiguity window (delta=%r)" % (delta,)
         worst_flagged = max(worst_flagged, float(amb[:n].mean()))
     assert worst_flagged < 2.0 ** -13  # the library fallback stays rare (expected 2^-15 on random inputs)
+
+
+def test_bench_c2_gpu_arm_against_a_mock_device(monkeypatch, capsys):
+    """bench.py --workload c2 (image CRF through the per-object API) cannot be timed without a GPU; its host logic --
+    step loop, event/host timing, profile folding, algorithmic bytes, JSON contract -- runs here against a mock device."""
+    import contextlib
+    import json
+    import time
+    import torch
+    bench = importlib.import_module("bench")
+    pkg = importlib.import_module("lc-crf-slam_b200")
+
+    class FakeStream:
+        cuda_stream = 0
+
+    class FakeEvent:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self, s=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t)
+
+    class FakeCtx:
+        kernel_launches = 0
+
+        def __init__(self, dev, stream=None):
+            pass
+
+        def set_option(self, k, v):
+            pass
+
+        def profile_report(self):
+            return {"k_blur": (99, 1.5), "k_embed": (2, 0.4), "k_mf_point_l2": (10, 0.5)}
+
+    class FakeCRF:
+        def __init__(self, ctx, N, L):
+            self.N = N
+            ctx.kernel_launches += 100
+
+        def setUnaryEnergyFromLabel(self, lab, energies=None):
+            assert lab.shape == (self.N,) and lab.dtype == np.int16
+
+        def addPairwiseFromImage(self, W, H, w, sd, img=None, fd=0.0):
+            assert img is None or (img.shape == (W * H, 3) and img.dtype == np.uint8)
+
+        def inference(self, T, with_map):
+            assert T == 10 and with_map
+
+        def getMap(self):
+            return np.zeros(self.N, np.int16)
+
+        def potts_vertices(self, k):
+            return (39890, 11600)[k]
+
+        def close(self):
+            pass
+
+    class FakeSampler:
+        def __init__(self, i):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
+
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch.cuda, "Stream", lambda: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch, "tensor", lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype))
+    monkeypatch.setattr(pkg, "Context", FakeCtx)
+    monkeypatch.setattr(pkg, "DenseCRF", FakeCRF)
+    monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "c2", "--steps", "2", "--warmup", "1", "--batch", "2", "--no-cpu-baseline"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "crf_problems_per_s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
+    assert d["config"]["workload"].startswith("C2") and d["config"]["problems_per_step_per_gpu"] == 2
+    assert d["gpu_launches"] == 2 * 2 * 100
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 640 * 480 * 5 and d["e2e"]["value"] <= d["value"] * 1.0000001
+    assert d["roofline"]["kernel"] == "k_blur" and abs(d["roofline"]["share_of_step"] - 0.625) < 1e-9
+    # k_blur: D passes per filter call, T calls with 2 labels + 1 norm call with 1 label, both lattices (SURVEY 8d B_blur)
+    want = (3 * 39890 + 6 * 11600) * ((8 * 2 + 8) * 10 + 16) / (9 * 11)
+    assert abs(d["roofline"]["algorithmic_bytes_per_launch"] - want) < 1e-6
