@@ -261,3 +261,147 @@ def test_bench_c2_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     # k_blur: D passes per filter call, T calls with 2 labels + 1 norm call with 1 label, both lattices (SURVEY 8d B_blur)
     want = (3 * 39890 + 6 * 11600) * ((8 * 2 + 8) * 10 + 16) / (9 * 11)
     assert abs(d["roofline"]["algorithmic_bytes_per_launch"] - want) < 1e-6
+
+
+def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
+    """The default bench arm (C3: device-resident loop, indexed and flat end-to-end loops, per-kernel profile, roofline,
+    cpu_baseline) on a reduced problem size against a mock device: guards the host logic and the JSON contract of the
+    line the driver parses."""
+    import contextlib
+    import json
+    import time
+    import torch
+    bench = importlib.import_module("bench")
+    pkg = importlib.import_module("lc-crf-slam_b200")
+    calls = {"run": 0, "indexed": 0, "flat": 0, "table": 0}
+
+    class FakeStream:
+        cuda_stream = 0
+
+    class FakeEvent:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self, s=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t) + 1e-3
+
+    class FakeCtx:
+        kernel_launches = 0
+
+        def __init__(self, dev, stream=None):
+            pass
+
+        def sync(self):
+            pass
+
+        def set_option(self, k, v):
+            pass
+
+        def profile_report(self):
+            return {"k_splat_tile": (36, 1.2), "k_scan_sums": (36, 0.3), "k_scan_compose": (36, 1.0), "k_scan_walk": (40, 0.4),
+                    "k_map_point_unary": (3, 2.0), "k_mf_point_l2": (15, 0.6), "k_blur": (9, 0.5)}
+
+    class FakeFrames:
+        def __init__(self, ctx, sizes, prm, energies=None):
+            self.ctx, self.NT, self.B = ctx, int(sum(sizes)), len(sizes)
+            self.map = (np.arange(self.NT) % 2).astype(np.int16)
+            self.prob = np.stack([1.0 - self.map, self.map], axis=1).astype(np.float32)
+
+        def set_map_inputs(self, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr=None):
+            assert obs_kf.dtype == np.int32 and obs_uv.shape == (obs_kf.size, 2) and obs_ptr[-1] == obs_kf.size
+
+        def set_keyframe_keypoints(self, table, kf_first=0):
+            assert table.ndim == 3 and table.shape[2] == 2 and table.dtype == np.float32
+            calls["table"] += 1
+
+        def run(self):
+            calls["run"] += 1
+            self.ctx.kernel_launches += 111
+
+        def _deliver(self, m, p):
+            m[:] = self.map
+            p[:] = self.prob
+
+        def get_outputs(self, m=None, p=None, want_prob=True):
+            self._deliver(m, p)
+            return m, p
+
+        def submit_map(self, slot, xyz, obs_ptr, obs_kf, obs_uv, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr, m, p):
+            assert obs_kf.dtype == np.uint16
+            calls["flat"] += 1
+            self._deliver(m, p)
+
+        def submit_map_indexed(self, slot, xyz, obs_ptr, obs_ref, kf_pose, kf_intr, kf_bounds, kp2d, kf_ptr, m, p):
+            assert obs_ref.dtype == np.uint16 and obs_ref.shape == (obs_ptr[-1], 2)
+            calls["indexed"] += 1
+            self._deliver(m, p)
+
+        def wait(self, slot):
+            pass
+
+        def get_debug(self):
+            return {"V": np.array([[29, 1200]] * self.B, dtype=np.int32)}
+
+        def debug_counters(self, k):
+            return {"long_rows": 1}
+
+        def algorithmic_bytes(self):
+            return {"total": 3.0e8, "per_iteration": 2.0e7, "unary": 1.0e8}
+
+    class FakeLattice:
+        V = 1000
+
+        def __init__(self, ctx, feat):
+            pass
+
+        def filter(self, x):
+            return x
+
+        def close(self):
+            pass
+
+    class FakeSampler:
+        def __init__(self, i):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
+
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch.cuda, "Stream", lambda: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch, "tensor", lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(pkg, "Context", FakeCtx)
+    monkeypatch.setattr(pkg, "Frames", FakeFrames)
+    monkeypatch.setattr(pkg, "Lattice", FakeLattice)
+    monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
+    monkeypatch.setitem(bench.WORKLOADS, "c3", ("C3 (reduced for the mock test)", 3, 1500, 8))
+    monkeypatch.setattr(bench, "KP_STRIDE", 1024)
+    # the blur stress lattice is a 2048 x 2048 grid: shrink the host-side feature assembly, the lattice is a mock anyway
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "1"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["steps"] == 4 and d["warmup"] == 3 and d["gpu_launches"] == 4 * 111 and d["vs_baseline"] is None
+    assert d["config"]["problems_per_step_per_gpu"] == 3 and d["config"]["points_per_step_per_gpu"] == 4500
+    nnz = 4500 * 8
+    assert d["e2e"]["h2d_bytes_per_step"] == 4500 * 12 + 4501 * 4 + nnz * 4 + 3 * 256 * (48 + 16 + 16) + 4500 * 8 + 4 * 4
+    assert d["e2e_full_snapshot"]["h2d_bytes_per_step"] == d["e2e"]["h2d_bytes_per_step"] + nnz * (2 + 8 - 4)
+    assert d["e2e"]["d2h_bytes_per_step"] == 4500 * (2 + 8)
+    assert calls["table"] == 1 and calls["indexed"] == 4 + 4 and calls["flat"] == 4 + 4
+    assert d["roofline"]["kernel"] == "k_splat_tile+k_scan_sums+k_scan_compose+k_scan_walk"
+    assert abs(d["roofline"]["share_of_step"] - 2.9 / 6.0) < 1e-3 and d["roofline"]["bound"] == "hbm"
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["cpu_baseline"]["value"] > 0
