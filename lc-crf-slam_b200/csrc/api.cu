@@ -1006,22 +1006,36 @@ void lccrf_frames_destroy(lccrf_frames *fr) {
 }
 
 // upload the direct per-frame vectors of one step into input set `in` on stream `st`
+// Input buffers are stream-ordered allocations of ctx->stream, but the pipelined submit path fills them on the copy
+// stream: after a (re)allocation the copy stream is ordered behind ctx->stream once, so that a block the pool recycled
+// from work still running there (the other slot's step) is not overwritten early.  Steady state allocates nothing.
+static int order_copies_after_alloc(Ctx *ctx, FrameInputs &in, cudaStream_t st) {
+    if (st == ctx->stream || !in.up_done) return LCCRF_OK;
+    LCCRF_CUDA(cudaEventRecord(in.up_done, ctx->stream));
+    LCCRF_CUDA(cudaStreamWaitEvent(st, in.up_done, 0));
+    return LCCRF_OK;
+}
+
 static int frames_upload_direct(lccrf_frames *fr, FrameInputs &in, cudaStream_t st, const float *observs,
                                 const float *error, const float *depth, const float *kp2d) {
     Ctx *ctx = fr->ctx;
     const size_t n = (size_t)fr->b.NT;
     if (n && (!observs || !error || !depth || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    bool fresh = false;
     if (!in.observs) {
         const size_t m = n ? n : 1;
         LCCRF_TRY(dev_alloc(ctx, (void **)&in.observs, m * 4));
         LCCRF_TRY(dev_alloc(ctx, (void **)&in.error, m * 4));
         LCCRF_TRY(dev_alloc(ctx, (void **)&in.depth, m * 4));
         frame_inputs_drop_graph(in);
+        fresh = true;
     }
     if (!in.kp2d) {
         LCCRF_TRY(dev_alloc(ctx, (void **)&in.kp2d, (n ? n : 1) * 8));
         frame_inputs_drop_graph(in);
+        fresh = true;
     }
+    if (fresh) LCCRF_TRY(order_copies_after_alloc(ctx, in, st));
     if (in.from_map) frame_inputs_drop_graph(in);
     in.from_map = false;
     if (n) {
@@ -1116,7 +1130,10 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
         regraph = true;
     }
     if (in.nKF != nKF || in.nnz != nnz || !in.from_map || in.have_kf_ptr != (kf_ptr != nullptr)) regraph = true;
-    if (regraph) frame_inputs_drop_graph(in);
+    if (regraph) {
+        frame_inputs_drop_graph(in);
+        LCCRF_TRY(order_copies_after_alloc(ctx, in, st));  // every (re)allocation above sets regraph
+    }
     in.nKF = nKF;
     in.nnz = nnz;
     in.obs_kf_bytes = obs_kf_bytes;
