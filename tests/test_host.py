@@ -263,10 +263,9 @@ def test_bench_c2_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     assert abs(d["roofline"]["algorithmic_bytes_per_launch"] - want) < 1e-6
 
 
-def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
-    """The default bench arm (C3: device-resident loop, indexed and flat end-to-end loops, per-kernel profile, roofline,
-    cpu_baseline) on a reduced problem size against a mock device: guards the host logic and the JSON contract of the
-    line the driver parses."""
+def _mock_device(monkeypatch):
+    """Replace CUDA (torch.cuda streams/events, pinned memory) and the device-side classes of the package by host mocks
+    that deliver fixed results; returns (bench module, call counters)."""
     import contextlib
     import json
     import time
@@ -339,6 +338,13 @@ def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
             calls["indexed"] += 1
             self._deliver(m, p)
 
+        def set_inputs(self, observs, error, depth, kp2d):
+            assert observs.shape == (self.NT,) and kp2d.shape == (self.NT, 2)
+
+        def submit(self, slot, observs, error, depth, kp2d, m, p):
+            calls["direct"] = calls.get("direct", 0) + 1
+            self._deliver(m, p)
+
         def wait(self, slot):
             pass
 
@@ -382,6 +388,15 @@ def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     monkeypatch.setattr(pkg, "Frames", FakeFrames)
     monkeypatch.setattr(pkg, "Lattice", FakeLattice)
     monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
+    return bench, calls
+
+
+def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
+    """The default bench arm (C3: device-resident loop, indexed and flat end-to-end loops, per-kernel profile, roofline,
+    cpu_baseline) on a reduced problem size against a mock device: guards the host logic and the JSON contract of the
+    line the driver parses."""
+    import json
+    bench, calls = _mock_device(monkeypatch)
     monkeypatch.setitem(bench.WORKLOADS, "c3", ("C3 (reduced for the mock test)", 3, 1500, 8))
     monkeypatch.setattr(bench, "KP_STRIDE", 1024)
     # the blur stress lattice is a 2048 x 2048 grid: shrink the host-side feature assembly, the lattice is a mock anyway
@@ -405,3 +420,22 @@ def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     assert d["roofline"]["kernel"] == "k_splat_tile+k_scan_sums+k_scan_compose+k_scan_walk"
     assert abs(d["roofline"]["share_of_step"] - 2.9 / 6.0) < 1e-3 and d["roofline"]["bound"] == "hbm"
     assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["cpu_baseline"]["value"] > 0
+
+
+def test_bench_c4_gpu_arm_against_a_mock_device(monkeypatch, capsys):
+    """The batched per-frame workload (C4: direct per-frame vectors, lccrf_frames_submit) through the same mock."""
+    import json
+    bench, calls = _mock_device(monkeypatch)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "c4", "--batch", "6", "--steps", "3", "--warmup", "1"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    NT = d["config"]["points_per_step_per_gpu"]
+    assert d["config"]["workload"].startswith("C4") and d["config"]["problems_per_step_per_gpu"] == 6
+    assert 6 * 4000 <= NT <= 6 * 6000
+    assert d["e2e"]["h2d_bytes_per_step"] == NT * (4 + 4 + 4 + 8) and d["e2e"]["d2h_bytes_per_step"] == NT * 10
+    assert d["e2e_full_snapshot"] is None and calls["direct"] == 4 + 3 and calls["indexed"] == 0
+    assert d["cpu_baseline"]["value"] > 0 and "fits the 126 MB L2" not in d["config"]["l2_policy"]
