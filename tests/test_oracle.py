@@ -154,6 +154,29 @@ def test_unary_vs_opencv_golden(oracle, name):
     assert (er > 0).any() and np.isfinite(er).all()
 
 
+def test_unary_vs_opencv_live(oracle):
+    """Where the cv2 wheel is importable (the build container) the cv::gemm-based evaluation of Tracking.cc:1803-1839
+    runs live on fresh random snapshots, beyond the committed fixture."""
+    pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, GOLD)
+    try:
+        gen = importlib.import_module("make_golden_unary")
+    finally:
+        sys.path.remove(GOLD)
+    for seed in range(6):
+        s = synth.map_snapshot(40 + 13 * seed, 3 + 4 * seed, seed=500 + seed, n_kf=12 + 5 * seed, ragged=seed % 2 == 0)
+        if seed >= 3:  # different cameras per keyframe
+            s.kf_intr = s.kf_intr.copy()
+            s.kf_intr[::2, :2] *= np.float32(1.0 + 0.01 * seed)
+            s.kf_bounds = s.kf_bounds.copy()
+            s.kf_bounds[1::3, 1] -= np.float32(11 * seed)
+        ob, er, de = gen.unary_cv2(s)
+        o_ob, o_er, o_de = oracle.map_point_unary(s)
+        assert np.array_equal(o_ob, ob), seed
+        assert np.array_equal(bits(o_er), bits(er)) and np.array_equal(bits(o_de), bits(de)), seed
+
+
 def test_bf_match_vs_opencv_golden(oracle):
     """Tracking::BfMatch restatement against cv::BFMatcher.knnMatch(k=2) outputs captured from OpenCV itself
     (tests/golden/make_golden_frontend.py): nearest-two lists incl. tie order, and the 0.6 ratio test."""
