@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--impl", default="lccrf", choices=["lccrf", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c2"])
     ap.add_argument("--batch", type=int, default=0, help="problems per step per GPU (0 = workload default)")
+    ap.add_argument("--splat", default="tree", choices=["tree", "ordered"],
+                    help="tree: fixed-shape tree reduction per lattice vertex (marginals within the 1e-4 gate); "
+                         "ordered: point-ordered sums, bit-identical to the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -64,6 +67,11 @@ WORKLOADS = {
 C2 = dict(W=640, H=480, conf=0.7, w_g=3.0, sd_g=3.0, w_b=10.0, sd_b=60.0, sd_rgb=20.0, iters=10)  # example_cpu.cpp:86-98
 
 
+SPLAT_MODES = {
+    "tree": "ordered_splat=0: fixed-shape tree reduction per lattice vertex (deterministic; marginals within 1e-4 relative of "
+            "the reference, MAP identical except near-ties -- tests/test_gpu_tree_splat.py)",
+    "ordered": "ordered_splat=1: every vertex row summed in point order (marginals bit-identical to the reference)",
+}
 KP_STRIDE = 32768  # keypoint slots per keyframe of the resident table (C3: ~24k observations per keyframe)
 
 
@@ -240,7 +248,8 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------- GPU arm
 # Kernels that together implement one stage are timed as a group (one "launch" of the group = one launch of its
 # first kernel): the ordered splat runs as k_splat_tile (short rows) + k_scan_sums/compose/walk (long rows) per filter call.
-KERNEL_GROUPS = {"splat": ("k_splat_tile", "k_scan_sums", "k_scan_compose", "k_scan_walk")}
+KERNEL_GROUPS = {"splat": ("k_splat_tile", "k_scan_sums", "k_scan_compose", "k_scan_walk"),
+                 "splat_tree": ("k_splat_tree", "k_splat_carry")}
 
 
 def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, kf_bytes=4, T=5, L=2, D=3, K=2):
@@ -253,6 +262,7 @@ def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, kf_bytes=4, T=5, L=2,
     return {
         "k_map_point_unary": nnz * (kf_bytes + 8) + N_tot * (12 + 4 + 12) + nKF * 80,   # B_u
         "splat": E * 8 + splat_io,                                   # (point, weight) entries + in + vertex sums
+        "splat_tree": E * 8 + splat_io,
         "k_blur_fused": D * V_tot * (8 * L + 8),                     # B_blur
         "k_mf_point_l2": N_tot * (K * D * 8 + K * 4 + 2 * L * 4) + K * V_tot * L * 4,  # slice x K + apply + softmax
         "k_slice": N_tot * D * 8 + N_tot * 4 * 2 + V_tot * 4,
@@ -462,6 +472,7 @@ def run_gpu_arm(args):
     problems = make_problems(args.workload, batch, seed0=1000 + 100000 * rank)
     stream = torch.cuda.Stream()
     ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
+    ctx.set_option("ordered_splat", 1 if args.splat == "ordered" else 0)
     prm = pkg.SlamParams.make()
     sizes = [p.n for p in problems]
     F = pkg.Frames(ctx, sizes, prm)
@@ -705,7 +716,8 @@ def run_gpu_arm(args):
                                 if abytes["total"] > 126e6 else
                                 ("working set %.1f MB per step fits the 126 MB L2 and is NOT flushed between steps: "
                                  "cache-resident latency figure, not a headline configuration" % (abytes["total"] / 1e6)),
-                   "sharding": "independent problems per rank, no collective"},
+                   "sharding": "independent problems per rank, no collective",
+                   "splat_mode": SPLAT_MODES[args.splat]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "inputs": e2e_mode},

@@ -333,6 +333,10 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
     if (!h || !name) return fail(LCCRF_ERR_ARG, "NULL argument");
     if (!strcmp(name, "graphs")) h->c.opt_graphs = value;
     else if (!strcmp(name, "fused")) h->c.opt_fused = value;
+    else if (!strcmp(name, "ordered_splat")) {
+        if (h->c.opt_ordered_splat != (value ? 1 : 0)) h->c.scratch_gen++;  // captured graphs hold the other kernel set
+        h->c.opt_ordered_splat = value ? 1 : 0;
+    }
     else if (!strcmp(name, "profile")) h->c.opt_profile = value;
     else if (!strcmp(name, "concurrent")) h->c.opt_concurrent = value;
     else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);

@@ -327,6 +327,17 @@ k_long_chunks(const int *__restrict__ row_ptr, const int *__restrict__ lng, int 
     }
 }
 
+// tile_row0[t] = the (non-empty) row that holds entry t * kTreeTile; tile_row0[n_tiles] = V - 1 (k_splat_tree)
+__global__ void __launch_bounds__(kThreads)
+k_tile_rows(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ tile_row0, int n_tiles) {
+    const int V = __ldg(vtotal);
+    if (blockIdx.x == 0 && threadIdx.x == 0) tile_row0[n_tiles] = V - 1;
+    for (int v = blockIdx.x * kThreads + threadIdx.x; v < V; v += gridDim.x * kThreads) {
+        const int s = __ldg(row_ptr + v), e = __ldg(row_ptr + v + 1);
+        for (int t = (s + kTreeTile - 1) / kTreeTile; t < n_tiles && t * kTreeTile < e; t++) tile_row0[t] = v;
+    }
+}
+
 }  // namespace
 
 int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
@@ -375,6 +386,10 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     rc |= dev_alloc(ctx, (void **)&ls->row_counts, 8 * 4);
     ls->max_pieces = (int)(((long long)b.NT * D) / kTileGranule + ((long long)b.NT * D) / kLongRow + 2);
     rc |= dev_alloc(ctx, (void **)&ls->piece_list, (size_t)ls->max_pieces * 4);
+    ls->n_tiles = (int)(((long long)b.NT * D + kTreeTile - 1) / kTreeTile);
+    rc |= dev_alloc(ctx, (void **)&ls->tile_row0, ((size_t)ls->n_tiles + 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->tile_info, ((size_t)ls->n_tiles + 1) * sizeof(int2));
+    if (ls->Lmax > 0) rc |= dev_alloc(ctx, (void **)&ls->tile_part, ((size_t)ls->n_tiles + 1) * ls->Lmax * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
     cudaStream_t st = ctx->stream;
     if (ls->csr_chunks > 0) {
@@ -405,6 +420,9 @@ void csr_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->chunk_rec);
     dev_free(ctx, ls->row_counts);
     dev_free(ctx, ls->piece_list);
+    dev_free(ctx, ls->tile_row0);
+    dev_free(ctx, ls->tile_info);
+    dev_free(ctx, ls->tile_part);
 }
 
 int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
@@ -444,6 +462,10 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     if (ls->max_long > 0) {
         LCCRF_KERNEL(ctx, "k_long_chunks");
         k_long_chunks<<<1, 1024, 0, st>>>(ls->row_ptr, ls->row_list_long, ls->row_counts, ls->long_chunk0, (int4 *)ls->chunk_desc);
+    }
+    if (ls->n_tiles > 0) {
+        LCCRF_KERNEL(ctx, "k_tile_rows");
+        k_tile_rows<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->tile_row0, ls->n_tiles);
     }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;

@@ -49,6 +49,11 @@ struct LatticeSet {
     // pieces of k_splat_tile: first rows of the maximal runs of short rows that start in one kTileGranule granule
     int *piece_list = nullptr;      // [max_pieces]
     int max_pieces = 0;
+    // tree splat (option "ordered_splat" = 0): fixed tiles of kTreeTile sorted entries
+    int n_tiles = 0;
+    int *tile_row0 = nullptr;       // [n_tiles+1] row that holds the first entry of each tile; [n_tiles] = V-1
+    int2 *tile_info = nullptr;      // [n_tiles] {position of the first row start inside the tile or -1, row open at the tile's end or -1}
+    float *tile_part = nullptr;     // [n_tiles*Lmax] sum of the tile's entries in front of its first row start
     // filter workspace
     float *valA = nullptr, *valB = nullptr;  // [Vcap*Lmax] blur ping-pong
     int Lmax = 0;
@@ -59,6 +64,7 @@ constexpr int kLongRow = 1024;    // rows at least this long leave the staged la
 constexpr int kScanChunk = 2048;  // entries per chunk of a long row
 constexpr int kChunkRecBytes = 16 + 2 * 24 + 4 * (kScanChunk / 256) * 4;  // sizeof(ChunkRec) of filter.cu
 constexpr int kTileGranule = 2048;  // entry granularity of the k_splat_tile windows
+constexpr int kTreeTile = 2048;     // entries per tile of the tree splat (filter.cu: k_splat_tree)
 
 struct Batch {
     Ctx *ctx = nullptr;
@@ -81,6 +87,9 @@ struct Ctx {
     uint64_t scratch_gen = 0;  // bumped whenever a scratch buffer moves (captured graphs hold raw pointers)
     int opt_graphs = 1;
     int opt_fused = 1;
+    // 1: splat sums every vertex row in point order (bit-identical to the reference's sequential loop);
+    // 0: fixed-shape tree reduction per row (deterministic; marginals within the 1e-4 gate, not bit-identical)
+    int opt_ordered_splat = 1;
     // per-kernel CUDA-event timing (option "profile"): every launch site is bracketed by two events
     int opt_profile = 0;
     struct ProfRec {

@@ -819,6 +819,254 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
     }
 }
 
+// ---------------------------------------------------------------- tree splat (option "ordered_splat" = 0)
+// The same segmented reduction over the vertex-sorted entries, but every row is summed by a FIXED-SHAPE TREE instead
+// of front to back: one streaming pass, balanced whatever the row lengths are, and deterministic (the shape depends on
+// row_ptr only).  Marginals agree with the reference within its own sequential rounding error (tests gate 1e-4
+// relative, north_star), not bit for bit -- the ordered kernels above stay the default.
+//   k_splat_tree   a CTA owns a tile of kTreeTile consecutive entries.  Phase 1: coalesced entry stream, gather
+//                  in[point], products to shared memory; row starts that fall into the tile are marked with their row
+//                  id.  Phase 2: thread t folds its 8 consecutive products left to right, a segmented scan over the
+//                  threads (warp shuffles + one shared level) closes every row that ends inside the tile.  What is
+//                  open at the tile's borders goes to tile_part (the part in front of the first row start) and, as a
+//                  partial sum, to val[row open at the end].
+//   k_splat_carry  rows that span tiles: partial + the leading parts of the following tiles, in tile order; rows without
+//                  entries (vertices only phantom points touch) are zeroed.
+constexpr int kTreeThreads = 256;
+constexpr int kTreeIT = kTreeTile / kTreeThreads;  // 8 consecutive entries per thread
+static_assert(kTreeIT == 8, "padding scheme below assumes 8 entries per thread");
+__device__ __forceinline__ int tpad(int i) { return i + (i >> 3); }  // one padding slot per thread: conflict-free both ways
+
+template <int LG>
+__global__ void __launch_bounds__(kTreeThreads)
+k_splat_tree(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0, const int2 *__restrict__ ent,
+             const float *__restrict__ in, float *__restrict__ val, float *__restrict__ tile_part,
+             int2 *__restrict__ tile_info, int n_tiles, long long E, int L, int lb) {
+    __shared__ float s_prod[LG][kTreeTile + kTreeTile / 8];
+    __shared__ int s_row[kTreeTile + kTreeTile / 8];   // row id of the row that starts at this entry, -1 otherwise
+    __shared__ float s_wv[kTreeThreads / 32][LG];
+    __shared__ int s_wf[kTreeThreads / 32], s_wr[kTreeThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long t0 = (long long)t * kTreeTile;
+        const int cnt = (int)min((long long)kTreeTile, E - t0);
+        // rows that start inside the tile: [ra, rb]; the first kTreeThreads of them are fetched alongside the entries
+        const int ra = __ldg(tile_row0 + t), rb = __ldg(tile_row0 + t + 1);
+        long long rs0 = -1, rz0 = -1;
+        if (ra + tid <= rb) {
+            rs0 = __ldg(row_ptr + ra + tid);
+            rz0 = __ldg(row_ptr + ra + tid + 1);
+        }
+        // phase 1
+        int2 e[kTreeIT];
+#pragma unroll
+        for (int q = 0; q < kTreeIT; q++) {
+            const int i = q * kTreeThreads + tid;
+            e[q] = i < cnt ? __ldg(ent + t0 + i) : make_int2(0, 0);
+            s_row[tpad(i)] = -1;
+        }
+        float x[kTreeIT][LG];
+#pragma unroll
+        for (int q = 0; q < kTreeIT; q++) {
+            const int i = q * kTreeThreads + tid;
+            if (LG == 2 && L == 2) {
+                const float2 v = i < cnt ? __ldg((const float2 *)in + e[q].x) : make_float2(0.f, 0.f);
+                x[q][0] = v.x;
+                x[q][LG - 1] = v.y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < LG; j++) x[q][j] = (i < cnt && lb + j < L) ? __ldg(in + (size_t)e[q].x * L + lb + j) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kTreeIT; q++) {
+            const int i = q * kTreeThreads + tid;
+            const float w = __int_as_float(e[q].y);
+#pragma unroll
+            for (int j = 0; j < LG; j++) s_prod[j][tpad(i)] = i < cnt ? __fmul_rn(w, x[q][j]) : 0.0f;
+        }
+        __syncthreads();  // s_row is cleared
+        if (rz0 > rs0 && rs0 >= t0 && rs0 < t0 + cnt) s_row[tpad((int)(rs0 - t0))] = ra + tid;
+        for (int r = ra + kTreeThreads + tid; r <= rb; r += kTreeThreads) {
+            const long long s = __ldg(row_ptr + r), z = __ldg(row_ptr + r + 1);
+            if (z > s && s >= t0 && s < t0 + cnt) s_row[tpad((int)(s - t0))] = r;
+        }
+        __syncthreads();
+        // phase 2: thread-sequential fold of 8 consecutive entries
+        float acc[LG], first[LG];
+#pragma unroll
+        for (int j = 0; j < LG; j++) acc[j] = first[j] = 0.0f;
+        int head_row = -1;       // row of the last row start among my entries
+        int first_pos = -1;      // position of my first row start
+        // (rows that start AND end among my entries are written at once)
+#pragma unroll
+        for (int k = 0; k < kTreeIT; k++) {
+            const int i = tid * kTreeIT + k;
+            const int r = s_row[tpad(i)];
+            if (r >= 0) {
+                if (head_row < 0) {
+                    first_pos = i;
+#pragma unroll
+                    for (int j = 0; j < LG; j++) first[j] = acc[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < LG; j++)
+                        if (lb + j < L) val[(size_t)head_row * L + lb + j] = acc[j];
+                }
+                head_row = r;
+#pragma unroll
+                for (int j = 0; j < LG; j++) acc[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < LG; j++) acc[j] = __fadd_rn(acc[j], s_prod[j][tpad(i)]);
+        }
+        const bool has = head_row >= 0;
+        if (!has) {
+#pragma unroll
+            for (int j = 0; j < LG; j++) first[j] = acc[j];
+        }
+        // segmented inclusive scan over the threads of (has, open sum, row): op (l, r) = r.has ? r : (l.has, l.v + r.v, l.row)
+        float v[LG];
+#pragma unroll
+        for (int j = 0; j < LG; j++) v[j] = acc[j];  // has: sum behind my last row start; else: all my entries
+        int f = has ? 1 : 0, rw = head_row;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            float vu[LG];
+#pragma unroll
+            for (int j = 0; j < LG; j++) vu[j] = __shfl_up_sync(0xffffffffu, v[j], o);
+            const int fu = __shfl_up_sync(0xffffffffu, f, o), ru = __shfl_up_sync(0xffffffffu, rw, o);
+            if (lane >= o && !f) {
+#pragma unroll
+                for (int j = 0; j < LG; j++) v[j] = __fadd_rn(vu[j], v[j]);
+                f = fu;
+                rw = ru;
+            }
+        }
+        // exclusive value inside the warp
+        float cv[LG];
+#pragma unroll
+        for (int j = 0; j < LG; j++) cv[j] = __shfl_up_sync(0xffffffffu, v[j], 1);
+        int cf = __shfl_up_sync(0xffffffffu, f, 1), cr = __shfl_up_sync(0xffffffffu, rw, 1);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < LG; j++) cv[j] = 0.0f;
+            cf = 0;
+            cr = -1;
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < LG; j++) s_wv[wid][j] = v[j];
+            s_wf[wid] = f;
+            s_wr[wid] = rw;
+        }
+        __syncthreads();
+        // carry of the preceding warps, combined in warp order
+        float pv[LG];
+#pragma unroll
+        for (int j = 0; j < LG; j++) pv[j] = 0.0f;
+        int pf = 0, pr = -1;
+        for (int w = 0; w < wid; w++) {
+            if (s_wf[w]) {
+#pragma unroll
+                for (int j = 0; j < LG; j++) pv[j] = s_wv[w][j];
+                pf = 1;
+                pr = s_wr[w];
+            } else {
+#pragma unroll
+                for (int j = 0; j < LG; j++) pv[j] = __fadd_rn(pv[j], s_wv[w][j]);
+            }
+        }
+        if (!cf) {  // no row start between the beginning of my warp and me: the carry reaches into the preceding warps
+#pragma unroll
+            for (int j = 0; j < LG; j++) cv[j] = __fadd_rn(pv[j], cv[j]);
+            cf = pf;
+            cr = pr;
+        }
+        // (cf, cv, cr) = what is open in front of my entries: started by row cr inside the tile (cf) or before the tile
+        if (has) {
+            // the open segment ends at my first row start
+            if (cf) {
+#pragma unroll
+                for (int j = 0; j < LG; j++)
+                    if (lb + j < L) val[(size_t)cr * L + lb + j] = __fadd_rn(cv[j], first[j]);
+            } else {  // I hold the first row start of the tile: everything in front of it belongs to an earlier tile's row
+#pragma unroll
+                for (int j = 0; j < LG; j++)
+                    if (lb + j < L) tile_part[(size_t)t * L + lb + j] = __fadd_rn(cv[j], first[j]);
+                if (lb == 0) tile_info[t].x = first_pos;
+            }
+        }
+        if (tid == kTreeThreads - 1) {  // what is open at the end of the tile
+            float ov[LG];
+            int orow;
+            if (has) {
+#pragma unroll
+                for (int j = 0; j < LG; j++) ov[j] = acc[j];
+                orow = head_row;
+            } else {
+#pragma unroll
+                for (int j = 0; j < LG; j++) ov[j] = __fadd_rn(cv[j], acc[j]);
+                orow = cf ? cr : -1;
+            }
+            if (orow >= 0) {
+#pragma unroll
+                for (int j = 0; j < LG; j++)
+                    if (lb + j < L) val[(size_t)orow * L + lb + j] = ov[j];
+            } else {  // no row start in the whole tile
+#pragma unroll
+                for (int j = 0; j < LG; j++)
+                    if (lb + j < L) tile_part[(size_t)t * L + lb + j] = ov[j];
+                if (lb == 0) tile_info[t].x = -1;
+            }
+            if (lb == 0) tile_info[t].y = orow;
+        }
+        __syncthreads();  // shared arrays are reused by the next tile
+    }
+}
+
+// rows that span tiles + rows without entries.  One thread per tile / per row.
+__global__ void __launch_bounds__(kThreads)
+k_splat_carry(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, const int2 *__restrict__ tile_info,
+              const float *__restrict__ tile_part, float *__restrict__ val, int n_tiles, int L) {
+    const int V = __ldg(vtotal);
+    const int gsz = gridDim.x * kThreads, g0 = blockIdx.x * kThreads + threadIdx.x;
+    for (int t = g0; t < n_tiles; t += gsz) {
+        const int row = __ldg(&tile_info[t].y);
+        // the row open at the end of tile t started in tile t iff tile t holds a row start
+        if (row < 0 || __ldg(&tile_info[t].x) < 0) continue;
+        int t2 = t + 1;
+        if (t2 >= n_tiles || __ldg(&tile_info[t2].x) == 0) continue;  // the next tile begins with a row start: complete
+        // the leading parts of the following tiles, in tile order; loads run kCarryU tiles ahead of the additions
+        constexpr int kCarryU = 8;
+        bool open = true;
+        for (int u0 = t2; open && u0 < n_tiles; u0 += kCarryU) {
+            int fp[kCarryU];
+#pragma unroll
+            for (int q = 0; q < kCarryU; q++) fp[q] = u0 + q < n_tiles ? __ldg(&tile_info[u0 + q].x) : 0;
+            for (int l = 0; l < L; l++) {
+                float pt[kCarryU];
+#pragma unroll
+                for (int q = 0; q < kCarryU; q++) pt[q] = u0 + q < n_tiles ? __ldg(tile_part + (size_t)(u0 + q) * L + l) : 0.0f;
+                float acc = val[(size_t)row * L + l];
+#pragma unroll
+                for (int q = 0; q < kCarryU; q++) {
+                    if (fp[q] == 0) break;
+                    acc = __fadd_rn(acc, pt[q]);
+                    if (fp[q] > 0) break;
+                }
+                val[(size_t)row * L + l] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < kCarryU; q++)
+                if (fp[q] >= 0) open = false;  // a row start (or the end of the tiles) closes the row
+        }
+    }
+    for (int r = g0; r < V; r += gsz)
+        if (__ldg(row_ptr + r + 1) == __ldg(row_ptr + r))
+            for (int l = 0; l < L; l++) val[(size_t)r * L + l] = 0.0f;
+}
+
 // ---------------------------------------------------------------- blur
 // One pass new[v] = old[v] + 0.5*(old[n1(v)] + old[n2(v)])  (permutohedral_cpu.h:663-679) for lattices that do not fit
 // one CTA (image-scale V).  HBM stream: per vertex one int2 neighbour pair, the vertex's own labels and the result
@@ -1003,7 +1251,23 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     const int D = ls->D;
     const int *vt = ls->vbase + ls->B;
     float *src = ls->valA, *dst = ls->valB;
-    if (b.NT > 0) {
+    if (b.NT > 0 && !ctx->opt_ordered_splat) {
+        // tree splat: one streaming pass over the sorted entries per label group + the cross-tile carries
+        const long long E = (long long)b.NT * D;
+        const int grid = ls->n_tiles < kNumSMs * 8 ? ls->n_tiles : kNumSMs * 8;
+        const int LG = L == 1 ? 1 : (L == 2 ? 2 : 4);
+        for (int lb = 0; lb < L; lb += LG) {
+            LCCRF_KERNEL(ctx, "k_splat_tree");
+            if (LG == 1) k_splat_tree<1><<<grid, kTreeThreads, 0, st>>>(ls->row_ptr, ls->tile_row0, ls->csr_ent, in_dev, src, ls->tile_part, ls->tile_info, ls->n_tiles, E, L, lb);
+            else if (LG == 2) k_splat_tree<2><<<grid, kTreeThreads, 0, st>>>(ls->row_ptr, ls->tile_row0, ls->csr_ent, in_dev, src, ls->tile_part, ls->tile_info, ls->n_tiles, E, L, lb);
+            else k_splat_tree<4><<<grid, kTreeThreads, 0, st>>>(ls->row_ptr, ls->tile_row0, ls->csr_ent, in_dev, src, ls->tile_part, ls->tile_info, ls->n_tiles, E, L, lb);
+        }
+        {
+            LCCRF_KERNEL(ctx, "k_splat_carry");
+            const int cg = persistent_grid(ls->n_tiles > ls->Vcap ? ls->n_tiles : ls->Vcap, kThreads, 4);
+            k_splat_carry<<<cg, kThreads, 0, st>>>(ls->row_ptr, vt, ls->tile_info, ls->tile_part, src, ls->n_tiles, L);
+        }
+    } else if (b.NT > 0) {
         const int LG = tile_labels(L);
         const int grid = ls->max_pieces < kNumSMs * 8 ? ls->max_pieces : kNumSMs * 8;
         const size_t smem = (size_t)(kTileGranule + kLongRow) * LG * sizeof(float);
@@ -1017,7 +1281,7 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     }
     // long rows (>= kLongRow entries): speculative parallel scan.  The lists live on the device, so the grids are
     // sized for the worst case a lattice set can hold and capped at a few waves (grid-stride inside).
-    if (b.NT > 0 && ls->max_chunks > 0) {
+    if (b.NT > 0 && ls->max_chunks > 0 && ctx->opt_ordered_splat) {
         const long long maxc = (long long)ls->max_chunks * ((L + 1) / 2), maxr = (long long)ls->max_long * L;
         const int gc = (int)(maxc < kNumSMs * 16 ? maxc : kNumSMs * 16);
         const int gk = (int)(maxc < kNumSMs * 3 ? maxc : kNumSMs * 3);  // compose: persistent, one resident wave

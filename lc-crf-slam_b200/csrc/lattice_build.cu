@@ -468,9 +468,11 @@ int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     dev_free(ctx, ls->valB);
     dev_free(ctx, ls->chunk_sum);
     dev_free(ctx, ls->chunk_rec);
+    dev_free(ctx, ls->tile_part);
     ls->valA = ls->valB = nullptr;
     ls->chunk_sum = nullptr;
     ls->chunk_rec = nullptr;
+    ls->tile_part = nullptr;
     ls->Lmax = 0;
     int rc = LCCRF_OK;
     {
@@ -480,6 +482,7 @@ int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     }
     rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * L * sizeof(float));
     rc |= dev_alloc(ctx, (void **)&ls->valB, (size_t)ls->Vcap * L * sizeof(float));
+    rc |= dev_alloc(ctx, (void **)&ls->tile_part, ((size_t)ls->n_tiles + 1) * L * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
     ls->Lmax = L;
     return LCCRF_OK;
