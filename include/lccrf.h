@@ -266,6 +266,87 @@ int lccrf_frames_debug_counters(lccrf_frames *fr, int k, int *out8);
 /* algorithmic bytes of one lccrf_frames_run by the SURVEY 8(d) formulas with the actual V (valid after a run) */
 int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_iteration, double *unary);
 
+/* ---------------------------------------------------------------- device-resident map ----- */
+/* In the reference the observation lists, keyframe poses and keypoints are persistent MAP state that tracking only reads
+ * (Tracking::ComputeMapPointErrAndObserv, src/Tracking.cc:1803-1839) and local mapping mutates a little per keyframe.
+ * lccrf_map keeps that state in HBM, so that per frame only the list of visible map points, the frame's keypoints and the
+ * step's changes cross PCIe.  One lccrf_map_delta carries the changes of one step; every member mirrors a reference
+ * mutator (counts of 0 / NULL arrays = nothing to do):
+ *   kf_*      new keyframes [kf_first, kf_first + kf_count)   KeyFrame ctor + Map::AddKeyFrame (src/Map.cc:32-38):
+ *             pose rows [Rcw|tcw] (12), fx fy cx cy, mnMinX mnMaxX mnMinY mnMaxY, and mvKeysUn as [kp_stride][2] rows
+ *             (include/KeyFrame.h:157,164,185-188).  Ids are the caller's dense indices; re-sending an id overwrites it.
+ *   pose      KeyFrame::SetPose (src/KeyFrame.cc:70-86; bundle adjustment, loop closing): pose_kf [n_pose] ids (NULL =
+ *             keyframes 0..n_pose-1), pose [n_pose*12]
+ *   xyz       MapPoint ctor / MapPoint::SetWorldPos (src/MapPoint.cc:73-78): xyz_id [n_xyz] (NULL = points 0..n_xyz-1)
+ *   erase     MapPoint::EraseObservation(pKF) (src/MapPoint.cc:111-141): removes the observation of point erase_pt[i] in
+ *             keyframe erase_kf[i] (no-op when absent, as :116); the rest of the list keeps its order
+ *   bad       MapPoint::SetBadFlag (src/MapPoint.cc:151-168, called for moving points at Tracking.cc:1952): the point
+ *             loses all observations
+ *   add       MapPoint::AddObservation(pKF, idx) (src/MapPoint.cc:98-109): appends (add_kf[i], add_fid[i]) to point
+ *             add_pt[i] unless the point already has an observation in that keyframe (:101-102); the observed keypoint mvKeysUn[idx].pt is looked up in the resident keyframe once, here
+ * Applied in exactly this order.  Within ONE delta a point may appear at most once in erase_* and at most once in add_*
+ * (one keyframe inserts / culls at most one observation per point; split anything else over several deltas) -- a
+ * repetition is detected on the device and reported as LCCRF_ERR_ARG by the call that synchronises.  Observation order
+ * = insertion order (the reference iterates a std::map<KeyFrame*, size_t>, i.e. pointer order, which no restatement can
+ * reproduce); a map filled through lccrf_map_set_observations / deltas gives bit-identical results to the same lists
+ * passed to lccrf_frames_set_map_inputs. */
+typedef struct lccrf_map lccrf_map;
+typedef struct lccrf_map_delta {
+    int kf_first, kf_count;
+    const float *kf_pose, *kf_intr, *kf_bounds, *kf_keypoints;
+    int n_pose;
+    const int *pose_kf;
+    const float *pose;
+    int n_xyz;
+    const int *xyz_id;
+    const float *xyz;
+    int n_erase;
+    const int *erase_pt, *erase_kf;
+    int n_bad;
+    const int *bad_pt;
+    int n_add;
+    const int *add_pt, *add_kf, *add_fid;
+} lccrf_map_delta;
+/* kp_stride: keypoint slots per keyframe (the ORB extractor's feature budget, ORBextractor.nFeatures) */
+int lccrf_map_create(lccrf_ctx *ctx, int kp_stride, lccrf_map **out);
+void lccrf_map_destroy(lccrf_map *map);
+/* apply one delta; synchronises, so the host arrays may be reused on return */
+int lccrf_map_apply(lccrf_map *map, const lccrf_map_delta *delta);
+/* bulk load (a map read from disk, a replay start): replaces the observation lists of points [pt_first, pt_first+count)
+ * by the CSR obs_ptr [count+1] / obs_ref [nnz][2] = {keyframe, feature index}; lists keep CSR order.  The keyframes must
+ * exist.  Synchronises. */
+int lccrf_map_set_observations(lccrf_map *map, int pt_first, int count, const int *obs_ptr, const int *obs_ref);
+/* room for `entries` more observations (the pool also grows on its own, by doubling, ahead of demand) */
+int lccrf_map_reserve_observations(lccrf_map *map, long long entries);
+/* keyframes, map points (highest id + 1), live observations, pool entries in use (incl. abandoned runs), pool capacity */
+int lccrf_map_sizes(lccrf_map *map, int *n_kf, int *n_points, long long *n_obs, long long *pool_used, long long *pool_cap);
+/* read back the observation lists of n points in the lccrf_frames_set_map_inputs layout (tests, snapshot files):
+ * obs_ptr [n+1]; obs_kf / obs_uv hold up to `cap` observations (LCCRF_ERR_ARG when more are needed; obs_ptr[n] tells).
+ * xyz [n*3] optional.  Synchronises. */
+int lccrf_map_export(lccrf_map *map, int n, const int *point_id, int *obs_ptr, int *obs_kf, float *obs_uv, long long cap,
+                     float *xyz);
+
+/* Frame batch against the resident map: problem b's points are the map points point_id[prob_ptr[b] .. prob_ptr[b+1])
+ * (mCurrentFrame.mvpMapPoints[i] of the matched features, Tracking.cc:1849-1870; every one needs >= 1 observation,
+ * :1858), kp2d [NT*2] their keypoints in the frame.  `delta` (optional) is applied first.  kf_ptr as in
+ * lccrf_frames_set_map_inputs.  set_visible uploads on the context's stream (follow with lccrf_frames_run);
+ * submit_visible is the pipelined form (slot 0 / 1, uploads on the copy stream, results into map_out / prob_out, finish
+ * with lccrf_frames_wait): host arrays, including the delta's, must stay valid until that wait returns. */
+int lccrf_frames_set_visible(lccrf_frames *fr, lccrf_map *map, const lccrf_map_delta *delta, const int *point_id,
+                             const float *kp2d, const int *kf_ptr);
+int lccrf_frames_submit_visible(lccrf_frames *fr, int slot, lccrf_map *map, const lccrf_map_delta *delta,
+                                const int *point_id, const float *kp2d, const int *kf_ptr, short *map_out, float *prob_out);
+/* Epipolar prior of the next run / submission of `slot` (RroughClassify's second branch, Tracking.cc:2001-2010):
+ * p4 [NT] = mvFeatureMatchProb[fid] of every point (0.0 without a match, :2003); has_prior [B] (optional) = 0 for the
+ * problems whose frame had no fundamental matrix (mvFeatureMatchProb.empty(), :1994) -- those take the first branch.
+ * p4 == NULL clears the prior.  The arrays are read when the slot's inputs are uploaded (same lifetime rule). */
+int lccrf_frames_set_prior(lccrf_frames *fr, int slot, const double *p4, const unsigned char *has_prior);
+/* Label-application lists of a pipelined submission: registers host buffers that lccrf_frames_submit_* fills for `slot`
+ * (lccrf_frames_partition semantics; dyn_list / stat_list [NT] each, dyn_ptr / stat_ptr [B+1], fid [NT] optional);
+ * valid after lccrf_frames_wait(slot).  All NULL unregisters. */
+int lccrf_frames_set_partition_outputs(lccrf_frames *fr, int slot, const int *fid, int *dyn_ptr, int *dyn_list, int *stat_ptr,
+                                       int *stat_list);
+
 /* ---------------------------------------------------------------- snapshot / replay files - */
 /* CRF-input snapshot format (host-only, no device needed).  A file holds, frame after frame, the flat
  * restatement of what Tracking::DynamicDetectionWithCRF gathers (src/Tracking.cc:1849-1870) and what

@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -113,6 +114,17 @@ SYMBOLS = {
     "lccrf_frames_get_debug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_frames_debug_counters": (C.c_int, [_vp, C.c_int, _vp]),
     "lccrf_frames_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lccrf_map_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "lccrf_map_destroy": (None, [_vp]),
+    "lccrf_map_apply": (C.c_int, [_vp, _vp]),
+    "lccrf_map_set_observations": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "lccrf_map_reserve_observations": (C.c_int, [_vp, C.c_longlong]),
+    "lccrf_map_sizes": (C.c_int, [_vp, _ip, _ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "lccrf_map_export": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
+    "lccrf_frames_set_visible": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_submit_visible": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lccrf_frames_set_prior": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "lccrf_frames_set_partition_outputs": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_snapshot_writer_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_vp)]),
     "lccrf_snapshot_write_frame": (C.c_int, [_vp, C.c_longlong, C.c_double, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lccrf_snapshot_writer_close": (C.c_int, [_vp]),
@@ -179,6 +191,7 @@ class Context:
         self._check(self.lib.lccrf_ctx_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()  # handles created from this context: closed before the context goes
         if stream is not None:
             self._check(self.lib.lccrf_ctx_set_stream(self.h, _vp(stream)))
 
@@ -188,6 +201,11 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(getattr(self, "_children", ())):
+                try:
+                    child.close()
+                except Exception:
+                    pass
             self.lib.lccrf_ctx_destroy(self.h)
             self.h = None
 
@@ -291,6 +309,7 @@ class Lattice:
         h = _vp()
         ctx._check(ctx.lib.lccrf_lattice_create(ctx.h, _ptr(f), self.d, self.N, C.byref(h)))
         self.h = h
+        ctx._children.add(self)
         v = C.c_int()
         ctx._check(ctx.lib.lccrf_lattice_sizes(self.h, None, None, C.byref(v)))
         self.V = v.value
@@ -330,6 +349,7 @@ class DenseCRF:
         h = _vp()
         ctx._check(ctx.lib.lccrf_crf_create(ctx.h, N, L, C.byref(h)))
         self.h = h
+        ctx._children.add(self)
 
     def setUnaryEnergy(self, unary):
         u = _arr(unary, np.float32)
@@ -407,6 +427,121 @@ class DenseCRF:
             pass
 
 
+class MapDelta(C.Structure):
+    """lccrf_map_delta: the map changes of one step (include/lccrf.h).  Build with MapDelta.make(...): the numpy arrays
+    are converted once and kept alive by the object; nothing is copied per use."""
+    _fields_ = [("kf_first", C.c_int), ("kf_count", C.c_int), ("kf_pose", _vp), ("kf_intr", _vp), ("kf_bounds", _vp),
+                ("kf_keypoints", _vp), ("n_pose", C.c_int), ("pose_kf", _vp), ("pose", _vp), ("n_xyz", C.c_int),
+                ("xyz_id", _vp), ("xyz", _vp), ("n_erase", C.c_int), ("erase_pt", _vp), ("erase_kf", _vp),
+                ("n_bad", C.c_int), ("bad_pt", _vp), ("n_add", C.c_int), ("add_pt", _vp), ("add_kf", _vp), ("add_fid", _vp)]
+
+    @classmethod
+    def make(cls, kf_first=0, kf_pose=None, kf_intr=None, kf_bounds=None, kf_keypoints=None, pose_kf=None, pose=None,
+             xyz_id=None, xyz=None, erase_pt=None, erase_kf=None, bad_pt=None, add_pt=None, add_kf=None, add_fid=None,
+             pin=None) -> "MapDelta":
+        """pin: optional callable array -> page-locked copy (bench.py passes a torch pin_memory wrapper)"""
+        d = cls()
+        keep = []
+
+        def f32(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            a = pin(a) if pin else a
+            keep.append(a)
+            return a
+
+        def i32(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            a = pin(a) if pin else a
+            keep.append(a)
+            return a
+
+        kf_pose, kf_intr, kf_bounds, kf_keypoints, pose, xyz = (f32(a) for a in (kf_pose, kf_intr, kf_bounds, kf_keypoints, pose, xyz))
+        pose_kf, xyz_id, erase_pt, erase_kf, bad_pt, add_pt, add_kf, add_fid = (
+            i32(a) for a in (pose_kf, xyz_id, erase_pt, erase_kf, bad_pt, add_pt, add_kf, add_fid))
+        d.kf_first = int(kf_first)
+        d.kf_count = 0 if kf_pose is None else int(kf_pose.size // 12)
+        d.kf_pose, d.kf_intr, d.kf_bounds, d.kf_keypoints = _ptr(kf_pose), _ptr(kf_intr), _ptr(kf_bounds), _ptr(kf_keypoints)
+        d.n_pose = 0 if pose is None else int(pose.size // 12)
+        d.pose_kf, d.pose = _ptr(pose_kf), _ptr(pose)
+        d.n_xyz = 0 if xyz is None else int(xyz.size // 3)
+        d.xyz_id, d.xyz = _ptr(xyz_id), _ptr(xyz)
+        d.n_erase = 0 if erase_pt is None else int(erase_pt.size)
+        d.erase_pt, d.erase_kf = _ptr(erase_pt), _ptr(erase_kf)
+        d.n_bad = 0 if bad_pt is None else int(bad_pt.size)
+        d.bad_pt = _ptr(bad_pt)
+        d.n_add = 0 if add_pt is None else int(add_pt.size)
+        d.add_pt, d.add_kf, d.add_fid = _ptr(add_pt), _ptr(add_kf), _ptr(add_fid)
+        if pose_kf is not None and pose_kf.size != d.n_pose or xyz_id is not None and xyz_id.size != d.n_xyz:
+            raise LccrfError("MapDelta: id arrays must match their value arrays")
+        if d.n_erase and (erase_kf is None or erase_kf.size != d.n_erase):
+            raise LccrfError("MapDelta: erase_pt / erase_kf sizes differ")
+        if d.n_add and (add_kf is None or add_fid is None or add_kf.size != d.n_add or add_fid.size != d.n_add):
+            raise LccrfError("MapDelta: add_pt / add_kf / add_fid sizes differ")
+        d._keep = keep
+        return d
+
+    @property
+    def nbytes(self) -> int:
+        """bytes this delta moves host -> device"""
+        return int(sum(a.nbytes for a in self._keep))
+
+
+class Map:
+    """lccrf_map: the device-resident SLAM map (keyframes, map points, observation lists)."""
+
+    def __init__(self, ctx: Context, kp_stride: int):
+        self.ctx, self.kp_stride = ctx, int(kp_stride)
+        h = _vp()
+        ctx._check(ctx.lib.lccrf_map_create(ctx.h, self.kp_stride, C.byref(h)))
+        self.h = h
+        ctx._children.add(self)
+
+    def apply(self, delta: MapDelta = None, **kw):
+        d = delta if delta is not None else MapDelta.make(**kw)
+        self.ctx._check(self.ctx.lib.lccrf_map_apply(self.h, C.byref(d)))
+
+    def set_observations(self, obs_ptr, obs_ref, pt_first=0):
+        obs_ptr = _arr(obs_ptr, np.int32)
+        obs_ref = _arr(obs_ref, np.int32)
+        assert obs_ref.ndim == 2 and obs_ref.shape[1] == 2
+        self.ctx._check(self.ctx.lib.lccrf_map_set_observations(self.h, int(pt_first), int(obs_ptr.size - 1), _ptr(obs_ptr), _ptr(obs_ref)))
+
+    def reserve_observations(self, entries: int):
+        self.ctx._check(self.ctx.lib.lccrf_map_reserve_observations(self.h, int(entries)))
+
+    def sizes(self) -> dict:
+        nk, npnt = C.c_int(), C.c_int()
+        no, pu, pc = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self.ctx._check(self.ctx.lib.lccrf_map_sizes(self.h, C.byref(nk), C.byref(npnt), C.byref(no), C.byref(pu), C.byref(pc)))
+        return dict(n_kf=nk.value, n_points=npnt.value, n_obs=no.value, pool_used=pu.value, pool_cap=pc.value)
+
+    def export(self, point_id):
+        """observation lists of the given points in the set_map_inputs layout: (obs_ptr, obs_kf, obs_uv, xyz)"""
+        ids = _arr(point_id, np.int32)
+        n = int(ids.size)
+        ptr = np.zeros(n + 1, np.int32)
+        self.ctx._check(self.ctx.lib.lccrf_map_export(self.h, n, _ptr(ids), _ptr(ptr), None, None, 0, None))
+        nnz = int(ptr[-1])
+        kf, uv, xyz = np.empty(nnz, np.int32), np.empty((nnz, 2), np.float32), np.empty((n, 3), np.float32)
+        self.ctx._check(self.ctx.lib.lccrf_map_export(self.h, n, _ptr(ids), _ptr(ptr), _ptr(kf), _ptr(uv), nnz, _ptr(xyz)))
+        return ptr, kf, uv, xyz
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lccrf_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Frames:
     """lccrf_frames: B independent per-frame CRF problems (Tracking.cc:1871-1930) in one launch sequence."""
 
@@ -422,6 +557,7 @@ class Frames:
         h = _vp()
         ctx._check(ctx.lib.lccrf_frames_create(ctx.h, self.B, _ptr(self.prob_ptr), C.byref(self.prm), _ptr(self.energies), C.byref(h)))
         self.h = h
+        ctx._children.add(self)
 
     def set_inputs(self, observs, error, depth, kp2d):
         a = [_arr(x, np.float32) for x in (observs, error, depth, kp2d)]
@@ -486,6 +622,44 @@ class Frames:
 
     def wait(self, slot):
         self.ctx._check(self.ctx.lib.lccrf_frames_wait(self.h, slot))
+
+    def set_visible(self, mp: "Map", point_id, kp2d, delta: MapDelta = None, kf_ptr=None):
+        """frame points = ids of the resident map's points (+ optional delta applied first); follow with run()"""
+        ids, kp, kfp = _arr(point_id, np.int32), _arr(kp2d, np.float32), _arr(kf_ptr, np.int32)
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_visible(self.h, mp.h, C.byref(delta) if delta is not None else None,
+                                                            _ptr(ids), _ptr(kp), _ptr(kfp)))
+
+    def submit_visible(self, slot, mp: "Map", point_id, kp2d, map_out, prob_out, delta: MapDelta = None, kf_ptr=None):
+        """pipelined step against the resident map through HOST buffers (no conversion here: pass contiguous int32 /
+        float32 arrays, ideally pinned; they and the delta must stay alive until wait(slot))"""
+        assert point_id.dtype == np.int32 and kp2d.dtype == np.float32 and (kf_ptr is None or kf_ptr.dtype == np.int32)
+        self._vis_keep = getattr(self, "_vis_keep", {})
+        self._vis_keep[slot] = (point_id, kp2d, delta, kf_ptr)
+        self.ctx._check(self.ctx.lib.lccrf_frames_submit_visible(
+            self.h, slot, mp.h, C.byref(delta) if delta is not None else None, _ptr(point_id), _ptr(kp2d), _ptr(kf_ptr),
+            _ptr(map_out), _ptr(prob_out)))
+
+    def set_prior(self, slot, p4=None, has_prior=None):
+        """epipolar prior p4 [NT] float64 (+ per-problem flags [B] uint8) of the next run / submission of `slot`"""
+        p4 = _arr(p4, np.float64)
+        hp = _arr(has_prior, np.uint8)
+        self._prior_keep = getattr(self, "_prior_keep", {})
+        self._prior_keep[slot] = (p4, hp)
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_prior(self.h, slot, _ptr(p4), _ptr(hp)))
+
+    def set_partition_outputs(self, slot, fid=None, enable=True):
+        """label-application lists delivered by submit_*(slot); returns the dict of host arrays they land in"""
+        self._part_keep = getattr(self, "_part_keep", {})
+        if not enable:
+            self._part_keep.pop(slot, None)
+            self.ctx._check(self.ctx.lib.lccrf_frames_set_partition_outputs(self.h, slot, None, None, None, None, None))
+            return None
+        out = dict(fid=_arr(fid, np.int32), dyn_ptr=np.zeros(self.B + 1, np.int32), dyn=np.zeros(max(self.NT, 1), np.int32),
+                   stat_ptr=np.zeros(self.B + 1, np.int32), stat=np.zeros(max(self.NT, 1), np.int32))
+        self._part_keep[slot] = out
+        self.ctx._check(self.ctx.lib.lccrf_frames_set_partition_outputs(
+            self.h, slot, _ptr(out["fid"]), _ptr(out["dyn_ptr"]), _ptr(out["dyn"]), _ptr(out["stat_ptr"]), _ptr(out["stat"])))
+        return out
 
     def partition(self, fid=None):
         """Label application (Tracking.cc:1945-1955): per-problem lists of moving / static points in point order.

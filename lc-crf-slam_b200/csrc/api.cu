@@ -92,12 +92,23 @@ static void scratch_release(Ctx *ctx, Ctx::Scratch &s, bool pinned) {
     s.bytes = 0;
 }
 
+// device status word -> error code (bits: 1 lattice key range, 2 index out of range, 4 visible point without
+// observations, 8 a point twice in one delta list, 16 observation pool exhausted)
+static int decode_status(int st) {
+    if (st & 1) return fail(LCCRF_ERR_RANGE, "lattice key outside the reference's short range (permutohedral_cpu.h:373)");
+    if (st & 2) return fail(LCCRF_ERR_ARG, "an observation, keyframe, feature or point index is outside its table");
+    if (st & 4) return fail(LCCRF_ERR_ARG, "a visible map point has no observations (Tracking.cc:1858 drops such points before the CRF)");
+    if (st & 8) return fail(LCCRF_ERR_ARG, "a point appears twice in one list of a map delta (split it over several deltas)");
+    if (st & 16) return fail(LCCRF_ERR_STATE, "observation pool exhausted: call lccrf_map_reserve_observations and repeat the step");
+    return LCCRF_OK;
+}
+
 static int check_status(Ctx *ctx) {  // synchronises
     LCCRF_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (*ctx->h_status & 1) {
+    if (*ctx->h_status) {
         cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
-        return fail(LCCRF_ERR_RANGE, "lattice key outside the reference's short range (permutohedral_cpu.h:373)");
+        return decode_status(*ctx->h_status);
     }
     return LCCRF_OK;
 }
@@ -173,6 +184,10 @@ struct lccrf_crf {
     float *d_energies = nullptr;  // n_en[L], p_en[L]
 };
 
+struct lccrf_map {
+    DevMap *m = nullptr;
+};
+
 // one set of device-resident inputs of a frames batch.  Two sets exist so that lccrf_frames_submit_* can upload
 // step i+1 on the copy stream while step i computes (the graph of a slot reads that slot's buffers).
 struct FrameInputs {
@@ -194,6 +209,25 @@ struct FrameInputs {
     float cam8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long nnz = 0, nnz_cap = 0;
     bool indexed = false;  // obs_kf holds {keyframe, feature index} pairs; keypoints come from lccrf_frames::kp_tab
+    // frame points named by ids of a device-resident map (lccrf_frames_set_visible / submit_visible)
+    bool visible = false;
+    DevMap *map = nullptr;
+    int *vis = nullptr;       // [NT] map point ids
+    uint64_t map_gen = 0;
+    int kf_bucket = 0;        // shared-memory keyframe slots the captured graph was sized for
+    void *stage = nullptr;    // staged arrays of this step's map delta
+    size_t stage_cap = 0;
+    DeltaDev delta;
+    bool has_delta = false;
+    // epipolar prior (lccrf_frames_set_prior): host arrays as registered, device copies
+    const double *h_p4 = nullptr;
+    const unsigned char *h_p4_has = nullptr;
+    double *p4 = nullptr;
+    unsigned char *p4_has = nullptr;
+    bool use_p4 = false, use_p4_has = false;
+    // label-application lists delivered by the pipelined submissions (lccrf_frames_set_partition_outputs)
+    const int *part_fid = nullptr;
+    int *part_dyn_ptr = nullptr, *part_dyn = nullptr, *part_stat_ptr = nullptr, *part_stat = nullptr;
     bool have_inputs = false;
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_launches = 0, graph_gen = 0, kp_gen = 0;
@@ -982,6 +1016,10 @@ static void frame_inputs_release(Ctx *ctx, FrameInputs &in) {
     dev_free(ctx, in.obs_kf);
     dev_free(ctx, in.kf_packed);
     dev_free(ctx, in.kf_ptr);
+    dev_free(ctx, in.vis);
+    dev_free(ctx, in.p4);
+    dev_free(ctx, in.p4_has);
+    if (in.stage) cudaFree(in.stage);
     if (in.up_done) cudaEventDestroy(in.up_done);
     if (in.run_done) cudaEventDestroy(in.run_done);
     if (in.out_done) cudaEventDestroy(in.out_done);
@@ -1020,6 +1058,27 @@ static int order_copies_after_alloc(Ctx *ctx, FrameInputs &in, cudaStream_t st) 
     return LCCRF_OK;
 }
 
+// epipolar prior registered with lccrf_frames_set_prior: uploaded with the slot's other inputs
+static int frames_upload_prior(lccrf_frames *fr, FrameInputs &in, cudaStream_t st) {
+    Ctx *ctx = fr->ctx;
+    const bool use = in.h_p4 != nullptr && fr->b.NT > 0, use_has = use && in.h_p4_has != nullptr;
+    if (use != in.use_p4 || use_has != in.use_p4_has) frame_inputs_drop_graph(in);  // the classifier's arguments change
+    in.use_p4 = use;
+    in.use_p4_has = use_has;
+    if (!use) return LCCRF_OK;
+    bool fresh = false;
+    if (!in.p4) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.p4, (size_t)fr->b.NT * sizeof(double)));
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.p4_has, (size_t)fr->b.B));
+        frame_inputs_drop_graph(in);
+        fresh = true;
+    }
+    if (fresh) LCCRF_TRY(order_copies_after_alloc(ctx, in, st));
+    LCCRF_CUDA(cudaMemcpyAsync(in.p4, in.h_p4, (size_t)fr->b.NT * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (use_has) LCCRF_CUDA(cudaMemcpyAsync(in.p4_has, in.h_p4_has, (size_t)fr->b.B, cudaMemcpyHostToDevice, st));
+    return LCCRF_OK;
+}
+
 static int frames_upload_direct(lccrf_frames *fr, FrameInputs &in, cudaStream_t st, const float *observs,
                                 const float *error, const float *depth, const float *kp2d) {
     Ctx *ctx = fr->ctx;
@@ -1042,6 +1101,8 @@ static int frames_upload_direct(lccrf_frames *fr, FrameInputs &in, cudaStream_t 
     if (fresh) LCCRF_TRY(order_copies_after_alloc(ctx, in, st));
     if (in.from_map) frame_inputs_drop_graph(in);
     in.from_map = false;
+    in.visible = false;
+    LCCRF_TRY(frames_upload_prior(fr, in, st));
     if (n) {
         LCCRF_CUDA(cudaMemcpyAsync(in.observs, observs, n * 4, cudaMemcpyHostToDevice, st));
         LCCRF_CUDA(cudaMemcpyAsync(in.error, error, n * 4, cudaMemcpyHostToDevice, st));
@@ -1133,7 +1194,8 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
         LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_ptr, (size_t)(fr->b.B + 1) * 4));
         regraph = true;
     }
-    if (in.nKF != nKF || in.nnz != nnz || !in.from_map || in.have_kf_ptr != (kf_ptr != nullptr)) regraph = true;
+    if (in.nKF != nKF || in.nnz != nnz || !in.from_map || in.visible || in.have_kf_ptr != (kf_ptr != nullptr)) regraph = true;
+    in.visible = false;
     if (regraph) {
         frame_inputs_drop_graph(in);
         LCCRF_TRY(order_copies_after_alloc(ctx, in, st));  // every (re)allocation above sets regraph
@@ -1142,6 +1204,7 @@ static int frames_upload_map(lccrf_frames *fr, FrameInputs &in, cudaStream_t st,
     in.nnz = nnz;
     in.obs_kf_bytes = obs_kf_bytes;
     in.have_kf_ptr = kf_ptr != nullptr;
+    LCCRF_TRY(frames_upload_prior(fr, in, st));
     if (kf_ptr) LCCRF_CUDA(cudaMemcpyAsync(in.kf_ptr, kf_ptr, (size_t)(fr->b.B + 1) * 4, cudaMemcpyHostToDevice, st));
     if (NT > 0) {
         LCCRF_CUDA(cudaMemcpyAsync(in.xyz, xyz, (size_t)NT * 12, cudaMemcpyHostToDevice, st));
@@ -1192,7 +1255,16 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
         LCCRF_TRY(potts_norm(ctx, b, b.lat[1]));
     }
     const float *observs = in.observs, *error = in.error, *depth = in.depth;
-    if (in.from_map) {
+    if (in.visible) {
+        DevMap *m = in.map;
+        LCCRF_TRY(unary_map_points_visible(ctx, NT, in.vis, m->pt_xyz, m->pt_start, m->pt_cnt, m->pool_kf, m->pool_uv,
+                                           m->kf_packed, in.kf_bucket, m->d_nkf, fr->observs, fr->error, fr->depth, b.prob_ptr,
+                                           in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max,
+                                           in.ucam ? in.cam8 : nullptr));
+        observs = fr->observs;
+        error = fr->error;
+        depth = fr->depth;
+    } else if (in.from_map) {
         LCCRF_TRY(unary_pack_kf(ctx, in.kf_packed, in.kf_pose, in.kf_intr, in.kf_bounds, in.nKF));
         LCCRF_TRY(unary_map_points_packed(ctx, NT, in.nKF, in.xyz, in.obs_ptr, in.obs_kf, in.obs_kf_bytes, in.obs_uv,
                                           in.kf_packed, fr->observs, fr->error, fr->depth, b.prob_ptr,
@@ -1203,7 +1275,8 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
         depth = fr->depth;
     }
     // RroughClassify -> setUnaryEnergyFromLabel   (Tracking.cc:1871,1921)
-    LCCRF_TRY(unary_classify(ctx, NT, observs, error, depth, nullptr, prm, fr->label));
+    LCCRF_TRY(unary_classify(ctx, NT, observs, error, depth, in.use_p4 ? in.p4 : nullptr, prm, fr->label,
+                             in.use_p4_has ? in.p4_has : nullptr, b.prob_ptr, b.B));
     LCCRF_TRY(mf_unary_from_label(ctx, b.unary, fr->label, NT, 2, fr->energies[0], fr->d_en, fr->d_en + 2));
     // appearanceKernel(N, w1, vobservs, verrors, mObservStdev, mRpjErrorStdev)   (Tracking.cc:1923)
     LCCRF_TRY(feat_div2(ctx, fr->feat, observs, 1, prm.stdev_beta, error, 1, prm.stdev_alpha, NT));
@@ -1221,6 +1294,12 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
 static int frames_run_slot(lccrf_frames *fr, FrameInputs &in) {
     Ctx *ctx = fr->ctx;
     if (!in.have_inputs) return fail(LCCRF_ERR_STATE, "frames_run before set_inputs");
+    if (in.has_delta) {  // this step's map changes: plain launches in front of the (captured) frame sequence
+        in.has_delta = false;
+        LCCRF_TRY(map_apply_dev(in.map, in.delta, nullptr));
+    }
+    if (in.visible && in.graph && in.map_gen != in.map->gen) frame_inputs_drop_graph(in);  // a map array moved
+    if (in.visible) in.map_gen = in.map->gen;
     if (!ctx->opt_graphs || ctx->opt_profile) {
         LCCRF_TRY(frames_enqueue(fr, in));
         fr->ran = true;
@@ -1271,6 +1350,10 @@ int lccrf_frames_run(lccrf_frames *fr) {
 int lccrf_frames_get_outputs(lccrf_frames *fr, short *map, float *prob) {
     if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
     if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_get_outputs before frames_run");
+    for (int s_ = 0; s_ < 2; s_++)
+        if (fr->in[s_].in_flight)
+            return fail(LCCRF_ERR_STATE, "a pipelined submission is in flight: its results go to the buffers given to "
+                                         "lccrf_frames_submit_* / lccrf_frames_set_partition_outputs; wait for both slots first");
     Ctx *ctx = fr->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)fr->b.NT;
@@ -1316,6 +1399,23 @@ static int frames_submit_epilogue(lccrf_frames *fr, int slot, FrameInputs &in, s
     const size_t n = (size_t)fr->b.NT;
     if (n && map_out) LCCRF_CUDA(cudaMemcpyAsync(map_out, fr->b.map, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
     if (n && prob_out) LCCRF_CUDA(cudaMemcpyAsync(prob_out, fr->b.cur, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (in.part_dyn_ptr || in.part_dyn || in.part_stat_ptr || in.part_stat) {
+        // label application of THIS submission (Tracking.cc:1945-1955), before the other slot's run reuses the labels
+        const int NT = fr->b.NT, B = fr->b.B;
+        const size_t nB = (size_t)(B + 1), nT = (size_t)(NT > 0 ? NT : 1);
+        if (!fr->part)
+            LCCRF_TRY(dev_alloc(ctx, (void **)&fr->part, (2 * nB + 3 * nT) * sizeof(int) + label_partition_scratch_bytes(NT)));
+        int *d_dyn_ptr = fr->part, *d_stat_ptr = d_dyn_ptr + nB, *d_dyn = d_stat_ptr + nB, *d_stat = d_dyn + nT,
+            *d_fid = d_stat + nT, *d_scratch = d_fid + nT;
+        cudaStream_t st = ctx->stream;
+        if (in.part_fid && NT) LCCRF_CUDA(cudaMemcpyAsync(d_fid, in.part_fid, (size_t)NT * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_TRY(label_partition(ctx, fr->b.map, NT, fr->b.prob_ptr, B, in.part_fid ? d_fid : nullptr, d_scratch, d_dyn_ptr,
+                                  d_dyn, d_stat_ptr, d_stat));
+        if (in.part_dyn_ptr) LCCRF_CUDA(cudaMemcpyAsync(in.part_dyn_ptr, d_dyn_ptr, nB * 4, cudaMemcpyDeviceToHost, st));
+        if (in.part_stat_ptr) LCCRF_CUDA(cudaMemcpyAsync(in.part_stat_ptr, d_stat_ptr, nB * 4, cudaMemcpyDeviceToHost, st));
+        if (in.part_dyn && NT) LCCRF_CUDA(cudaMemcpyAsync(in.part_dyn, d_dyn, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
+        if (in.part_stat && NT) LCCRF_CUDA(cudaMemcpyAsync(in.part_stat, d_stat, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
+    }
     LCCRF_CUDA(cudaMemcpyAsync(in.h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LCCRF_CUDA(cudaEventRecord(in.out_done, ctx->stream));
     in.in_flight = true;
@@ -1405,9 +1505,9 @@ int lccrf_frames_wait(lccrf_frames *fr, int slot) {
     LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
     LCCRF_CUDA(cudaEventSynchronize(in.out_done));
     in.in_flight = false;
-    if (*in.h_status & 1) {
+    if (*in.h_status) {
         cudaMemsetAsync(fr->ctx->d_status, 0, sizeof(int), fr->ctx->stream);
-        return fail(LCCRF_ERR_RANGE, "lattice key outside the reference's short range (permutohedral_cpu.h:373)");
+        return decode_status(*in.h_status);
     }
     return LCCRF_OK;
 }
@@ -1415,6 +1515,10 @@ int lccrf_frames_wait(lccrf_frames *fr, int slot) {
 int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, float *error, float *depth, int *V) {
     if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
     if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_get_debug before frames_run");
+    for (int s_ = 0; s_ < 2; s_++)
+        if (fr->in[s_].in_flight)
+            return fail(LCCRF_ERR_STATE, "a pipelined submission is in flight: its results go to the buffers given to "
+                                         "lccrf_frames_submit_* / lccrf_frames_set_partition_outputs; wait for both slots first");
     Ctx *ctx = fr->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)fr->b.NT;
@@ -1444,6 +1548,10 @@ int lccrf_frames_get_debug(lccrf_frames *fr, short *init_label, float *observs, 
 int lccrf_frames_partition(lccrf_frames *fr, const int *fid, int *dyn_ptr, int *dyn_list, int *stat_ptr, int *stat_list) {
     if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
     if (!fr->ran) return fail(LCCRF_ERR_STATE, "frames_partition before frames_run");
+    for (int s_ = 0; s_ < 2; s_++)
+        if (fr->in[s_].in_flight)
+            return fail(LCCRF_ERR_STATE, "a pipelined submission is in flight: its results go to the buffers given to "
+                                         "lccrf_frames_submit_* / lccrf_frames_set_partition_outputs; wait for both slots first");
     Ctx *ctx = fr->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
     const int NT = fr->b.NT, B = fr->b.B;
@@ -1500,10 +1608,401 @@ int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_
     }
     double u = 0;
     const FrameInputs &in = fr->in[fr->last_slot];
-    if (in.from_map) u = (double)in.nnz * 12 + (double)fr->b.NT * 24 + (double)in.nKF * 80;
+    long long nnz = in.nnz;
+    if (in.visible && fr->b.NT > 0) {  // observations of the visible points: counted on the device
+        Ctx *ctx = fr->ctx;
+        int *d_cnt = nullptr;
+        LCCRF_TRY(dev_alloc(ctx, (void **)&d_cnt, (size_t)fr->b.NT * 4));
+        int rc = map_export_dev(in.map, fr->b.NT, in.vis, d_cnt);
+        std::vector<int> cnt((size_t)fr->b.NT);
+        if (rc == LCCRF_OK) {
+            cudaError_t e = cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+        }
+        dev_free(ctx, d_cnt);
+        LCCRF_TRY(rc);
+        nnz = 0;
+        for (int c : cnt) nnz += c;
+    }
+    if (in.from_map) u = (double)nnz * 12 + (double)fr->b.NT * 24 + (double)in.nKF * 80;
     if (total) *total = tot + u;
     if (per_iteration) *per_iteration = it_tot;
     if (unary) *unary = u;
+    return LCCRF_OK;
+}
+
+// ------------------------------------------------------------------ device-resident map
+int lccrf_map_create(lccrf_ctx *h, int kp_stride, lccrf_map **out) {
+    if (!h || !out) return fail(LCCRF_ERR_ARG, "NULL argument");
+    if (kp_stride < 1 || kp_stride > (1 << 20)) return fail(LCCRF_ERR_ARG, "kp_stride must be in [1, 2^20]");
+    *out = nullptr;
+    Ctx *ctx = &h->c;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    auto *mp = new lccrf_map();
+    int rc = map_create(ctx, kp_stride, &mp->m);
+    if (rc != LCCRF_OK) {
+        delete mp;
+        return rc;
+    }
+    *out = mp;
+    return LCCRF_OK;
+}
+
+void lccrf_map_destroy(lccrf_map *map) {
+    if (!map) return;
+    if (map->m) {
+        cudaSetDevice(map->m->ctx->device);
+        map_destroy(map->m);
+    }
+    delete map;
+}
+
+// bytes of the staged arrays of a delta (every array 256-byte aligned); with_keypoints = false when the new keyframes'
+// keypoints are copied straight from the host array
+static size_t delta_stage_bytes(const lccrf_map_delta &d, int kp_stride, bool with_keypoints) {
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    size_t n = 0;
+    n += al((size_t)d.kf_count * 48) + al((size_t)d.kf_count * 16) * 2;
+    if (with_keypoints && d.kf_keypoints) n += al((size_t)d.kf_count * kp_stride * 8);
+    n += al((size_t)d.n_pose * 4) + al((size_t)d.n_pose * 48);
+    n += al((size_t)d.n_xyz * 4) + al((size_t)d.n_xyz * 12);
+    n += al((size_t)d.n_erase * 4) * 2 + al((size_t)d.n_bad * 4) + al((size_t)d.n_add * 4) * 3;
+    return n + 256;
+}
+
+// copy the delta's host arrays to `base` on stream st and describe them in `out`
+static int delta_stage(const lccrf_map_delta &d, int kp_stride, bool with_keypoints, char *base, cudaStream_t st, DeltaDev *out) {
+    size_t off = 0;
+    cudaError_t err = cudaSuccess;
+    auto put = [&](const void *src, size_t bytes) -> const void * {
+        if (!src || bytes == 0) return nullptr;
+        char *dst = base + off;
+        off += (bytes + 255) / 256 * 256;
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) err = e;
+        return dst;
+    };
+    DeltaDev o;
+    o.kf_first = d.kf_first;
+    o.kf_count = d.kf_count;
+    o.kf_pose = (const float *)put(d.kf_pose, (size_t)d.kf_count * 48);
+    o.kf_intr = (const float *)put(d.kf_intr, (size_t)d.kf_count * 16);
+    o.kf_bounds = (const float *)put(d.kf_bounds, (size_t)d.kf_count * 16);
+    if (with_keypoints) o.kf_keypoints = (const float *)put(d.kf_keypoints, (size_t)d.kf_count * kp_stride * 8);
+    o.n_pose = d.n_pose;
+    o.pose_kf = (const int *)put(d.pose_kf, (size_t)d.n_pose * 4);
+    o.pose = (const float *)put(d.pose, (size_t)d.n_pose * 48);
+    o.n_xyz = d.n_xyz;
+    o.xyz_id = (const int *)put(d.xyz_id, (size_t)d.n_xyz * 4);
+    o.xyz = (const float *)put(d.xyz, (size_t)d.n_xyz * 12);
+    o.n_erase = d.n_erase;
+    o.erase_pt = (const int *)put(d.erase_pt, (size_t)d.n_erase * 4);
+    o.erase_kf = (const int *)put(d.erase_kf, (size_t)d.n_erase * 4);
+    o.n_bad = d.n_bad;
+    o.bad_pt = (const int *)put(d.bad_pt, (size_t)d.n_bad * 4);
+    o.n_add = d.n_add;
+    o.add_pt = (const int *)put(d.add_pt, (size_t)d.n_add * 4);
+    o.add_kf = (const int *)put(d.add_kf, (size_t)d.n_add * 4);
+    o.add_fid = (const int *)put(d.add_fid, (size_t)d.n_add * 4);
+    if (err != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("map delta upload: ") + cudaGetErrorString(err));
+    *out = o;
+    return LCCRF_OK;
+}
+
+// explicit point ids name points the caller creates densely: raise the capacity to the largest id of the delta
+static int delta_grow_points(DevMap *m, const lccrf_map_delta &d) {
+    if (d.n_xyz > 0 && d.xyz_id) {
+        int mx = -1;
+        for (int i = 0; i < d.n_xyz; i++) {
+            if (d.xyz_id[i] < 0) return fail(LCCRF_ERR_ARG, "map delta: negative point id");
+            if (d.xyz_id[i] > mx) mx = d.xyz_id[i];
+        }
+        LCCRF_TRY(map_reserve_points(m, mx + 1));
+        if (mx + 1 > m->n_pt) m->n_pt = mx + 1;
+    }
+    return LCCRF_OK;
+}
+
+int lccrf_map_apply(lccrf_map *map, const lccrf_map_delta *delta) {
+    if (!map || !map->m || !delta) return fail(LCCRF_ERR_ARG, "NULL argument");
+    DevMap *m = map->m;
+    Ctx *ctx = m->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    LCCRF_TRY(map_prepare(m, *delta));
+    LCCRF_TRY(delta_grow_points(m, *delta));
+    void *stage = nullptr;
+    LCCRF_TRY(dev_alloc(ctx, &stage, delta_stage_bytes(*delta, m->kp_stride, false)));
+    DeltaDev dd;
+    int rc = delta_stage(*delta, m->kp_stride, false, (char *)stage, ctx->stream, &dd);
+    if (rc == LCCRF_OK) rc = map_apply_dev(m, dd, delta->kf_count > 0 ? delta->kf_keypoints : nullptr);
+    dev_free(ctx, stage);
+    if (rc != LCCRF_OK) return rc;
+    return check_status(ctx);  // synchronises: the host arrays are free on return
+}
+
+int lccrf_map_set_observations(lccrf_map *map, int pt_first, int count, const int *obs_ptr, const int *obs_ref) {
+    if (!map || !map->m) return fail(LCCRF_ERR_ARG, "map is NULL");
+    if (pt_first < 0 || count < 0) return fail(LCCRF_ERR_ARG, "negative point range");
+    if (count == 0) return LCCRF_OK;
+    if (!obs_ptr) return fail(LCCRF_ERR_ARG, "obs_ptr is NULL");
+    DevMap *m = map->m;
+    Ctx *ctx = m->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    if (obs_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "obs_ptr must start at 0");
+    const long long nnz = obs_ptr[count];
+    if (nnz > 0 && !obs_ref) return fail(LCCRF_ERR_ARG, "obs_ref is NULL");
+    // runs with 25% room to spare (at least 2 entries): the first appends do not move the list
+    std::vector<int> ptrs(2 * (size_t)count + 2);
+    long long run = 0;
+    for (int i = 0; i < count; i++) {
+        const int c = obs_ptr[i + 1] - obs_ptr[i];
+        if (c < 0) return fail(LCCRF_ERR_ARG, "obs_ptr must be non-decreasing");
+        ptrs[i] = obs_ptr[i];
+        ptrs[count + 1 + i] = (int)run;
+        const int extra = (c + 3) / 4;
+        run += c + (extra < 2 ? 2 : extra);
+        if (run > 0x7fffffffLL) return fail(LCCRF_ERR_ARG, "bulk load exceeds 2^31 pool entries");
+    }
+    ptrs[count] = (int)nnz;
+    ptrs[2 * (size_t)count + 1] = (int)run;
+    if ((long long)pt_first + count > 0x7fffffffLL) return fail(LCCRF_ERR_ARG, "point id overflow");
+    LCCRF_TRY(map_reserve_points(m, pt_first + count));
+    if (pt_first + count > m->n_pt) m->n_pt = pt_first + count;
+    LCCRF_TRY(map_bulk_reserve(m, run));
+    int *d_ptrs = nullptr, *d_ref = nullptr;
+    LCCRF_TRY(dev_alloc(ctx, (void **)&d_ptrs, ptrs.size() * 4));
+    int rc = dev_alloc(ctx, (void **)&d_ref, (size_t)(nnz > 0 ? nnz : 1) * 8);
+    if (rc == LCCRF_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_ptrs, ptrs.data(), ptrs.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_ref, obs_ref, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc == LCCRF_OK) rc = map_bulk_observations(m, pt_first, count, d_ptrs, d_ref, nnz, 25);
+    dev_free(ctx, d_ptrs);
+    dev_free(ctx, d_ref);
+    if (rc != LCCRF_OK) return rc;
+    rc = check_status(ctx);  // synchronises
+    map_counters(m, nullptr, nullptr);
+    return rc;
+}
+
+int lccrf_map_reserve_observations(lccrf_map *map, long long entries) {
+    if (!map || !map->m) return fail(LCCRF_ERR_ARG, "map is NULL");
+    if (entries < 0) return fail(LCCRF_ERR_ARG, "negative size");
+    DevMap *m = map->m;
+    LCCRF_CUDA(cudaSetDevice(m->ctx->device));
+    long long tail = 0;
+    LCCRF_TRY(map_counters(m, &tail, nullptr));
+    return map_reserve_pool(m, tail + entries);
+}
+
+int lccrf_map_sizes(lccrf_map *map, int *n_kf, int *n_points, long long *n_obs, long long *pool_used, long long *pool_cap) {
+    if (!map || !map->m) return fail(LCCRF_ERR_ARG, "map is NULL");
+    DevMap *m = map->m;
+    LCCRF_CUDA(cudaSetDevice(m->ctx->device));
+    long long tail = 0, live = 0;
+    LCCRF_TRY(map_counters(m, &tail, &live));
+    if (n_kf) *n_kf = m->n_kf;
+    if (n_points) *n_points = m->n_pt;
+    if (n_obs) *n_obs = live;
+    if (pool_used) *pool_used = tail;
+    if (pool_cap) *pool_cap = m->pool_cap;
+    return LCCRF_OK;
+}
+
+int lccrf_map_export(lccrf_map *map, int n, const int *point_id, int *obs_ptr, int *obs_kf, float *obs_uv, long long cap,
+                     float *xyz) {
+    if (!map || !map->m) return fail(LCCRF_ERR_ARG, "map is NULL");
+    if (n < 0 || cap < 0) return fail(LCCRF_ERR_ARG, "negative size");
+    if (n == 0) return LCCRF_OK;
+    if (!point_id || !obs_ptr) return fail(LCCRF_ERR_ARG, "NULL argument");
+    DevMap *m = map->m;
+    Ctx *ctx = m->ctx;
+    LCCRF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int *d_ids = nullptr, *d_ptr = nullptr;
+    LCCRF_TRY(dev_alloc(ctx, (void **)&d_ids, (size_t)n * 4));
+    int rc = dev_alloc(ctx, (void **)&d_ptr, ((size_t)n + 1) * 4);
+    std::vector<int> cnt((size_t)n + 1);
+    if (rc == LCCRF_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_ids, point_id, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc == LCCRF_OK) rc = map_export_dev(m, n, d_ids, d_ptr);
+    if (rc == LCCRF_OK) {
+        cudaError_t e = cudaMemcpyAsync(cnt.data(), d_ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    long long tot = 0;
+    if (rc == LCCRF_OK) {
+        for (int i = 0; i < n; i++) {
+            obs_ptr[i] = (int)tot;
+            tot += cnt[i];
+        }
+        obs_ptr[n] = (int)tot;
+        if (tot > cap && (obs_kf || obs_uv)) rc = fail(LCCRF_ERR_ARG, "lccrf_map_export: output capacity too small (obs_ptr[n] tells the need)");
+    }
+    int *d_kf = nullptr;
+    float *d_uv = nullptr, *d_xyz = nullptr;
+    if (rc == LCCRF_OK && (obs_kf || obs_uv || xyz)) {
+        const size_t ne = (size_t)(tot > 0 ? tot : 1);
+        rc = dev_alloc(ctx, (void **)&d_kf, ne * 4);
+        if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&d_uv, ne * 8);
+        if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&d_xyz, (size_t)n * 12);
+        if (rc == LCCRF_OK) {
+            cudaError_t e = cudaMemcpyAsync(d_ptr, obs_ptr, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+        }
+        if (rc == LCCRF_OK) rc = map_export_entries_dev(m, n, d_ids, d_ptr, d_kf, d_uv, d_xyz, tot);
+        if (rc == LCCRF_OK) {
+            cudaError_t e = cudaSuccess;
+            if (obs_kf && tot) e = cudaMemcpyAsync(obs_kf, d_kf, (size_t)tot * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && obs_uv && tot) e = cudaMemcpyAsync(obs_uv, d_uv, (size_t)tot * 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && xyz) e = cudaMemcpyAsync(xyz, d_xyz, (size_t)n * 12, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(LCCRF_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    dev_free(ctx, d_ids);
+    dev_free(ctx, d_ptr);
+    dev_free(ctx, d_kf);
+    dev_free(ctx, d_uv);
+    dev_free(ctx, d_xyz);
+    if (rc != LCCRF_OK) return rc;
+    return check_status(ctx);
+}
+
+// ---- frame batches against the resident map ----
+static int frames_upload_visible(lccrf_frames *fr, FrameInputs &in, cudaStream_t st, lccrf_map *map, const lccrf_map_delta *delta,
+                                 const int *point_id, const float *kp2d, const int *kf_ptr) {
+    Ctx *ctx = fr->ctx;
+    if (!map || !map->m) return fail(LCCRF_ERR_ARG, "map is NULL");
+    DevMap *m = map->m;
+    if (m->ctx != ctx) return fail(LCCRF_ERR_ARG, "map and frames belong to different contexts");
+    const int NT = fr->b.NT, B = fr->b.B;
+    if (NT > 0 && (!point_id || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
+    const bool pipelined = st != ctx->stream;
+    bool regraph = false, fresh = false;
+    if (delta) {
+        // host-side bookkeeping + capacity growth (stream-ordered on the context's stream, before the delta's kernels)
+        LCCRF_TRY(map_prepare(m, *delta));
+        LCCRF_TRY(delta_grow_points(m, *delta));
+        const size_t need = delta_stage_bytes(*delta, m->kp_stride, true);
+        if (need > in.stage_cap) {
+            // rare (first steps): cudaFree waits for the device, so nothing still reads the old block
+            if (in.stage) LCCRF_CUDA(cudaFree(in.stage));
+            in.stage = nullptr;
+            in.stage_cap = 0;
+            const size_t cap = need + need / 2;
+            LCCRF_CUDA(cudaMalloc(&in.stage, cap));
+            in.stage_cap = cap;
+        }
+    }
+    if (m->n_kf <= 0 && NT > 0) return fail(LCCRF_ERR_STATE, "the map has no keyframes");
+    int slice_max = 0;
+    if (kf_ptr) {
+        if (kf_ptr[0] != 0 || kf_ptr[B] != m->n_kf) return fail(LCCRF_ERR_ARG, "kf_ptr must span [0, number of keyframes]");
+        for (int i = 0; i < B; i++) {
+            if (kf_ptr[i + 1] < kf_ptr[i]) return fail(LCCRF_ERR_ARG, "kf_ptr must be non-decreasing");
+            if (kf_ptr[i + 1] - kf_ptr[i] > slice_max) slice_max = kf_ptr[i + 1] - kf_ptr[i];
+        }
+    }
+    if (slice_max != in.kf_slice_max) regraph = true;
+    in.kf_slice_max = slice_max;
+    {   // camera model and shared-memory keyframe slots are kernel parameters of the captured graph
+        const bool ucam = m->cam_set && m->ucam;
+        if (ucam != in.ucam || (ucam && memcmp(m->cam8, in.cam8, sizeof(in.cam8)) != 0)) regraph = true;
+        in.ucam = ucam;
+        memcpy(in.cam8, m->cam8, sizeof(in.cam8));
+        int bucket = (m->n_kf + 127) / 128 * 128;
+        if (bucket != in.kf_bucket) regraph = true;
+        in.kf_bucket = bucket;
+    }
+    if (!in.vis) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.vis, (size_t)(NT ? NT : 1) * 4));
+        regraph = fresh = true;
+    }
+    if (!in.kp2d) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kp2d, (size_t)(NT ? NT : 1) * 8));
+        regraph = fresh = true;
+    }
+    if (kf_ptr && !in.kf_ptr) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.kf_ptr, (size_t)(B + 1) * 4));
+        regraph = fresh = true;
+    }
+    if (!in.visible || in.map != m || in.have_kf_ptr != (kf_ptr != nullptr)) regraph = true;
+    if (regraph) frame_inputs_drop_graph(in);
+    if (fresh) LCCRF_TRY(order_copies_after_alloc(ctx, in, st));
+    in.visible = true;
+    in.from_map = true;
+    in.indexed = false;
+    in.map = m;
+    in.have_kf_ptr = kf_ptr != nullptr;
+    in.nKF = m->n_kf;
+    in.nnz = -1;
+    LCCRF_TRY(frames_upload_prior(fr, in, st));
+    in.has_delta = false;
+    if (delta) {
+        if (pipelined) {
+            LCCRF_TRY(delta_stage(*delta, m->kp_stride, true, (char *)in.stage, st, &in.delta));
+            in.has_delta = true;  // applied on the context's stream once the upload has landed (frames_run_slot)
+        } else {
+            DeltaDev dd;
+            LCCRF_TRY(delta_stage(*delta, m->kp_stride, false, (char *)in.stage, st, &dd));
+            LCCRF_TRY(map_apply_dev(m, dd, delta->kf_count > 0 ? delta->kf_keypoints : nullptr));
+        }
+    }
+    if (kf_ptr) LCCRF_CUDA(cudaMemcpyAsync(in.kf_ptr, kf_ptr, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (NT > 0) {
+        LCCRF_CUDA(cudaMemcpyAsync(in.vis, point_id, (size_t)NT * 4, cudaMemcpyHostToDevice, st));
+        LCCRF_CUDA(cudaMemcpyAsync(in.kp2d, kp2d, (size_t)NT * 8, cudaMemcpyHostToDevice, st));
+    }
+    in.have_inputs = true;
+    return LCCRF_OK;
+}
+
+int lccrf_frames_set_visible(lccrf_frames *fr, lccrf_map *map, const lccrf_map_delta *delta, const int *point_id,
+                             const float *kp2d, const int *kf_ptr) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    LCCRF_CUDA(cudaSetDevice(fr->ctx->device));
+    for (int s_ = 0; s_ < 2; s_++)
+        if (fr->in[s_].in_flight) return fail(LCCRF_ERR_STATE, "a submission is in flight: call lccrf_frames_wait first");
+    LCCRF_TRY(frames_upload_visible(fr, fr->in[0], fr->ctx->stream, map, delta, point_id, kp2d, kf_ptr));
+    // the host arrays (delta included) are free on return
+    LCCRF_CUDA(cudaStreamSynchronize(fr->ctx->stream));
+    return LCCRF_OK;
+}
+
+int lccrf_frames_submit_visible(lccrf_frames *fr, int slot, lccrf_map *map, const lccrf_map_delta *delta, const int *point_id,
+                                const float *kp2d, const int *kf_ptr, short *map_out, float *prob_out) {
+    FrameInputs *in = nullptr;
+    LCCRF_TRY(frames_submit_prologue(fr, slot, &in));
+    LCCRF_TRY(frames_upload_visible(fr, *in, fr->ctx->copy_stream, map, delta, point_id, kp2d, kf_ptr));
+    return frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
+}
+
+int lccrf_frames_set_prior(lccrf_frames *fr, int slot, const double *p4, const unsigned char *has_prior) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (slot < 0 || slot > 1) return fail(LCCRF_ERR_ARG, "slot must be 0 or 1");
+    if (!p4 && has_prior) return fail(LCCRF_ERR_ARG, "has_prior without p4");
+    fr->in[slot].h_p4 = p4;
+    fr->in[slot].h_p4_has = has_prior;
+    return LCCRF_OK;
+}
+
+int lccrf_frames_set_partition_outputs(lccrf_frames *fr, int slot, const int *fid, int *dyn_ptr, int *dyn_list, int *stat_ptr,
+                                       int *stat_list) {
+    if (!fr) return fail(LCCRF_ERR_ARG, "frames is NULL");
+    if (slot < 0 || slot > 1) return fail(LCCRF_ERR_ARG, "slot must be 0 or 1");
+    FrameInputs &in = fr->in[slot];
+    if (in.in_flight) return fail(LCCRF_ERR_STATE, "slot still in flight: call lccrf_frames_wait first");
+    in.part_fid = fid;
+    in.part_dyn_ptr = dyn_ptr;
+    in.part_dyn = dyn_list;
+    in.part_stat_ptr = stat_ptr;
+    in.part_stat = stat_list;
     return LCCRF_OK;
 }
 

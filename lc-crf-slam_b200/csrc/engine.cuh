@@ -181,6 +181,79 @@ inline int ensure_dyn_smem(Ctx *ctx, Kernel *kernel, int bytes) {
 int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero = false);
 void dev_free(Ctx *ctx, void *p);
 
+// ------------------------------------------------------------------ device-resident map (map.cu)
+struct KfPack {  // one keyframe as the unary kernel reads it: rows of [Rcw|tcw], intrinsics, image bounds
+    float4 r0, r1, r2, intr, bnd;
+};
+
+// The state Tracking::ComputeMapPointErrAndObserv dereferences (src/Tracking.cc:1803-1839), kept in HBM across frames:
+// keyframes (pose, intrinsics, bounds, undistorted keypoints) and map points (world position + observation list).
+// Observation lists live in one pool: point p owns pool entries [pt_start[p], pt_start[p] + pt_cnt[p]) out of a
+// reserved run of pt_room[p]; a list that outgrows its run moves to the pool's tail with twice the room.
+struct DevMap {
+    Ctx *ctx = nullptr;
+    int kp_stride = 0;
+    // keyframes
+    int kf_cap = 0, n_kf = 0;
+    KfPack *kf_packed = nullptr;  // [kf_cap]
+    float *kp_tab = nullptr;      // [kf_cap][kp_stride] float2   KeyFrame::mvKeysUn
+    int *d_nkf = nullptr;         // device copy of n_kf (read by captured graphs)
+    bool cam_set = false, ucam = true;
+    float cam8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // map points
+    int pt_cap = 0, n_pt = 0;
+    float *pt_xyz = nullptr;      // [pt_cap*3]   MapPoint::mWorldPos
+    int *pt_start = nullptr, *pt_cnt = nullptr, *pt_room = nullptr, *pt_stamp = nullptr;  // [pt_cap]
+    // observation pool
+    long long pool_cap = 0;
+    int *pool_kf = nullptr;       // [pool_cap] keyframe index
+    float *pool_uv = nullptr;     // [pool_cap] float2: the observed keypoint, resolved when the observation is added
+    int *d_ctr = nullptr;         // device counters: [0] pool tail, [1] pool capacity, [2] live entries, [3] scratch
+    int *h_ctr = nullptr;         // pinned snapshot of d_ctr
+    cudaEvent_t ctr_ev = nullptr;
+    bool ctr_pending = false;
+    long long tail_seen = 0;      // last snapshot of the pool tail
+    long long tail_unseen = 0;    // entries bulk loads added behind that snapshot (known exactly on the host)
+    int epoch = 0;
+    uint64_t gen = 0;             // bumped whenever a device array moves (captured graphs hold raw pointers)
+};
+
+// a lccrf_map_delta whose arrays are in device memory
+struct DeltaDev {
+    int kf_first = 0, kf_count = 0;
+    const float *kf_pose = nullptr, *kf_intr = nullptr, *kf_bounds = nullptr, *kf_keypoints = nullptr;
+    int n_pose = 0;
+    const int *pose_kf = nullptr;
+    const float *pose = nullptr;
+    int n_xyz = 0;
+    const int *xyz_id = nullptr;
+    const float *xyz = nullptr;
+    int n_erase = 0;
+    const int *erase_pt = nullptr, *erase_kf = nullptr;
+    int n_bad = 0;
+    const int *bad_pt = nullptr;
+    int n_add = 0;
+    const int *add_pt = nullptr, *add_kf = nullptr, *add_fid = nullptr;
+};
+
+int map_create(Ctx *ctx, int kp_stride, DevMap **out);
+void map_destroy(DevMap *m);
+// host-side bookkeeping of a delta before its kernels run: capacity growth (stream-ordered on ctx->stream), camera
+// uniformity, keyframe / point counts.  Host arrays are only inspected where the header says so (kf_intr / kf_bounds).
+int map_prepare(DevMap *m, const lccrf_map_delta &h);
+// enqueue the kernels that apply a staged delta on ctx->stream (order: keyframes, poses, positions, erase, bad, add);
+// kp_host != nullptr: the new keyframes' keypoints are copied straight from that host array (synchronous API)
+int map_apply_dev(DevMap *m, const DeltaDev &d, const float *kp_host);
+int map_bulk_observations(DevMap *m, int pt_first, int count, const int *obs_ptr_dev, const int *obs_ref_dev, long long nnz,
+                          int slack_percent);
+int map_reserve_pool(DevMap *m, long long entries);
+int map_reserve_points(DevMap *m, int n);
+int map_bulk_reserve(DevMap *m, long long need);
+int map_export_dev(DevMap *m, int n, const int *ids_dev, int *cnt_dev);
+int map_export_entries_dev(DevMap *m, int n, const int *ids_dev, const int *ptr_dev, int *kf_dev, float *uv_dev, float *xyz_dev,
+                           long long cap);
+int map_counters(DevMap *m, long long *tail, long long *live);  // synchronises
+
 // ------------------------------------------------------------------ stages (each enqueues kernels on ctx->stream)
 // lattice build: features [NT*d] on device -> offset/bary/nbr/vbase (lattice_build.cu)
 int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, LatticeSet **out);
@@ -222,6 +295,10 @@ int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const in
                             int obs_kf_bytes, const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
                             const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max, const float *cam8,
                             const float *kp_tab, int kp_stride);
+int unary_map_points_visible(Ctx *ctx, int N, const int *vis, const float *pt_xyz, const int *pt_start, const int *pt_cnt,
+                             const int *pool_kf, const float *pool_uv, const void *kf_packed, int n_kf_bucket,
+                             const int *nkf_dev, float *observs, float *error, float *depth, const int *prob_ptr,
+                             const int *kf_ptr, int B, int kf_slice_max, const float *cam8);
 // kp_tab != nullptr: indexed observations -- obs_kf holds {keyframe, feature index} pairs (uint16 pairs when
 // obs_kf_bytes == 2, int32 pairs when 4), obs_uv is unused and the observed keypoint is kp_tab[kf*kp_stride + fid]
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,
@@ -230,8 +307,10 @@ int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, cons
 // cam8 (host, 8 floats {fx fy cx cy, minx maxx miny maxy}) when every keyframe has the same intrinsics and image
 // bounds, else nullptr; uniform_camera() decides from the host tables
 bool uniform_camera(const float *kf_intr, const float *kf_bounds, int nKF, float *cam8);
+// has_prior (optional, [B] bytes): problems whose flag is 0 take the no-prior branch (Tracking.cc:1994-1999)
 int unary_classify(Ctx *ctx, int N, const float *observs, const float *error, const float *depth,
-                   const double *p4, const lccrf_slam_params &prm, short *label);
+                   const double *p4, const lccrf_slam_params &prm, short *label, const unsigned char *has_prior = nullptr,
+                   const int *prob_ptr = nullptr, int B = 0);
 
 // label application (apply.cu): stable partition of MAP labels into moving / static lists; all device pointers
 size_t label_partition_scratch_bytes(int NT);
