@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lccrf", choices=["lccrf", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c2"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c2", "c5"])
     ap.add_argument("--batch", type=int, default=0, help="problems per step per GPU (0 = workload default)")
     ap.add_argument("--splat", default="tree", choices=["tree", "ordered"],
                     help="tree: fixed-shape tree reduction per lattice vertex (marginals within the 1e-4 gate); "
@@ -63,7 +63,11 @@ WORKLOADS = {
     "c1": ("C1: per-frame CRF, N=3000 points, L=2, K=2 (d=2,2), T=5 (reference's own CPU-runnable case)", 1, 3000, 0),
     "c4": ("C4: 1024 independent per-frame CRFs of N~U[4000,6000] points in one launch sequence", 1024, 5000, 0),
     "c2": ("C2: full-image DenseCRF 640x480, L=2, Gaussian (sigma 3) + 5-D bilateral (sigma 60 / 20), T=10", 4, 640 * 480, 0),
+    "c5": ("C5: 8 synthetic sequences (4 TUM-walking-shaped + 4 Bonn-shaped) replayed as batches of 64 frame CRFs (N~U[4000,6000]) "
+           "against a device-resident map with keyframe insertion / culling / bad points / BA updates per batch; sequences "
+           "round-robin over the GPUs, no collective", 64, 5000, 0),
 }
+C5_SEQUENCES = 8
 C2 = dict(W=640, H=480, conf=0.7, w_g=3.0, sd_g=3.0, w_b=10.0, sd_b=60.0, sd_rgb=20.0, iters=10)  # example_cpu.cpp:86-98
 
 
@@ -75,20 +79,53 @@ SPLAT_MODES = {
 KP_STRIDE = 32768  # keypoint slots per keyframe of the resident table (C3: ~24k observations per keyframe)
 
 
-def make_problems(workload: str, batch: int, seed0: int):
+def workload_config(workload: str, batch: int, splat: str) -> dict:
+    """The `config` object of the JSON line: a pure function of the command line, so that both arms (--impl lccrf and
+    --impl reference) print the SAME object; what a run measured or sampled goes into `run_info` / `cpu_baseline`."""
+    desc, dbatch, n, _ = WORKLOADS[workload]
+    batch = batch or dbatch
+    l2 = {
+        "c3": "inputs larger than L2 (about 3 GB read per step vs 126 MB L2), nothing flushed",
+        "c4": "inputs larger than L2 (about 2 GB of lattice / entry streams per step at 1024 problems), nothing flushed",
+        "c1": "working set of a few MB fits the 126 MB L2 and is NOT flushed between steps: cache-resident latency figure, "
+              "not a headline configuration",
+        "c2": "per-image working set (~60 MB of lattice arrays) fits the 126 MB L2 and is NOT flushed: every step builds its "
+              "lattices from fresh host inputs, so nothing is reused across steps",
+        "c5": "every step brings new host inputs and a changed map; per-sequence working sets (~60 MB) are NOT flushed between "
+              "the sequences of a step",
+    }[workload]
+    cfg = {"workload": desc, "l2_policy": l2, "splat_mode": SPLAT_MODES[splat]}
+    if workload == "c5":
+        cfg.update({"sequences": C5_SEQUENCES, "frames_per_batch": batch, "problems_per_step": C5_SEQUENCES * batch,
+                    "sharding": "sequences round-robin over ranks (lc-crf-slam_b200/shard.py), no collective; strong scaling"})
+    elif workload == "c4":
+        cfg.update({"problems_per_step": batch,
+                    "sharding": "ONE job of independent problems cut into contiguous ranges of balanced size over the ranks "
+                                "(lc-crf-slam_b200/shard.py), no collective; strong scaling"})
+    else:
+        cfg.update({"problems_per_step_per_gpu": batch, "points_per_step_per_gpu": batch * n,
+                    "sharding": "independent problems per rank, no collective; weak scaling"})
+    if workload == "c2":
+        cfg["timing"] = "value: CUDA events on the launching stream; e2e: host clock around the same calls"
+    return cfg
+
+
+def make_problems(workload: str, batch: int, seed0: int, shard=None):
     """Seeded synthetic problems.  Returns a list of MapSnapshot (c3) or SlamFrame (c1/c4)."""
     synth = importlib.import_module("lc-crf-slam_b200.synth")
     _, _, n, obs = WORKLOADS[workload]
     if workload == "c3":  # seeded per problem, so the pool only changes the wall time of the set-up
         with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-            return list(ex.map(lambda i: synth.map_snapshot(n, obs, seed=seed0 + i), range(batch)))
+            return list(ex.map(lambda i: synth.map_snapshot(n, obs, seed=seed0 + i, unique_kf=True), range(batch)))
     if workload == "c1":
         return [synth.slam_frame(n, seed=seed0 + i) for i in range(batch)]
     if workload == "c2":  # (uint8 RGB image [W*H,3], labels [W*H] with 70% unknown)
         return [synth.image_problem(C2["W"], C2["H"], seed0 + i) for i in range(batch)]
     rng = np.random.default_rng(seed0)
     sizes = rng.integers(4000, 6001, batch)
-    return [synth.slam_frame(int(s), seed=seed0 + 1 + i, dyn_frac=float(rng.uniform(0.15, 0.3))) for i, s in enumerate(sizes)]
+    dyn = rng.uniform(0.15, 0.3, batch)
+    lo, hi = shard if shard is not None else (0, batch)
+    return [synth.slam_frame(int(sizes[i]), seed=seed0 + 1 + i, dyn_frac=float(dyn[i])) for i in range(lo, hi)]
 
 
 def concat_snapshots(snaps):
@@ -183,7 +220,7 @@ def cpu_problem_runner(workload):
     def run(p):
         if workload == "c2":
             return run_image(p)
-        if workload == "c3":
+        if workload in ("c3", "c5"):
             ob, er, de = o.map_point_unary(p)
             kp = p.kp2d
         else:
@@ -219,8 +256,18 @@ def run_reference_arm(args):
     desc, dbatch, n, obs = WORKLOADS[args.workload]
     # bounded sample: two problems per host thread per step (c3: ~0.1 s of CPU work per problem), so that a step keeps
     # every core busy and the pool start-up is amortised
-    per_step = 2 * cores if args.workload != "c4" else 8 * cores
-    base = make_problems(args.workload, min(per_step, 4), seed0=1000)
+    per_step = 2 * cores if args.workload not in ("c4", "c5") else 8 * cores
+    if args.workload == "c5":   # frames of the first two sequences after two replayed batches
+        base = []
+        for s_ in (0, C5_SEQUENCES - 1):
+            gen = replay_sequence(s_, dbatch)
+            gen.initial_map()
+            for _ in range(2):
+                b_ = gen.next_batch()
+            pf = np.concatenate([[0], np.cumsum(gen.sizes)])
+            base += [gen.snapshot(b_["ids"][pf[j]:pf[j + 1]], b_["kp2d"][pf[j]:pf[j + 1]]) for j in range(4)]
+    else:
+        base = make_problems(args.workload, min(per_step, 4), seed0=1000)
     problems = [base[i % len(base)] for i in range(per_step)]
     run, kind = cpu_problem_runner(args.workload)
     with ThreadPoolExecutor(max_workers=cores) as ex:
@@ -238,7 +285,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "problems_per_step": per_step},
+        "config": workload_config(args.workload, args.batch, args.splat),
+        "run_info": {"problems_per_step_reference_arm": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -271,6 +319,65 @@ def algorithmic_kernel_bytes(name, N_tot, V_tot, nnz, nKF, kf_bytes=4, T=5, L=2,
         "k_csr_count": E * 4,
         "k_exp_normalize": 2 * N_tot * L * 4,
     }.get(name)
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_kernels(ctx, F, NT, nnz, nKF, iters, peak, peak_src, nprof=3):
+    """Per-kernel CUDA events (option "profile") over nprof runs of F -> (roofline of the dominant kernel / kernel group,
+    kernel shares, mean launch ms).  Algorithmic bytes: algorithmic_kernel_bytes (SURVEY 8d figures x units per launch)."""
+    ctx.set_option("profile", 1)
+    ctx.profile_report()
+    for _ in range(nprof):
+        F.run()
+    rep = ctx.profile_report()
+    ctx.set_option("profile", 0)
+    grp = {}
+    for k, (cnt, tms) in rep.items():  # fold kernel groups
+        g = next((gn for gn, members in KERNEL_GROUPS.items() if k in members), k)
+        c0, t0_ = grp.get(g, (0, 0.0))
+        first = g == k or k == KERNEL_GROUPS[g][0]
+        grp[g] = (c0 + (cnt if first else 0), t0_ + tms)
+    tot = sum(v[1] for v in grp.values()) or 1.0
+    shares = {k: round(v[1] / tot, 4) for k, v in sorted(grp.items(), key=lambda kv: -kv[1][1])}
+    kernel_ms = {k: round(v[1] / max(v[0], 1), 5) for k, v in grp.items()}
+    for k, (cnt, tms) in rep.items():  # members of a group also one by one
+        if k not in kernel_ms:
+            kernel_ms[k] = round(tms / max(cnt, 1), 5)
+    dbg = F.get_debug()
+    Vtot = float(dbg["V"].sum()) / 2.0  # mean over the two lattice sets
+    kf_bytes = 4  # the observation streams hold int32 keyframe indices next to the float2 keypoints
+    rl_all = {}
+    for k, (cnt, tms) in grp.items():
+        ab = algorithmic_kernel_bytes(k, NT, Vtot, nnz, nKF, kf_bytes, T=iters)
+        if ab is not None and cnt:
+            rl_all[k] = round(ab / (tms / cnt * 1e-3) / 1e9, 1)
+    top = next(iter(shares))
+    cnt, tms = grp[top]
+    ab = algorithmic_kernel_bytes(top, NT, Vtot, nnz, nKF, kf_bytes, T=iters)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the last ncu --set full capture
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        members_t = KERNEL_GROUPS.get(top, (top,))
+        vals = [tj.get(m) for m in members_t if tj.get(m) is not None] if top not in tj else [tj[top]]
+        if vals and tj.get("_captured_points_per_step") == NT:  # only a capture of exactly this step counts
+            traffic, traffic_src = float(sum(vals)), tj.get("_source")
+    members = KERNEL_GROUPS.get(top, (top,))
+    roofline = {"kernel": "+".join(members), "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "share_of_step": shares[top],
+                "achieved_gbs_all_kernels": rl_all,
+                "note": "per-kernel CUDA events on the launching stream, concurrency and graphs off while profiling"}
+    if ab is not None:
+        per_launch_ms = tms / cnt
+        ach = ab / (per_launch_ms * 1e-3) / 1e9
+        roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": per_launch_ms})
+    return roofline, shares, kernel_ms
 
 
 def blur_measurements(pkg, ctx, peak):
@@ -432,11 +539,7 @@ def run_gpu_arm_image(args):
         "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "problems_per_step_per_gpu": batch, "points_per_step_per_gpu": batch * N,
-                   "l2_policy": "per-image working set (~60 MB of lattice arrays) fits the 126 MB L2 and is NOT flushed: every step "
-                                "builds its lattices from fresh host inputs, so nothing is reused across steps",
-                   "sharding": "independent images per rank, no collective",
-                   "timing": "value: CUDA events on the launching stream; e2e: host clock around the same calls"},
+        "config": workload_config("c2", args.batch, args.splat),
         "clocks": clocks,
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
                 "ms_per_step": ms_e2e / args.steps, "inputs": "labels (int16) + RGB image (uint8) per image, pageable host arrays"},
@@ -449,9 +552,205 @@ def run_gpu_arm_image(args):
         dist.destroy_process_group()
 
 
+def replay_sequence(s: int, FB: int):
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    return synth.SequenceReplay(seed=5000 + s, kind="tum" if s < C5_SEQUENCES // 2 else "bonn", frames_per_batch=FB)
+
+
+def run_gpu_arm_replay(args):
+    """C5 (BASELINE configs[4]): sequences replayed against device-resident maps, sharded round-robin over the ranks.
+    A step = one batch of FB frame CRFs of EVERY sequence (strong scaling: the job is the 8 sequences).  Per step and
+    sequence the host sends the frames' visible point ids + keypoints and one map delta (new keyframes with their
+    keypoint rows and observations, culled observations, bad points, all poses, all positions).
+      e2e    the pipelined loop (lccrf_frames_submit_visible / wait), host clock vs CUDA events, whichever is longer
+      value  the same frame batches against the final map with their inputs uploaded before the timed region"""
+    import torch
+    pkg = importlib.import_module("lc-crf-slam_b200")
+    shard_mod = importlib.import_module("lc-crf-slam_b200.shard")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    desc, dbatch, _, _ = WORKLOADS["c5"]
+    FB = args.batch or dbatch
+    W, K = max(args.warmup, 3), args.steps
+    stream = torch.cuda.Stream()
+    ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
+    ctx.set_option("ordered_splat", 1 if args.splat == "ordered" else 0)
+    prm = pkg.SlamParams.make()
+    keep = []
+
+    def keep_pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+
+    def build(s):
+        gen = replay_sequence(s, FB)
+        kfs, xyz, ptr, ref = gen.initial_map()
+        steps = []
+        for _ in range(W + K):
+            b = gen.next_batch()
+            steps.append((b["ids"], b["kp2d"], b["delta"]))
+        return gen, kfs, xyz, ptr, ref, steps
+
+    local = shard_mod.shard_round_robin(C5_SEQUENCES, world, rank)
+    with ThreadPoolExecutor(max_workers=min(len(local) or 1, os.cpu_count() or 1)) as ex:
+        built = list(ex.map(build, local))
+    S = []
+    for s, (gen, kfs, xyz, ptr, ref, steps) in zip(local, built):
+        mp = pkg.Map(ctx, gen.stride)
+        mp.apply(kf_pose=kfs["pose"], kf_intr=kfs["intr"], kf_bounds=kfs["bounds"], kf_keypoints=kfs["kp"], xyz=xyz)
+        mp.set_observations(ptr, ref)
+        F = pkg.Frames(ctx, gen.sizes, prm)
+        NTs = int(sum(gen.sizes))
+        pin_steps = [(keep_pinned(i), keep_pinned(k), pkg.MapDelta.make(pin=keep_pinned, **d)) for i, k, d in steps]
+        outs = [(keep_pinned(np.zeros(NTs, np.int16)), keep_pinned(np.zeros((NTs, 2), np.float32))) for _ in (0, 1)]
+        S.append(dict(seq=s, gen=gen, mp=mp, F=F, steps=pin_steps, outs=outs, NT=NTs))
+    del built
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(i0, i1):
+        for i in range(i0, i1):
+            for st in S:
+                ids, kp, delta = st["steps"][i]
+                st["F"].wait(i & 1)
+                st["F"].submit_visible(i & 1, st["mp"], ids, kp, st["outs"][i & 1][0], st["outs"][i & 1][1], delta=delta)
+        for st in S:
+            st["F"].wait(0)
+            st["F"].wait(1)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        run_steps(0, W)
+        l0 = ctx.kernel_launches
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps(W, W + K)
+        e1.record(stream)
+        barrier()
+        ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+        launches = ctx.kernel_launches - l0
+        last = [(st["outs"][(W + K - 1) & 1][0].copy(), st["outs"][(W + K - 1) & 1][1].copy()) for st in S]
+        # device-resident: the timed frame batches again, against the final map, inputs uploaded outside the timed region
+        ms = 0.0
+        for i in range(W, W + K):
+            for st in S:
+                ids, kp, _ = st["steps"][i]
+                st["F"].set_visible(st["mp"], ids, kp)
+                st["F"].run()  # (first use after the pipelined loop: graph of slot 0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                st["F"].run()
+                b.record(stream)
+                torch.cuda.synchronize()
+                ms += a.elapsed_time(b)
+        clocks = sampler.stop() if sampler else None
+        # the last step once more against the final map: the pipelined loop delivered exactly these results
+        for st, (m_, p_) in zip(S, last):
+            m2, p2 = st["F"].get_outputs()
+            assert np.array_equal(m_, m2) and np.array_equal(p_.view(np.int32), p2.view(np.int32))
+    t_dev = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = (float(x) for x in t_dev.tolist())
+    total = C5_SEQUENCES * FB * K
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- parity of the replayed state (rank 0, first local sequence): frames of the LAST batch against the oracle on the
+    # generator's host model, which has seen the same keyframes, culls, bad points and BA updates
+    st = S[0]
+    from oracle.pyoracle import Oracle, slam_params
+    synth = importlib.import_module("lc-crf-slam_b200.synth")
+    o, prm_o, en = Oracle(), slam_params(**synth.SLAM_PARAMS), pkg.label_energies(2, prm.confidence)
+    ids, kp, _ = st["steps"][W + K - 1]
+    mp_out, pr_out = last[0]
+    dbg = st["F"].get_debug()
+    ptr_f = np.concatenate([[0], np.cumsum(st["gen"].sizes)])
+    parity = {"frames_checked": 0, "unary_bit_exact": True, "init_label_mismatches": 0, "max_rel_marginal_err": 0.0,
+              "map_mismatches": 0, "map_mismatches_not_near_tie": 0}
+    for j in (0, FB // 2, FB - 1):
+        a, b = int(ptr_f[j]), int(ptr_f[j + 1])
+        snap = st["gen"].snapshot(ids[a:b], kp[a:b])
+        ob, er, de = o.map_point_unary(snap)
+        parity["unary_bit_exact"] &= bool(np.array_equal(er.view(np.int32), dbg["error"][a:b].view(np.int32)) and
+                                          np.array_equal(de.view(np.int32), dbg["depth"][a:b].view(np.int32)))
+        lab = dbg["init_label"][a:b]
+        parity["init_label_mismatches"] += int((o.rough_classify(ob, er, de, prm_o) != lab).sum())
+        Qo, mo, _ = o.slam_crf(ob, er, snap.kp2d, lab, en, prm_o)
+        rel = np.abs(pr_out[a:b].astype(np.float64) - Qo) / np.maximum(np.abs(Qo), 1e-300)
+        rel[(Qo == 0) & (pr_out[a:b] == 0)] = 0
+        parity["max_rel_marginal_err"] = max(parity["max_rel_marginal_err"], float(rel.max()))
+        diff = np.nonzero(mp_out[a:b] != mo)[0]
+        parity["map_mismatches"] += int(diff.size)
+        parity["map_mismatches_not_near_tie"] += int((np.abs(Qo[diff, 0] - Qo[diff, 1]) >= 1e-5).sum())
+        parity["frames_checked"] += 1
+    assert parity["unary_bit_exact"] and parity["max_rel_marginal_err"] <= 1e-4 and parity["map_mismatches_not_near_tie"] == 0, parity
+    # ---- roofline (first local sequence, last batch) and CPU baseline
+    peak, peak_src = hbm_peak()
+    roofline = shares = kernel_ms = None
+    ab = st["F"].algorithmic_bytes()
+    nnz = int(round((ab["unary"] - st["NT"] * 24 - st["gen"].n_kf * 80) / 12.0))
+    if not args.no_profile:
+        with torch.cuda.stream(stream):
+            roofline, shares, kernel_ms = profile_kernels(ctx, st["F"], st["NT"], nnz, st["gen"].n_kf, prm.iters, peak, peak_src)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        frames = []
+        for j in range(min(FB, 2 * cores)):
+            a, b = int(ptr_f[j]), int(ptr_f[j + 1])
+            frames.append(st["gen"].snapshot(ids[a:b], kp[a:b]))
+        sample = [frames[i % len(frames)] for i in range(8 * cores)]
+        v, kind, dt = time_cpu("c5", sample, cores, repeats=8)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d frames on %d host threads in %.1f s; CRF = %s, unary = oracle port" % (
+                   8 * len(sample), cores, dt, "reference headers compiled in place" if kind == "reference" else "oracle port")}
+    h2d = int(np.mean([sum(d.nbytes + i.nbytes + k.nbytes for st_ in S for (i, k, d) in [st_["steps"][t]]) for t in range(W, W + K)]))
+    d2h = int(sum(st_["NT"] * 10 for st_ in S))
+    line = {
+        "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config("c5", args.batch, args.splat),
+        "run_info": {"sequences_on_rank0": len(S), "points_per_step_rank0": int(sum(st_["NT"] for st_ in S)),
+                     "map_points_per_sequence": st["gen"].P, "keyframes_after_replay": st["gen"].n_kf,
+                     "churn_per_step_and_sequence": "8 new keyframes (pose, intrinsics, bounds, 8192-slot keypoint row) with up to 6000 "
+                                                    "AddObservation each, culling of keyframes beyond 24 alive (EraseObservation in every "
+                                                    "point that holds them), ~0.4% of the live points SetBadFlag, ALL poses and ALL 40000 "
+                                                    "positions re-sent"},
+        "clocks": clocks,
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K, "inputs": "resident maps; per step and sequence: visible ids, keypoints, one map delta"},
+        "gpu_launches": int(launches), "roofline": roofline, "kernel_shares": shares, "kernel_avg_launch_ms": kernel_ms,
+        "parity_vs_oracle": parity, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_gpu_arm(args):
     if args.workload == "c2":
         return run_gpu_arm_image(args)
+    if args.workload == "c5":
+        return run_gpu_arm_replay(args)
     import torch
     pkg = importlib.import_module("lc-crf-slam_b200")
     synth_mod = importlib.import_module("lc-crf-slam_b200.synth")
@@ -469,7 +768,17 @@ def run_gpu_arm(args):
     batch = args.batch or dbatch
 
     # ---- problems of this rank (independent units: no collective on the data path)
-    problems = make_problems(args.workload, batch, seed0=1000 + 100000 * rank)
+    if args.workload == "c4":
+        # ONE job of `batch` problems, cut into contiguous ranges of balanced total size (strong scaling)
+        shard_mod = importlib.import_module("lc-crf-slam_b200.shard")
+        all_sizes = np.random.default_rng(1000).integers(4000, 6001, batch)
+        lo, hi = shard_mod.shard_contiguous(all_sizes.tolist(), world)[rank]
+        problems = make_problems("c4", batch, seed0=1000, shard=(lo, hi))
+        job_problems = batch
+        batch = hi - lo
+    else:
+        problems = make_problems(args.workload, batch, seed0=1000 + 100000 * rank)
+        job_problems = world * batch
     stream = torch.cuda.Stream()
     ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
     ctx.set_option("ordered_splat", 1 if args.splat == "ordered" else 0)
@@ -482,6 +791,11 @@ def run_gpu_arm(args):
         return t.numpy(), t
 
     keep = []
+
+    def keep_pinned(a):
+        v, t = pinned(a)
+        keep.append(t)
+        return v
     if args.workload == "c3":
         cat = concat_snapshots(problems)
         # the same observations as (keyframe, feature index) pairs + per-keyframe keypoint rows; obs_uv is replaced by
@@ -507,10 +821,17 @@ def run_gpu_arm(args):
             keep.append(t)
         nnz, nKF = int(host["obs_kf"].size), int(host["kf_pose"].shape[0])
 
+        # The map of every problem lives in HBM (lccrf_map): keyframes with their keypoint rows, map points, observation
+        # lists -- loaded once, as a SLAM system fills it keyframe by keyframe.  A step names its points by map ids.
+        mp = pkg.Map(ctx, KP_STRIDE)
+        mp.apply(kf_pose=host["kf_pose"], kf_intr=host["kf_intr"], kf_bounds=host["kf_bounds"], kf_keypoints=kp_table, xyz=host["xyz"])
+        mp.set_observations(host["obs_ptr"], host["obs_ref"].astype(np.int32))
+        host["ids"], t = pinned(np.arange(int(sum(sizes)), dtype=np.int32))
+        keep.append(t)
+
         def upload():
-            F.set_map_inputs(host["xyz"], host["obs_ptr"], host["obs_kf"], host["obs_uv"], host["kf_pose"],
-                             host["kf_intr"], host["kf_bounds"], host["kp2d"], host["kf_ptr"])
-        h2d = sum(int(v.nbytes) for v in host.values())
+            F.set_visible(mp, host["ids"], host["kp2d"], kf_ptr=host["kf_ptr"])
+        h2d = 0
     else:
         host = {}
         for k in ("observs", "error", "depth", "kp2d"):
@@ -562,29 +883,50 @@ def run_gpu_arm(args):
             if nKF <= 65536:  # compact snapshot: uint16 keyframe indices
                 host["obs_kf"], t = pinned(host["obs_kf"].astype(np.uint16))
                 keep.append(t)
-            h2d_flat = sum(int(v.nbytes) for k, v in host.items() if k not in ("obs_ref",))
+            h2d_flat = sum(int(v.nbytes) for k, v in host.items() if k not in ("obs_ref", "ids"))
 
             def submit_flat(slot):
                 F.submit_map(slot, host["xyz"], host["obs_ptr"], host["obs_kf"], host["obs_uv"], host["kf_pose"],
                              host["kf_intr"], host["kf_bounds"], host["kp2d"], host["kf_ptr"], *outs[slot])
-            # headline end-to-end path: observations as (keyframe, feature index) pairs -- the reference's own
-            # MapPoint::mObservations entries -- against keyframe keypoint arrays that are uploaded ONCE, when a
-            # keyframe is inserted (KeyFrame::mvKeysUn never changes afterwards; the reference's CPU path likewise
-            # reads them from the resident KeyFrame objects, not from per-frame inputs).  Everything that changes
-            # from frame to frame (points, observation lists, keyframe poses, keypoints of the frame) is copied
-            # from pinned host memory every step.
+            # previous headline path, kept for comparison: observations re-sent every step as (keyframe, feature index)
+            # pairs against keyframe keypoint rows that are resident in the frames object
             F.set_keyframe_keypoints(kp_table)
             kp_table_bytes = int(kp_table.nbytes)
             del kp_table
-            h2d = sum(int(host[k].nbytes) for k in ("xyz", "obs_ptr", "obs_ref", "kf_pose", "kf_intr", "kf_bounds", "kp2d", "kf_ptr"))
-            e2e_mode = ("indexed observations (uint16 keyframe, uint16 feature index) + resident keyframe keypoint "
-                        "table (%.0f MB, uploaded once at keyframe insertion, not per step)" % (kp_table_bytes / 1e6))
+            h2d_indexed = sum(int(host[k].nbytes) for k in ("xyz", "obs_ptr", "obs_ref", "kf_pose", "kf_intr", "kf_bounds", "kp2d", "kf_ptr"))
 
-            def submit(slot):
+            def submit_indexed(slot):
                 F.submit_map_indexed(slot, host["xyz"], host["obs_ptr"], host["obs_ref"], host["kf_pose"],
                                      host["kf_intr"], host["kf_bounds"], host["kp2d"], host["kf_ptr"], *outs[slot])
+            # HEADLINE end-to-end path: the resident map.  Per step the host sends the ids of the frame's map points, the
+            # frame's keypoints and a map delta with a stated, conservative churn:
+            #   - ALL keyframe poses and ALL map point positions again (as if bundle adjustment moved everything),
+            #   - one keyframe's worth of observation churn per problem: a quarter of the points (25k per problem, the
+            #     mean number of observations of one C3 keyframe) lose their newest observation (EraseObservation) and
+            #     get it back (AddObservation).  Re-adding the same pair keeps the workload exactly C3 (N = 100k x 64)
+            #     and lets every step be checked against the device-resident results; the bytes and the kernels are
+            #     those of a real keyframe insertion + culling.
+            last = host["obs_ptr"][1:].astype(np.int64) - 1
+            deltas = []
+            for q in range(4):
+                sel = np.concatenate([np.arange(int(o) + q, int(o) + n_, 4) for o, n_ in zip(np.cumsum([0] + sizes[:-1]), sizes)]).astype(np.int32)
+                ref_last = host["obs_ref"][last[sel]].astype(np.int32)
+                d = pkg.MapDelta.make(pose=host["kf_pose"], xyz=host["xyz"], erase_pt=sel, erase_kf=ref_last[:, 0],
+                                      add_pt=sel, add_kf=ref_last[:, 0], add_fid=ref_last[:, 1], pin=lambda a: keep_pinned(a))
+                deltas.append(d)
+            h2d = int(deltas[0].nbytes + host["ids"].nbytes + host["kp2d"].nbytes + host["kf_ptr"].nbytes)
+            e2e_mode = ("resident map (lccrf_map): per step the visible point ids, the frame's keypoints and a map delta = all %d "
+                        "keyframe poses + all %d point positions + %d EraseObservation + %d AddObservation; keyframe keypoint "
+                        "rows (%.0f MB) and observation lists (%d observations) were uploaded once" % (
+                            nKF, NT, deltas[0].n_erase, deltas[0].n_add, kp_table_bytes / 1e6, nnz))
+            step_no = [0]
+
+            def submit(slot):
+                F.submit_visible(slot, mp, host["ids"], host["kp2d"], outs[slot][0], outs[slot][1],
+                                 delta=deltas[step_no[0] & 3], kf_ptr=host["kf_ptr"])
+                step_no[0] += 1
         else:
-            submit_flat, h2d_flat = None, 0
+            submit_flat, h2d_flat, submit_indexed, h2d_indexed = None, 0, None, 0
 
             def submit(slot):
                 F.submit(slot, host["observs"], host["error"], host["depth"], host["kp2d"], *outs[slot])
@@ -612,17 +954,18 @@ def run_gpu_arm(args):
         ms_e2e = e2e_time(submit, args.steps)
         for m_, p_ in outs[:min(2, args.steps)]:  # both slots delivered the same (deterministic) results
             assert np.array_equal(m_, ref_map) and np.array_equal(p_.view(np.int32), ref_prob.view(np.int32))
-        # the same steps with the complete flat snapshot (every observed keypoint travels with its observation)
-        n_flat = min(args.steps, 20)
+        # the same steps without a resident map: observation lists re-sent as index pairs / as the complete flat snapshot
+        n_flat = min(args.steps, 10)
+        ms_indexed = e2e_time(submit_indexed, n_flat) * args.steps / n_flat if submit_indexed else 0.0
         ms_flat = e2e_time(submit_flat, n_flat) * args.steps / n_flat if submit_flat else 0.0
         clocks = sampler.stop() if sampler else None
         for m_, p_ in outs[:min(2, args.steps)]:
             assert np.array_equal(m_, ref_map) and np.array_equal(p_.view(np.int32), ref_prob.view(np.int32))
-    t_dev = torch.tensor([ms, ms_e2e, ms_flat], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([ms, ms_e2e, ms_flat, ms_indexed], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)  # max over ranks
-    ms, ms_e2e, ms_flat = (float(x) for x in t_dev.tolist())
-    total_problems = world * batch * args.steps
+    ms, ms_e2e, ms_flat, ms_indexed = (float(x) for x in t_dev.tolist())
+    total_problems = job_problems * args.steps
     value = total_problems / (ms * 1e-3)
     e2e_value = total_problems / (ms_e2e * 1e-3)
 
@@ -633,61 +976,13 @@ def run_gpu_arm(args):
         return
 
     # ---- roofline of the dominant kernel (rank 0): per-kernel CUDA events on the launching stream
+    peak, peak_src = hbm_peak()
     roofline, shares, kernel_ms = None, None, None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if not args.no_profile:
         with torch.cuda.stream(stream):
-            ctx.set_option("profile", 1)
-            ctx.profile_report()
-            nprof = 3
-            for _ in range(nprof):
-                F.run()
-            rep = ctx.profile_report()
-            ctx.set_option("profile", 0)
-        # fold kernel groups
-        grp = {}
-        for k, (cnt, tms) in rep.items():
-            g = next((gn for gn, members in KERNEL_GROUPS.items() if k in members), k)
-            c0, t0_ = grp.get(g, (0, 0.0))
-            first = g == k or k == KERNEL_GROUPS[g][0]
-            grp[g] = (c0 + (cnt if first else 0), t0_ + tms)
-        tot = sum(v[1] for v in grp.values()) or 1.0
-        shares = {k: round(v[1] / tot, 4) for k, v in sorted(grp.items(), key=lambda kv: -kv[1][1])}
-        kernel_ms = {k: round(v[1] / max(v[0], 1), 5) for k, v in grp.items()}
-        dbg = F.get_debug()
-        Vtot = float(dbg["V"].sum()) / 2.0  # mean over the two lattice sets
-        kf_bytes = int(host["obs_kf"].dtype.itemsize) if args.workload == "c3" else 4
-        rl_all = {}
-        for k, (cnt, tms) in grp.items():
-            ab = algorithmic_kernel_bytes(k, NT, Vtot, nnz, nKF, kf_bytes, T=prm.iters)
-            if ab is not None and cnt:
-                rl_all[k] = round(ab / (tms / cnt * 1e-3) / 1e9, 1)
-        top = next(iter(shares))
-        cnt, tms = grp[top]
-        ab = algorithmic_kernel_bytes(top, NT, Vtot, nnz, nKF, kf_bytes, T=prm.iters)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the last ncu --set full capture
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = tj.get(top)
-            if traffic is not None and tj.get("_captured_points_per_step"):
-                traffic = traffic * NT / float(tj["_captured_points_per_step"])  # DRAM traffic is linear in the batch
-        members = KERNEL_GROUPS.get(top, (top,))
-        if ab is not None:
-            per_launch_ms = tms / cnt
-            ach = ab / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"kernel": "+".join(members), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": ab, "avg_launch_ms": per_launch_ms,
-                        "share_of_step": shares[top], "achieved_gbs_all_kernels": rl_all,
-                        "note": "per-kernel CUDA events on the launching stream, concurrency and graphs off while profiling"}
-        else:
-            roofline = {"kernel": "+".join(members), "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s",
-                        "frac": None, "traffic": traffic, "peak_source": peak_src, "share_of_step": shares[top]}
+            upload()  # profile the input variant `value` was timed on (the end-to-end loops left theirs in the slots)
+            F.run()
+            roofline, shares, kernel_ms = profile_kernels(ctx, F, NT, nnz, nKF, prm.iters, peak, peak_src)
     blur = None
     if not args.no_profile and world == 1:
         with torch.cuda.stream(stream):
@@ -709,18 +1004,19 @@ def run_gpu_arm(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "problems_per_step_per_gpu": batch, "points_per_step_per_gpu": NT,
-                   "l2_policy": ("inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (abytes["total"] / 1e6))
-                                if abytes["total"] > 126e6 else
-                                ("working set %.1f MB per step fits the 126 MB L2 and is NOT flushed between steps: "
-                                 "cache-resident latency figure, not a headline configuration" % (abytes["total"] / 1e6)),
-                   "sharding": "independent problems per rank, no collective",
-                   "splat_mode": SPLAT_MODES[args.splat]},
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, args.batch, args.splat),
+        "run_info": {"problems_per_step_rank0": batch, "points_per_step_rank0": NT,
+                     "bytes_read_per_step_rank0": abytes["total"]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "inputs": e2e_mode},
+        "e2e_indexed_snapshot": None if not ms_indexed else {
+            "value": total_problems / (ms_indexed * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_indexed,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms_indexed / args.steps,
+            "inputs": "no resident map: observation lists re-sent every step as (uint16 keyframe, uint16 feature index) pairs; "
+                      "keyframe keypoint rows resident"},
         "e2e_full_snapshot": None if not ms_flat else {
             "value": total_problems / (ms_flat * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_flat,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms_flat / args.steps,

@@ -284,8 +284,8 @@ int lccrf_frames_algorithmic_bytes(lccrf_frames *fr, double *total, double *per_
  *             loses all observations
  *   add       MapPoint::AddObservation(pKF, idx) (src/MapPoint.cc:98-109): appends (add_kf[i], add_fid[i]) to point
  *             add_pt[i] unless the point already has an observation in that keyframe (:101-102); the observed keypoint mvKeysUn[idx].pt is looked up in the resident keyframe once, here
- * Applied in exactly this order.  Within ONE delta a point may appear at most once in erase_* and at most once in add_*
- * (one keyframe inserts / culls at most one observation per point; split anything else over several deltas) -- a
+ * Applied in exactly this order.  Within one SEGMENT of the erase / add lists (the whole list unless *_seg_ptr says
+ * otherwise) a point may appear at most once: one keyframe inserts / culls at most one observation per point.  A
  * repetition is detected on the device and reported as LCCRF_ERR_ARG by the call that synchronises.  Observation order
  * = insertion order (the reference iterates a std::map<KeyFrame*, size_t>, i.e. pointer order, which no restatement can
  * reproduce); a map filled through lccrf_map_set_observations / deltas gives bit-identical results to the same lists
@@ -306,6 +306,13 @@ typedef struct lccrf_map_delta {
     const int *bad_pt;
     int n_add;
     const int *add_pt, *add_kf, *add_fid;
+    /* optional segmentation of the erase / add lists (host arrays [n_*_seg + 1], first 0, last n_erase / n_add): one
+     * segment per culled / inserted keyframe, applied one after the other, so that a step may carry several keyframes
+     * that touch the same point; the once-per-point rule then holds per segment.  0 / NULL = one segment. */
+    int n_erase_seg;
+    const int *erase_seg_ptr;
+    int n_add_seg;
+    const int *add_seg_ptr;
 } lccrf_map_delta;
 /* kp_stride: keypoint slots per keyframe (the ORB extractor's feature budget, ORBextractor.nFeatures) */
 int lccrf_map_create(lccrf_ctx *ctx, int kp_stride, lccrf_map **out);

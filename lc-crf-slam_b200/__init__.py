@@ -433,12 +433,13 @@ class MapDelta(C.Structure):
     _fields_ = [("kf_first", C.c_int), ("kf_count", C.c_int), ("kf_pose", _vp), ("kf_intr", _vp), ("kf_bounds", _vp),
                 ("kf_keypoints", _vp), ("n_pose", C.c_int), ("pose_kf", _vp), ("pose", _vp), ("n_xyz", C.c_int),
                 ("xyz_id", _vp), ("xyz", _vp), ("n_erase", C.c_int), ("erase_pt", _vp), ("erase_kf", _vp),
-                ("n_bad", C.c_int), ("bad_pt", _vp), ("n_add", C.c_int), ("add_pt", _vp), ("add_kf", _vp), ("add_fid", _vp)]
+                ("n_bad", C.c_int), ("bad_pt", _vp), ("n_add", C.c_int), ("add_pt", _vp), ("add_kf", _vp), ("add_fid", _vp),
+                ("n_erase_seg", C.c_int), ("erase_seg_ptr", _vp), ("n_add_seg", C.c_int), ("add_seg_ptr", _vp)]
 
     @classmethod
     def make(cls, kf_first=0, kf_pose=None, kf_intr=None, kf_bounds=None, kf_keypoints=None, pose_kf=None, pose=None,
              xyz_id=None, xyz=None, erase_pt=None, erase_kf=None, bad_pt=None, add_pt=None, add_kf=None, add_fid=None,
-             pin=None) -> "MapDelta":
+             erase_seg_ptr=None, add_seg_ptr=None, pin=None) -> "MapDelta":
         """pin: optional callable array -> page-locked copy (bench.py passes a torch pin_memory wrapper)"""
         d = cls()
         keep = []
@@ -475,6 +476,10 @@ class MapDelta(C.Structure):
         d.bad_pt = _ptr(bad_pt)
         d.n_add = 0 if add_pt is None else int(add_pt.size)
         d.add_pt, d.add_kf, d.add_fid = _ptr(add_pt), _ptr(add_kf), _ptr(add_fid)
+        d._seg = [None if a is None else np.ascontiguousarray(a, dtype=np.int32) for a in (erase_seg_ptr, add_seg_ptr)]
+        d.n_erase_seg = 0 if d._seg[0] is None else int(d._seg[0].size - 1)
+        d.n_add_seg = 0 if d._seg[1] is None else int(d._seg[1].size - 1)
+        d.erase_seg_ptr, d.add_seg_ptr = _ptr(d._seg[0]), _ptr(d._seg[1])
         if pose_kf is not None and pose_kf.size != d.n_pose or xyz_id is not None and xyz_id.size != d.n_xyz:
             raise LccrfError("MapDelta: id arrays must match their value arrays")
         if d.n_erase and (erase_kf is None or erase_kf.size != d.n_erase):

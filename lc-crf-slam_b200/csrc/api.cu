@@ -215,6 +215,8 @@ struct FrameInputs {
     int *vis = nullptr;       // [NT] map point ids
     uint64_t map_gen = 0;
     int kf_bucket = 0;        // shared-memory keyframe slots the captured graph was sized for
+    void *out_stage = nullptr;     // per-slot copy of the results (marginals, labels, status word) on their way to the host
+    cudaEvent_t res_ready = nullptr;
     void *stage = nullptr;    // staged arrays of this step's map delta
     size_t stage_cap = 0;
     DeltaDev delta;
@@ -332,6 +334,7 @@ void lccrf_ctx_destroy(lccrf_ctx *h) {
     cudaFree(c->d_status);
     cudaFreeHost(c->h_status);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1017,6 +1020,8 @@ static void frame_inputs_release(Ctx *ctx, FrameInputs &in) {
     dev_free(ctx, in.kf_packed);
     dev_free(ctx, in.kf_ptr);
     dev_free(ctx, in.vis);
+    dev_free(ctx, in.out_stage);
+    if (in.res_ready) cudaEventDestroy(in.res_ready);
     dev_free(ctx, in.p4);
     dev_free(ctx, in.p4_has);
     if (in.stage) cudaFree(in.stage);
@@ -1033,6 +1038,7 @@ void lccrf_frames_destroy(lccrf_frames *fr) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
     for (auto &in : fr->in) frame_inputs_release(ctx, in);
     batch_release(ctx, fr->b);
     dev_free(ctx, fr->observs);
@@ -1396,9 +1402,18 @@ static int frames_submit_epilogue(lccrf_frames *fr, int slot, FrameInputs &in, s
     }
     LCCRF_TRY(frames_run_slot(fr, in));
     LCCRF_CUDA(cudaEventRecord(in.run_done, ctx->stream));
+    // Results leave through per-slot device staging on a third stream: the next slot's run neither waits for the PCIe
+    // copy nor overwrites labels / marginals that are still on their way out.
     const size_t n = (size_t)fr->b.NT;
-    if (n && map_out) LCCRF_CUDA(cudaMemcpyAsync(map_out, fr->b.map, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n && prob_out) LCCRF_CUDA(cudaMemcpyAsync(prob_out, fr->b.cur, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->d2h_stream) LCCRF_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    if (!in.out_stage) {
+        LCCRF_TRY(dev_alloc(ctx, (void **)&in.out_stage, (n ? n : 1) * 10 + 256));
+        LCCRF_CUDA(cudaEventCreateWithFlags(&in.res_ready, cudaEventDisableTiming));
+    }
+    char *st_prob = (char *)in.out_stage, *st_map = st_prob + n * 8, *st_status = st_map + ((n * 2 + 15) / 16) * 16;
+    if (n && map_out) LCCRF_CUDA(cudaMemcpyAsync(st_map, fr->b.map, n * 2, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n && prob_out) LCCRF_CUDA(cudaMemcpyAsync(st_prob, fr->b.cur, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    LCCRF_CUDA(cudaMemcpyAsync(st_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     if (in.part_dyn_ptr || in.part_dyn || in.part_stat_ptr || in.part_stat) {
         // label application of THIS submission (Tracking.cc:1945-1955), before the other slot's run reuses the labels
         const int NT = fr->b.NT, B = fr->b.B;
@@ -1416,8 +1431,12 @@ static int frames_submit_epilogue(lccrf_frames *fr, int slot, FrameInputs &in, s
         if (in.part_dyn && NT) LCCRF_CUDA(cudaMemcpyAsync(in.part_dyn, d_dyn, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
         if (in.part_stat && NT) LCCRF_CUDA(cudaMemcpyAsync(in.part_stat, d_stat, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
     }
-    LCCRF_CUDA(cudaMemcpyAsync(in.h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    LCCRF_CUDA(cudaEventRecord(in.out_done, ctx->stream));
+    LCCRF_CUDA(cudaEventRecord(in.res_ready, ctx->stream));
+    LCCRF_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, in.res_ready, 0));
+    if (n && map_out) LCCRF_CUDA(cudaMemcpyAsync(map_out, st_map, n * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (n && prob_out) LCCRF_CUDA(cudaMemcpyAsync(prob_out, st_prob, n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    LCCRF_CUDA(cudaMemcpyAsync(in.h_status, st_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    LCCRF_CUDA(cudaEventRecord(in.out_done, ctx->d2h_stream));
     in.in_flight = true;
     fr->last_slot = slot;
     return LCCRF_OK;
@@ -1705,6 +1724,8 @@ static int delta_stage(const lccrf_map_delta &d, int kp_stride, bool with_keypoi
     o.add_pt = (const int *)put(d.add_pt, (size_t)d.n_add * 4);
     o.add_kf = (const int *)put(d.add_kf, (size_t)d.n_add * 4);
     o.add_fid = (const int *)put(d.add_fid, (size_t)d.n_add * 4);
+    if (d.n_erase_seg > 0) o.erase_seg.assign(d.erase_seg_ptr, d.erase_seg_ptr + d.n_erase_seg + 1);
+    if (d.n_add_seg > 0) o.add_seg.assign(d.add_seg_ptr, d.add_seg_ptr + d.n_add_seg + 1);
     if (err != cudaSuccess) return fail(LCCRF_ERR_CUDA, std::string("map delta upload: ") + cudaGetErrorString(err));
     *out = o;
     return LCCRF_OK;

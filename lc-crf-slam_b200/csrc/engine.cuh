@@ -83,6 +83,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // uploads of the pipelined submit path (created on first use)
+    cudaStream_t d2h_stream = nullptr;   // results of the pipelined submit path on their way to the host
     uint64_t launches = 0;
     uint64_t scratch_gen = 0;  // bumped whenever a scratch buffer moves (captured graphs hold raw pointers)
     int opt_graphs = 1;
@@ -234,6 +235,7 @@ struct DeltaDev {
     const int *bad_pt = nullptr;
     int n_add = 0;
     const int *add_pt = nullptr, *add_kf = nullptr, *add_fid = nullptr;
+    std::vector<int> erase_seg, add_seg;  // host copies of the segment boundaries (empty = one segment)
 };
 
 int map_create(Ctx *ctx, int kp_stride, DevMap **out);

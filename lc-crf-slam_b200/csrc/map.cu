@@ -403,6 +403,16 @@ int map_prepare(DevMap *m, const lccrf_map_delta &h) {
         // the capacity was raised first (lccrf_map_set_observations / an id-less xyz block / the first delta below)
     }
     if (h.n_erase > 0 && (!h.erase_pt || !h.erase_kf)) return fail(LCCRF_ERR_ARG, "map delta: erase arrays are NULL");
+    for (int which = 0; which < 2; which++) {
+        const int ns = which ? h.n_add_seg : h.n_erase_seg, total = which ? h.n_add : h.n_erase;
+        const int *sp = which ? h.add_seg_ptr : h.erase_seg_ptr;
+        if (ns < 0 || (ns > 0 && !sp)) return fail(LCCRF_ERR_ARG, "map delta: segment pointer array is NULL");
+        if (ns > 0) {
+            if (sp[0] != 0 || sp[ns] != total) return fail(LCCRF_ERR_ARG, "map delta: segments must span the whole list");
+            for (int g = 0; g < ns; g++)
+                if (sp[g + 1] < sp[g]) return fail(LCCRF_ERR_ARG, "map delta: segment boundaries must be non-decreasing");
+        }
+    }
     if (h.n_bad > 0 && !h.bad_pt) return fail(LCCRF_ERR_ARG, "map delta: bad_pt is NULL");
     if (h.n_add > 0) {
         if (!h.add_pt || !h.add_kf || !h.add_fid) return fail(LCCRF_ERR_ARG, "map delta: add arrays are NULL");
@@ -439,21 +449,25 @@ int map_apply_dev(DevMap *m, const DeltaDev &d, const float *kp_host) {
         k_map_set_xyz<<<cdiv(d.n_xyz, kThreads), kThreads, 0, st>>>(m->pt_xyz, d.xyz_id, d.xyz, d.n_xyz, m->pt_cap, ctx->d_status);
     }
     PoolArgs a = pool_args(m);
-    if (d.n_erase > 0) {
+    for (size_t g = 0; d.n_erase > 0 && g < (d.erase_seg.empty() ? 1 : d.erase_seg.size() - 1); g++) {
+        const int e0 = d.erase_seg.empty() ? 0 : d.erase_seg[g], e1 = d.erase_seg.empty() ? d.n_erase : d.erase_seg[g + 1];
+        if (e1 <= e0) continue;
         a.stamp = ++m->epoch;
         LCCRF_KERNEL(ctx, "k_map_erase");
-        k_map_erase<<<cdiv(d.n_erase, kThreads), kThreads, 0, st>>>(a, d.erase_pt, d.erase_kf, d.n_erase);
+        k_map_erase<<<cdiv(e1 - e0, kThreads), kThreads, 0, st>>>(a, d.erase_pt + e0, d.erase_kf + e0, e1 - e0);
     }
     if (d.n_bad > 0) {
         LCCRF_KERNEL(ctx, "k_map_bad");
         k_map_bad<<<cdiv(d.n_bad, kThreads), kThreads, 0, st>>>(a, d.bad_pt, d.n_bad);
     }
-    if (d.n_add > 0) {
+    for (size_t g = 0; d.n_add > 0 && g < (d.add_seg.empty() ? 1 : d.add_seg.size() - 1); g++) {
+        const int e0 = d.add_seg.empty() ? 0 : d.add_seg[g], e1 = d.add_seg.empty() ? d.n_add : d.add_seg[g + 1];
+        if (e1 <= e0) continue;
         a.stamp = ++m->epoch;
-        { LCCRF_KERNEL(ctx, "k_map_add");
-          k_map_add<<<cdiv(d.n_add, kThreads), kThreads, 0, st>>>(a, d.add_pt, d.add_kf, d.add_fid, d.n_add); }
-        LCCRF_TRY(poll_counters(m, true));
+        LCCRF_KERNEL(ctx, "k_map_add");
+        k_map_add<<<cdiv(e1 - e0, kThreads), kThreads, 0, st>>>(a, d.add_pt + e0, d.add_kf + e0, d.add_fid + e0, e1 - e0);
     }
+    if (d.n_add > 0) LCCRF_TRY(poll_counters(m, true));
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;
 }

@@ -101,10 +101,12 @@ def _rot(rx: float, ry: float, rz: float) -> np.ndarray:
 
 
 def map_snapshot(n: int, obs_per_point: int, seed: int, n_kf: int = 256, intr=TUM_INTR,
-                 dyn_frac: float = 0.2, ragged: bool = False, bad_frac: float = 0.05) -> MapSnapshot:
+                 dyn_frac: float = 0.2, ragged: bool = False, bad_frac: float = 0.05, unique_kf: bool = False) -> MapSnapshot:
     """C3: N map points x `obs_per_point` keyframe observations on a smooth trajectory.
     ~bad_frac of the observations are deliberately behind the camera / out of bounds to
-    exercise the skip rules (Tracking.cc:1823,1828)."""
+    exercise the skip rules (Tracking.cc:1823,1828).
+    unique_kf: every point is observed at most once per keyframe, as in the reference's std::map<KeyFrame*, size_t>
+    (MapPoint.h:115) -- what a device-resident map filled through AddObservation / EraseObservation needs."""
     rng = np.random.default_rng(seed)
     fx, fy, cx, cy = intr
     # keyframes: small smooth motion around the origin, looking down +z
@@ -129,7 +131,15 @@ def map_snapshot(n: int, obs_per_point: int, seed: int, n_kf: int = 256, intr=TU
     np.cumsum(cnt, out=obs_ptr[1:])
     nnz = int(obs_ptr[-1])
     pt = np.repeat(np.arange(n), cnt)
-    obs_kf = rng.integers(0, n_kf, nnz)
+    if unique_kf:
+        # observation j of point p sits in keyframe perm[row_p][(j + off_p) % M]: distinct keyframes within a point
+        M = n_kf - 2 if (bad_frac > 0 and n_kf >= 4) else n_kf
+        assert obs_per_point <= M, "more observations per point than keyframes"
+        perms = np.stack([rng.permutation(M) for _ in range(257)])
+        j = np.arange(nnz) - obs_ptr[:-1][pt]
+        obs_kf = perms[rng.integers(0, 257, n)[pt], (j + rng.integers(0, M, n)[pt]) % M]
+    else:
+        obs_kf = rng.integers(0, n_kf, nnz)
     P = pose[obs_kf].reshape(nnz, 3, 4)
     X = xyz[pt]
     Xc = np.einsum('nij,nj->ni', P[:, :, :3], X) + P[:, :, 3]
@@ -151,7 +161,13 @@ def map_snapshot(n: int, obs_per_point: int, seed: int, n_kf: int = 256, intr=TU
         Ro = _rot(0, 1.2, 0)
         kf_pose[n_kf - 2] = np.concatenate([Ro, np.zeros((3, 1))], axis=1).reshape(-1).astype(np.float32)
         bad = rng.random(nnz) < bad_frac
-        obs_kf = np.where(bad, rng.integers(n_kf - 2, n_kf, nnz), np.minimum(obs_kf, n_kf - 3))
+        if unique_kf:
+            # at most one observation per point in each of the two bad keyframes: the first two marked ones
+            cs = np.cumsum(bad)
+            rank = cs - (cs[obs_ptr[:-1]] - bad[obs_ptr[:-1]])[pt]   # 1-based rank of a marked observation inside its point
+            obs_kf = np.where(bad & (rank == 1), n_kf - 1, np.where(bad & (rank == 2), n_kf - 2, obs_kf))
+        else:
+            obs_kf = np.where(bad, rng.integers(n_kf - 2, n_kf, nnz), np.minimum(obs_kf, n_kf - 3))
     kf_intr = np.tile(np.array(intr, dtype=np.float32), (n_kf, 1))
     kf_bounds = np.tile(np.array([0, IMG_W, 0, IMG_H], dtype=np.float32), (n_kf, 1))
     return MapSnapshot(xyz32, obs_ptr.astype(np.int32), obs_kf.astype(np.int32), uv.astype(np.float32),
@@ -252,3 +268,169 @@ def epipolar_matches(m: int, seed: int, outlier_frac: float = 0.3):
     F = Kinv.T @ tx @ R @ Kinv
     F = F / np.linalg.norm(F)
     return x1.astype(np.float32), x2.astype(np.float32), np.ascontiguousarray(F, dtype=np.float64), out
+
+
+class SequenceReplay:
+    """C5: one synthetic RGB-D sequence replayed as batches of frame CRFs against a map that changes as it would in
+    LC-CRF-SLAM: a keyframe is inserted every `kf_interval` frames (KeyFrame ctor + MapPoint::AddObservation for the
+    points it sees), the oldest keyframe is culled once more than `kf_window` are alive (MapPoint::EraseObservation in
+    every point that holds it), a few points go bad per batch (SetBadFlag), and bundle adjustment moves all poses and
+    positions a little.  The host model is a boolean point x keyframe matrix; everything is seeded and vectorised.
+
+    kind 'tum': TUM3 intrinsics (TUM3.yaml:8-11), one moving blob (~25% of the points);
+    kind 'bonn': Bonn intrinsics (BONN.yaml:8-11), two larger blobs (~35%)."""
+
+    def __init__(self, seed: int, kind: str = "tum", n_points: int = 40000, frames_per_batch: int = 64,
+                 kf_interval: int = 8, kf_window: int = 24, stride: int = 8192, n_frame_points=(4000, 6000), kf0: int = 16,
+                 kf_obs: int = 6000):
+        self.rng = np.random.default_rng(seed)
+        rng = self.rng
+        self.kind, self.P, self.FB, self.kfi, self.win, self.stride = kind, n_points, frames_per_batch, kf_interval, kf_window, stride
+        self.kf_obs = min(kf_obs, stride)
+        self.intr = np.array(TUM_INTR if kind == "tum" else BONN_INTR, np.float32)
+        self.bounds = np.array([0, IMG_W, 0, IMG_H], np.float32)
+        self.xyz = np.stack([rng.uniform(-2.6, 2.6, n_points), rng.uniform(-1.9, 1.9, n_points), rng.uniform(2.0, 5.5, n_points)], 1).astype(np.float32)
+        blobs = 1 if kind == "tum" else 2
+        self.dynamic = np.zeros(n_points, bool)
+        for _ in range(blobs):
+            c = np.array([rng.uniform(-1.0, 1.0), rng.uniform(-0.6, 0.6), rng.uniform(3.0, 4.5)])
+            r = np.array([1.75, 1.4, 1.5]) if kind == "tum" else np.array([1.7, 1.35, 1.5])
+            self.dynamic |= (((self.xyz - c) / r) ** 2).sum(1) <= 1.0
+        self.sizes = rng.integers(n_frame_points[0], n_frame_points[1] + 1, frames_per_batch).tolist()
+        self.frame = 0
+        self.n_kf = 0
+        self.has = np.zeros((n_points, 0), bool)        # has[p, k]: point p holds an observation in keyframe k
+        self.fid_of = np.zeros((n_points, 0), np.int32)  # its feature index there
+        self.kp_rows = []                                # keypoint row of every keyframe
+        self.kf_pose = np.zeros((0, 12), np.float32)     # pose of every keyframe as last sent to the map
+        self.alive = []                                  # keyframes not yet culled, oldest first
+        self.bad = np.zeros(n_points, bool)
+        # initial map: kf0 keyframes before frame 0, loaded in bulk by the caller (initial_map)
+        self._init = self._make_keyframes(range(-kf0 * kf_interval, 0, kf_interval))
+
+    # ---- camera: a smooth hand-held path looking down +z
+    def pose_of(self, f: float) -> np.ndarray:
+        t = f / 400.0
+        R = _rot(0.06 * np.sin(2 * np.pi * t), 0.09 * np.sin(2 * np.pi * t + 1.0), 0.03 * np.cos(2 * np.pi * t))
+        c = np.array([0.5 * np.sin(2 * np.pi * t), 0.15 * np.cos(2 * np.pi * t), 0.3 * np.sin(np.pi * t)])
+        return np.concatenate([R, (-R @ c)[:, None]], axis=1).reshape(-1).astype(np.float32)
+
+    def project(self, pose12: np.ndarray, ids: np.ndarray):
+        P = pose12.reshape(3, 4).astype(np.float64)
+        Xc = self.xyz[ids].astype(np.float64) @ P[:, :3].T + P[:, 3]
+        fx, fy, cx, cy = self.intr.astype(np.float64)
+        z = np.maximum(Xc[:, 2], 1e-6)
+        return np.stack([fx * Xc[:, 0] / z + cx, fy * Xc[:, 1] / z + cy], 1), Xc[:, 2]
+
+    def in_view(self, pose12: np.ndarray) -> np.ndarray:
+        uv, z = self.project(pose12, np.arange(self.P))
+        return np.nonzero((z > 0.3) & (uv[:, 0] > 4) & (uv[:, 0] < IMG_W - 4) & (uv[:, 1] > 4) & (uv[:, 1] < IMG_H - 4) & ~self.bad)[0]
+
+    def _observe(self, pose12, ids, noise=1.0):
+        """keypoints of the given points in a camera: projection + noise (moving points drift 5-20 px)"""
+        uv, _ = self.project(pose12, ids)
+        uv = uv + self.rng.normal(0, noise, uv.shape)
+        d = self.dynamic[ids]
+        drift = self.rng.uniform(5, 20, ids.size) * d
+        ang = self.rng.uniform(0, 2 * np.pi, ids.size)
+        return (uv + np.stack([drift * np.cos(ang), drift * np.sin(ang)], 1)).astype(np.float32)
+
+    def _make_keyframes(self, frames):
+        """new keyframes at the given frame numbers: each observes up to kf_obs of the points in its view"""
+        out = dict(pose=[], kp=[], pt=[], kf=[], fid=[], seg=[0])
+        for f in frames:
+            pose = self.pose_of(f)
+            vis = self.in_view(pose)
+            vis = np.sort(vis[self.rng.permutation(vis.size)[: self.kf_obs]])
+            fid = self.rng.permutation(self.stride)[: vis.size]
+            row = np.zeros((self.stride, 2), np.float32)
+            row[fid] = self._observe(pose, vis)
+            k = self.n_kf
+            self.n_kf += 1
+            self.has = np.concatenate([self.has, np.zeros((self.P, 1), bool)], axis=1)
+            self.fid_of = np.concatenate([self.fid_of, np.zeros((self.P, 1), np.int32)], axis=1)
+            self.has[vis, k] = True
+            self.fid_of[vis, k] = fid
+            self.kp_rows.append(row)
+            self.kf_pose = np.concatenate([self.kf_pose, pose[None]])
+            self.alive.append(k)
+            out["pose"].append(pose)
+            out["kp"].append(row)
+            out["pt"].append(vis.astype(np.int32))
+            out["kf"].append(np.full(vis.size, k, np.int32))
+            out["fid"].append(fid.astype(np.int32))
+            out["seg"].append(out["seg"][-1] + vis.size)
+        n = len(out["pose"])
+        cat = lambda k, dt: np.concatenate(out[k]).astype(dt) if n else np.zeros(0, dt)
+        return dict(first=self.n_kf - n, pose=np.stack(out["pose"]) if n else np.zeros((0, 12), np.float32),
+                    intr=np.tile(self.intr, (n, 1)), bounds=np.tile(self.bounds, (n, 1)),
+                    kp=np.stack(out["kp"]) if n else np.zeros((0, self.stride, 2), np.float32),
+                    pt=cat("pt", np.int32), kf=cat("kf", np.int32), fid=cat("fid", np.int32), seg=np.asarray(out["seg"], np.int32))
+
+    def initial_map(self):
+        """(keyframes dict, xyz, obs_ptr, obs_ref): the bulk load of the map as it is before frame 0"""
+        kfs = self._init
+        order = np.argsort(kfs["pt"], kind="stable")   # per point, keyframes in insertion order
+        ptr = np.zeros(self.P + 1, np.int32)
+        np.cumsum(np.bincount(kfs["pt"], minlength=self.P), out=ptr[1:])
+        ref = np.stack([kfs["kf"][order], kfs["fid"][order]], 1).astype(np.int32)
+        return kfs, self.xyz.copy(), ptr, ref
+
+    def snapshot(self, ids, kp2d) -> MapSnapshot:
+        """the model's current state for the given frame points in the lccrf_frames_set_map_inputs layout
+        (observations of a point in keyframe insertion order, which is the order the map appends them in)"""
+        ids = np.asarray(ids)
+        rows, kfi = np.nonzero(self.has[ids])
+        ptr = np.zeros(ids.size + 1, np.int32)
+        np.cumsum(np.bincount(rows, minlength=ids.size), out=ptr[1:])
+        kp = np.stack(self.kp_rows)
+        uv = kp[kfi, self.fid_of[ids[rows], kfi]]
+        n = self.n_kf
+        return MapSnapshot(self.xyz[ids].copy(), ptr, kfi.astype(np.int32), uv.astype(np.float32), self.kf_pose.copy(),
+                           np.tile(self.intr, (n, 1)), np.tile(self.bounds, (n, 1)), np.asarray(kp2d, np.float32),
+                           self.dynamic[ids].copy())
+
+    def next_batch(self):
+        """frames [frame, frame + FB): returns dict(ids [NT] int32, kp2d [NT,2], delta kwargs for MapDelta.make)"""
+        rng = self.rng
+        f0 = self.frame
+        self.frame += self.FB
+        # map changes of this span, in the delta's order: new keyframes, poses, positions, erase, bad, add
+        kfs = self._make_keyframes([f for f in range(f0, f0 + self.FB) if f % self.kfi == 0])
+        er_pt, er_kf, er_seg = [], [], [0]
+        while len(self.alive) > self.win:                  # culling of the oldest keyframes
+            k = self.alive.pop(0)
+            pts = np.nonzero(self.has[:, k])[0]
+            self.has[pts, k] = False
+            er_pt.append(pts.astype(np.int32))
+            er_kf.append(np.full(pts.size, k, np.int32))
+            er_seg.append(er_seg[-1] + pts.size)
+        cand = np.nonzero(self.has.any(1) & ~self.bad)[0]
+        bad = cand[rng.random(cand.size) < 0.004]          # SetBadFlag: the point loses all observations
+        self.bad[bad] = True
+        self.has[bad] = False
+        # bundle adjustment: every pose and every position moves a little
+        self.xyz = (self.xyz + rng.normal(0, 5e-4, self.xyz.shape)).astype(np.float32)
+        poses = np.stack([self.pose_of(-16 * self.kfi + k * self.kfi) for k in range(self.n_kf)]) if self.n_kf else np.zeros((0, 12), np.float32)
+        poses = (poses + rng.normal(0, 2e-4, poses.shape)).astype(np.float32)
+        self.kf_pose[: kfs["first"]] = poses[: kfs["first"]]   # the new keyframes keep the pose they were created with
+        # the frames of the batch: visible points = points in view that still hold an observation
+        live = self.has.any(1) & ~self.bad
+        ids, kp2d = [], []
+        for j in range(self.FB):
+            pose = self.pose_of(f0 + j + 0.37)             # tracked frames lie between keyframes
+            vis = self.in_view(pose)
+            vis = vis[live[vis]]
+            n = self.sizes[j]
+            vis = vis[rng.permutation(vis.size)[:n]] if vis.size >= n else rng.choice(np.nonzero(live)[0], n, replace=False)
+            ids.append(vis.astype(np.int32))
+            kp2d.append(self._observe(pose, vis, noise=0.8))
+        delta = dict(kf_first=kfs["first"], kf_pose=kfs["pose"] if kfs["pose"].size else None,
+                     kf_intr=kfs["intr"] if kfs["pose"].size else None, kf_bounds=kfs["bounds"] if kfs["pose"].size else None,
+                     kf_keypoints=kfs["kp"] if kfs["pose"].size else None,
+                     pose=poses[: kfs["first"]] if kfs["first"] > 0 else None, xyz=self.xyz.copy(),
+                     erase_pt=np.concatenate(er_pt) if er_pt else None, erase_kf=np.concatenate(er_kf) if er_kf else None,
+                     erase_seg_ptr=np.asarray(er_seg, np.int32) if er_pt else None, bad_pt=bad.astype(np.int32) if bad.size else None,
+                     add_pt=kfs["pt"] if kfs["pt"].size else None, add_kf=kfs["kf"] if kfs["pt"].size else None,
+                     add_fid=kfs["fid"] if kfs["pt"].size else None, add_seg_ptr=kfs["seg"] if kfs["pt"].size else None)
+        return dict(ids=np.concatenate(ids), kp2d=np.concatenate(kp2d), delta=delta)

@@ -272,7 +272,7 @@ def _mock_device(monkeypatch):
     import torch
     bench = importlib.import_module("bench")
     pkg = importlib.import_module("lc-crf-slam_b200")
-    calls = {"run": 0, "indexed": 0, "flat": 0, "table": 0}
+    calls = {"run": 0, "indexed": 0, "flat": 0, "table": 0, "visible": 0, "map_apply": 0, "map_bulk": 0}
 
     class FakeStream:
         cuda_stream = 0
@@ -341,6 +341,14 @@ def _mock_device(monkeypatch):
         def set_inputs(self, observs, error, depth, kp2d):
             assert observs.shape == (self.NT,) and kp2d.shape == (self.NT, 2)
 
+        def set_visible(self, mp, ids, kp2d, delta=None, kf_ptr=None):
+            assert ids.dtype == np.int32 and ids.shape == (self.NT,) and kp2d.shape == (self.NT, 2)
+
+        def submit_visible(self, slot, mp, ids, kp2d, m, p, delta=None, kf_ptr=None):
+            assert ids.dtype == np.int32 and delta is not None and delta.n_add == delta.n_erase > 0 and delta.n_xyz == self.NT
+            calls["visible"] += 1
+            self._deliver(m, p)
+
         def submit(self, slot, observs, error, depth, kp2d, m, p):
             calls["direct"] = calls.get("direct", 0) + 1
             self._deliver(m, p)
@@ -369,6 +377,18 @@ def _mock_device(monkeypatch):
         def close(self):
             pass
 
+    class FakeMap:
+        def __init__(self, ctx, stride):
+            self.stride = stride
+
+        def apply(self, delta=None, **kw):
+            assert kw["kf_keypoints"].shape[1:] == (self.stride, 2) and kw["kf_pose"].shape[0] == kw["kf_keypoints"].shape[0]
+            calls["map_apply"] += 1
+
+        def set_observations(self, obs_ptr, obs_ref, pt_first=0):
+            assert obs_ref.dtype == np.int32 and obs_ref.shape == (obs_ptr[-1], 2)
+            calls["map_bulk"] += 1
+
     class FakeSampler:
         def __init__(self, i):
             pass
@@ -386,6 +406,7 @@ def _mock_device(monkeypatch):
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setattr(pkg, "Context", FakeCtx)
     monkeypatch.setattr(pkg, "Frames", FakeFrames)
+    monkeypatch.setattr(pkg, "Map", FakeMap)
     monkeypatch.setattr(pkg, "Lattice", FakeLattice)
     monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
     return bench, calls
@@ -413,9 +434,14 @@ def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     assert d["steps"] == 4 and d["warmup"] == 3 and d["gpu_launches"] == 4 * 111 and d["vs_baseline"] is None
     assert d["config"]["problems_per_step_per_gpu"] == 3 and d["config"]["points_per_step_per_gpu"] == 4500
     nnz = 4500 * 8
-    assert d["e2e"]["h2d_bytes_per_step"] == 4500 * 12 + 4501 * 4 + nnz * 4 + 3 * 256 * (48 + 16 + 16) + 4500 * 8 + 4 * 4
-    assert d["e2e_full_snapshot"]["h2d_bytes_per_step"] == d["e2e"]["h2d_bytes_per_step"] + nnz * (2 + 8 - 4)
+    # resident map: ids + keypoints + kf_ptr + delta (all poses, all positions, a quarter of the points erased and re-added)
+    churn = 3 * 375
+    assert d["e2e"]["h2d_bytes_per_step"] == 4500 * 4 + 4500 * 8 + 4 * 4 + 3 * 256 * 48 + 4500 * 12 + churn * (8 + 12)
+    indexed = 4500 * 12 + 4501 * 4 + nnz * 4 + 3 * 256 * (48 + 16 + 16) + 4500 * 8 + 4 * 4
+    assert d["e2e_indexed_snapshot"]["h2d_bytes_per_step"] == indexed
+    assert d["e2e_full_snapshot"]["h2d_bytes_per_step"] == indexed + nnz * (2 + 8 - 4)
     assert d["e2e"]["d2h_bytes_per_step"] == 4500 * (2 + 8)
+    assert calls["map_apply"] == 1 and calls["map_bulk"] == 1 and calls["visible"] == 4 + 4
     assert calls["table"] == 1 and calls["indexed"] == 4 + 4 and calls["flat"] == 4 + 4
     assert d["roofline"]["kernel"] == "k_splat_tile+k_scan_sums+k_scan_compose+k_scan_walk"
     assert abs(d["roofline"]["share_of_step"] - 2.9 / 6.0) < 1e-3 and d["roofline"]["bound"] == "hbm"
@@ -433,8 +459,8 @@ def test_bench_c4_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    NT = d["config"]["points_per_step_per_gpu"]
-    assert d["config"]["workload"].startswith("C4") and d["config"]["problems_per_step_per_gpu"] == 6
+    NT = d["run_info"]["points_per_step_rank0"]
+    assert d["config"]["workload"].startswith("C4") and d["config"]["problems_per_step"] == 6 and d["scaling"] == "strong"
     assert 6 * 4000 <= NT <= 6 * 6000
     assert d["e2e"]["h2d_bytes_per_step"] == NT * (4 + 4 + 4 + 8) and d["e2e"]["d2h_bytes_per_step"] == NT * 10
     assert d["e2e_full_snapshot"] is None and calls["direct"] == 4 + 3 and calls["indexed"] == 0
