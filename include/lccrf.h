@@ -81,6 +81,12 @@ int lccrf_lattice_export(const lccrf_lattice *lat, int *offset, float *bary, int
 /* Replaces PermutohedralLatticeCPU::compute(out, in, value_size) with default windowing
  *   permutohedral_cpu.h:634-699.  in/out: [N*L]; out may alias in (pairwise3d.h:24). */
 int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L);
+/* ... with its windowing arguments (permutohedral_cpu.h:634-637): only points [in_offset, in_offset + in_size) are
+ * splatted (in: [in_size*L]) and only points [out_offset, out_offset + out_size) are sliced (out: [out_size*L]);
+ * -1 = up to the last point.  Bit-identical to the reference: a window is a zero-padded input (a running sum that
+ * starts at +0 is unchanged by +-0 addends) and a cropped output. */
+int lccrf_lattice_filter_window(lccrf_lattice *lat, float *out, const float *in, int L, int in_offset, int out_offset,
+                                int in_size, int out_size);
 
 /* ---------------------------------------------------------------- dense CRF -------------- */
 /* Replaces DenseCRF3D<M>(N) / DenseCRFCPU<M>(N)   densecrf3d.h:23-28, densecrf_cpu.h:22-27 */

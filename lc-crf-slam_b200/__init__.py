@@ -74,6 +74,7 @@ SYMBOLS = {
     "lccrf_lattice_sizes": (C.c_int, [_vp, _ip, _ip, _ip]),
     "lccrf_lattice_export": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lccrf_lattice_filter": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "lccrf_lattice_filter_window": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lccrf_crf_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lccrf_crf_destroy": (None, [_vp]),
     "lccrf_crf_set_unary": (C.c_int, [_vp, _vp]),
@@ -327,6 +328,14 @@ class Lattice:
         L = x.size // self.N if self.N else 1
         out = np.empty_like(x)
         self.ctx._check(self.ctx.lib.lccrf_lattice_filter(self.h, _ptr(out), _ptr(x), L))
+        return out
+
+    def filter_window(self, x, L, in_offset=0, out_offset=0, in_size=-1, out_size=-1) -> np.ndarray:
+        """compute() with its windowing arguments: x holds the in_size input points, the result the out_size points"""
+        x = _arr(x, np.float32)
+        n_out = self.N - out_offset if out_size == -1 else out_size
+        out = np.empty((max(n_out, 0), L), dtype=np.float32)
+        self.ctx._check(self.ctx.lib.lccrf_lattice_filter_window(self.h, _ptr(out), _ptr(x), L, in_offset, out_offset, in_size, out_size))
         return out
 
     def close(self):

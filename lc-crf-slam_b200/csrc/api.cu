@@ -485,13 +485,20 @@ int lccrf_lattice_export(const lccrf_lattice *lat, int *offset, float *bary, int
     return LCCRF_OK;
 }
 
-int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L) {
+int lccrf_lattice_filter_window(lccrf_lattice *lat, float *out, const float *in, int L, int in_offset, int out_offset,
+                                int in_size, int out_size) {
     if (!lat || !out || !in) return fail(LCCRF_ERR_ARG, "NULL argument");
     if (L < 1 || L > LCCRF_MAX_L) return fail(LCCRF_ERR_ARG, "L out of range");
+    const int N = lat->b.NT;
+    if (in_size == -1) in_size = N - in_offset;      // permutohedral_cpu.h:636-637
+    if (out_size == -1) out_size = N - out_offset;
+    if (in_offset < 0 || out_offset < 0 || in_size < 0 || out_size < 0 || (long long)in_offset + in_size > N ||
+        (long long)out_offset + out_size > N)
+        return fail(LCCRF_ERR_ARG, "filter window outside [0, N)");
     Ctx *ctx = lat->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)lat->b.NT * L;
-    if (n == 0) return LCCRF_OK;
+    const size_t n = (size_t)N * L;
+    if (n == 0 || out_size == 0) return LCCRF_OK;
     LCCRF_TRY(lattice_set_ensure_L(ctx, lat->ls, L));
     if (lat->io_bytes < 2 * n * sizeof(float)) {
         dev_free(ctx, lat->io);
@@ -501,11 +508,18 @@ int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L)
         lat->io_bytes = 2 * n * sizeof(float);
     }
     float *d_in = lat->io, *d_out = lat->io + n;
-    LCCRF_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // points outside the input window contribute products of +-0, which leave the (+0-started) vertex sums untouched
+    if (in_size != N) LCCRF_CUDA(cudaMemsetAsync(d_in, 0, n * sizeof(float), ctx->stream));
+    if (in_size > 0)
+        LCCRF_CUDA(cudaMemcpyAsync(d_in + (size_t)in_offset * L, in, (size_t)in_size * L * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     LCCRF_TRY(filter_full(ctx, lat->b, lat->ls, d_out, d_in, L));
-    LCCRF_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LCCRF_CUDA(cudaMemcpyAsync(out, d_out + (size_t)out_offset * L, (size_t)out_size * L * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
     return LCCRF_OK;
+}
+
+int lccrf_lattice_filter(lccrf_lattice *lat, float *out, const float *in, int L) {
+    return lccrf_lattice_filter_window(lat, out, in, L, 0, 0, -1, -1);
 }
 
 // ------------------------------------------------------------------ dense CRF

@@ -327,14 +327,21 @@ k_long_chunks(const int *__restrict__ row_ptr, const int *__restrict__ lng, int 
     }
 }
 
-// tile_row0[t] = the (non-empty) row that holds entry t * kTreeTile; tile_row0[n_tiles] = V - 1 (k_splat_tree)
+// tile_row0[t] = the (non-empty) row that holds entry t * kTreeTile; tile_row0[n_tiles] = V - 1 (k_splat_tree, k_splat_rows);
+// tile_own[t] != 0 iff the ordered short-row splat has work in tile t: a row shorter than kLongRow starts there, or a row
+// without entries belongs to it (same ownership rule as k_splat_rows)
 __global__ void __launch_bounds__(kThreads)
-k_tile_rows(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ tile_row0, int n_tiles) {
+k_tile_rows(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ tile_row0,
+            int *__restrict__ tile_own, int n_tiles) {
     const int V = __ldg(vtotal);
     if (blockIdx.x == 0 && threadIdx.x == 0) tile_row0[n_tiles] = V - 1;
     for (int v = blockIdx.x * kThreads + threadIdx.x; v < V; v += gridDim.x * kThreads) {
         const int s = __ldg(row_ptr + v), e = __ldg(row_ptr + v + 1);
         for (int t = (s + kTreeTile - 1) / kTreeTile; t < n_tiles && t * kTreeTile < e; t++) tile_row0[t] = v;
+        if (e - s < kLongRow && n_tiles > 0) {
+            const int t = e > s ? s / kTreeTile : (s > 0 ? (s - 1) / kTreeTile : 0);
+            tile_own[t < n_tiles ? t : n_tiles - 1] = 1;
+        }
     }
 }
 
@@ -388,6 +395,7 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     rc |= dev_alloc(ctx, (void **)&ls->piece_list, (size_t)ls->max_pieces * 4);
     ls->n_tiles = (int)(((long long)b.NT * D + kTreeTile - 1) / kTreeTile);
     rc |= dev_alloc(ctx, (void **)&ls->tile_row0, ((size_t)ls->n_tiles + 1) * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->tile_own, ((size_t)ls->n_tiles + 1) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->tile_info, ((size_t)ls->n_tiles + 1) * sizeof(int2));
     if (ls->Lmax > 0) rc |= dev_alloc(ctx, (void **)&ls->tile_part, ((size_t)ls->n_tiles + 1) * ls->Lmax * sizeof(float));
     if (rc != LCCRF_OK) return LCCRF_ERR_CUDA;
@@ -421,6 +429,7 @@ void csr_destroy(Ctx *ctx, LatticeSet *ls) {
     dev_free(ctx, ls->row_counts);
     dev_free(ctx, ls->piece_list);
     dev_free(ctx, ls->tile_row0);
+    dev_free(ctx, ls->tile_own);
     dev_free(ctx, ls->tile_info);
     dev_free(ctx, ls->tile_part);
 }
@@ -464,8 +473,9 @@ int csr_build(Ctx *ctx, const Batch &b, LatticeSet *ls) {
         k_long_chunks<<<1, 1024, 0, st>>>(ls->row_ptr, ls->row_list_long, ls->row_counts, ls->long_chunk0, (int4 *)ls->chunk_desc);
     }
     if (ls->n_tiles > 0) {
+        LCCRF_CUDA(cudaMemsetAsync(ls->tile_own, 0, (size_t)ls->n_tiles * sizeof(int), st));
         LCCRF_KERNEL(ctx, "k_tile_rows");
-        k_tile_rows<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->tile_row0, ls->n_tiles);
+        k_tile_rows<<<vgrid, kThreads, 0, st>>>(ls->row_ptr, vt, ls->tile_row0, ls->tile_own, ls->n_tiles);
     }
     LCCRF_CUDA(cudaGetLastError());
     return LCCRF_OK;

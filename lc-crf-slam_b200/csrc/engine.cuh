@@ -52,6 +52,7 @@ struct LatticeSet {
     // tree splat (option "ordered_splat" = 0): fixed tiles of kTreeTile sorted entries
     int n_tiles = 0;
     int *tile_row0 = nullptr;       // [n_tiles+1] row that holds the first entry of each tile; [n_tiles] = V-1
+    int *tile_own = nullptr;        // [n_tiles] != 0: the ordered short-row splat has rows to sum in this tile
     int2 *tile_info = nullptr;      // [n_tiles] {position of the first row start inside the tile or -1, row open at the tile's end or -1}
     float *tile_part = nullptr;     // [n_tiles*Lmax] sum of the tile's entries in front of its first row start
     // filter workspace

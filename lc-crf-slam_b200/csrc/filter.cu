@@ -642,6 +642,43 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
     ScanPair tot;
     int hi0, lo0, hi1, lo1;
     if (kind == kRecPlain) {
+        // Monotone fast path (the CRF's case: barycentric weights and marginals are >= 0): without a round-half-even tie
+        // the increment of every entry is the same for either parity, prefixes only grow, so the composite is the plain
+        // integer sum of the increments and its extreme prefixes are 0 and the total -- one block reduction instead of
+        // the pair scan with its four range trackers.  Anything else (a negative product, a tie, a quotient beyond 2^24)
+        // takes the general path below.
+        bool easy = true;
+        int inc_sum = 0;
+#pragma unroll
+        for (int q = 0; q < IT; q++) {
+            if (q < n_valid) {
+                const float qv = __fmul_rn(cq[q], inv_u);
+                easy = easy && (cq[q] >= 0.0f) && (qv < 16777216.0f);
+                const int ni = __float2int_rd(qv);
+                const float fr = __fsub_rn(qv, (float)ni);
+                easy = easy && (fr != 0.5f);
+                inc_sum += ni + (fr > 0.5f ? 1 : 0);
+            }
+        }
+        if (__syncthreads_and(easy)) {  // (uniform)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) inc_sum += __shfl_xor_sync(0xffffffffu, inc_sum, o);
+            if (lane == 0) sc.cs.bnd[wid][0] = inc_sum;
+            __syncthreads();
+            if (tid == 0) {
+                long long t8 = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) t8 += sc.cs.bnd[w][0];
+                const int tt = t8 > (1 << 25) ? (1 << 25) : (int)t8;  // beyond the binade either way: the walk rejects it
+                Composite A;
+                A.a0 = A.a1 = A.hi0 = A.hi1 = tt;
+                A.lo0 = A.lo1 = 0;
+                rec_out->kind = kRecPlain;
+                rec_out->E = E;
+                rec_out->A = A;
+            }
+            return;
+        }
         thread_composite<IT>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
         const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
         if (tid == 0) {
@@ -816,6 +853,108 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
         atomicAdd(counts + 5, n_cross);
         atomicAdd(counts + 6, n_fall);
         atomicAdd(counts + 7, n_zero);
+    }
+}
+
+// ---------------------------------------------------------------- ordered splat, short rows, by entry tiles
+// Same result as k_splat_tile (every row summed front to back), organised by fixed tiles of kTreeTile sorted entries instead
+// of pieces: a CTA owns the short rows that START in its tile and stages the tile plus the kLongRow - 1 entries a short
+// row can reach beyond it.  Phase 1: coalesced entry stream, gather in[point], products to shared memory.  Phase 2: row
+// ra + i of the tile is walked by thread i -- one FADD chain per (row, label), operands prefetched eight entries ahead so
+// that the chain runs at the adder's latency.  No row pointer staging, no atomics; rows >= kLongRow are left to the scan.
+constexpr int kRowsThreads = 256;
+constexpr int kRowsWin = kTreeTile + kLongRow;             // staged entries per tile (3072)
+constexpr int kRowsIT = kRowsWin / kRowsThreads;           // 12 entries per thread in phase 1
+
+template <int LG>
+__global__ void __launch_bounds__(kRowsThreads)
+k_splat_rows(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0, const int *__restrict__ tile_own,
+             const int2 *__restrict__ ent, const float *__restrict__ in, float *__restrict__ val, int n_tiles, long long E,
+             int L, int lb) {
+    extern __shared__ float s_rows[];  // [kRowsWin][LG] products
+    const int tid = threadIdx.x;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (!__ldg(tile_own + t)) continue;  // (uniform) only long rows here: the scan kernels' business
+        const long long t0 = (long long)t * kTreeTile;
+        const int cnt = (int)min((long long)kRowsWin - 1, E - t0);
+        const int ra = __ldg(tile_row0 + t), rb = __ldg(tile_row0 + t + 1);
+        // phase 1
+        {
+            int2 e[kRowsIT];
+#pragma unroll
+            for (int q = 0; q < kRowsIT; q++) {
+                const int i = q * kRowsThreads + tid;
+                e[q] = i < cnt ? __ldg(ent + t0 + i) : make_int2(0, 0);
+            }
+            float x[kRowsIT][LG];
+#pragma unroll
+            for (int q = 0; q < kRowsIT; q++) {
+                const int i = q * kRowsThreads + tid;
+                if (LG == 2 && L == 2) {
+                    const float2 v = i < cnt ? __ldg((const float2 *)in + e[q].x) : make_float2(0.f, 0.f);
+                    x[q][0] = v.x;
+                    x[q][LG - 1] = v.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < LG; j++) x[q][j] = (i < cnt && lb + j < L) ? __ldg(in + (size_t)e[q].x * L + lb + j) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kRowsIT; q++) {
+                const int i = q * kRowsThreads + tid;
+                const float w = __int_as_float(e[q].y);
+                if (i < cnt) {
+#pragma unroll
+                    for (int j = 0; j < LG; j++) s_rows[(size_t)i * LG + j] = __fmul_rn(w, x[q][j]);
+                }
+            }
+        }
+        __syncthreads();
+        // phase 2: rows that start in this tile
+        // (a row without entries -- a vertex only phantom points touch -- belongs to the tile its position follows)
+        for (int r = (t == 0 ? 0 : ra) + tid; r <= rb; r += kRowsThreads) {
+            const long long s = __ldg(row_ptr + r), z = __ldg(row_ptr + r + 1);
+            const bool mine = z > s ? (s >= t0 && s < t0 + kTreeTile) : ((s > t0 && s <= t0 + kTreeTile) || (s == 0 && t == 0));
+            if (!mine || z - s >= kLongRow) continue;
+            const int a = (int)(s - t0), b = (int)(z - t0);
+            float acc[LG];
+#pragma unroll
+            for (int j = 0; j < LG; j++) acc[j] = 0.0f;
+            int i = a;
+            if (i + 8 <= b) {
+                float y[8][LG], yn[8][LG];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+#pragma unroll
+                    for (int j = 0; j < LG; j++) y[q][j] = s_rows[(size_t)(i + q) * LG + j];
+                for (; i + 16 <= b; i += 8) {  // the next eight operands travel while these eight are added
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+#pragma unroll
+                        for (int j = 0; j < LG; j++) yn[q][j] = s_rows[(size_t)(i + 8 + q) * LG + j];
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+#pragma unroll
+                        for (int j = 0; j < LG; j++) acc[j] = __fadd_rn(acc[j], y[q][j]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+#pragma unroll
+                        for (int j = 0; j < LG; j++) y[q][j] = yn[q][j];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+#pragma unroll
+                    for (int j = 0; j < LG; j++) acc[j] = __fadd_rn(acc[j], y[q][j]);
+                i += 8;
+            }
+            for (; i < b; i++)
+#pragma unroll
+                for (int j = 0; j < LG; j++) acc[j] = __fadd_rn(acc[j], s_rows[(size_t)i * LG + j]);
+#pragma unroll
+            for (int j = 0; j < LG; j++)
+                if (lb + j < L) val[(size_t)r * L + lb + j] = acc[j];
+        }
+        __syncthreads();
     }
 }
 
@@ -1268,15 +1407,18 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
             k_splat_carry<<<cg, kThreads, 0, st>>>(ls->row_ptr, vt, ls->tile_info, ls->tile_part, src, ls->n_tiles, L);
         }
     } else if (b.NT > 0) {
+        const long long E = (long long)b.NT * D;
         const int LG = tile_labels(L);
-        const int grid = ls->max_pieces < kNumSMs * 8 ? ls->max_pieces : kNumSMs * 8;
-        const size_t smem = (size_t)(kTileGranule + kLongRow) * LG * sizeof(float);
-        LCCRF_TRY(ensure_dyn_smem(ctx, k_splat_tile<4>, (int)((kTileGranule + kLongRow) * 4 * sizeof(float))));
-        LCCRF_KERNEL(ctx, "k_splat_tile");
-        switch (LG) {
-            case 1: k_splat_tile<1><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
-            case 2: k_splat_tile<2><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
-            default: k_splat_tile<4><<<grid, kTileThreads, smem, st>>>(ls->row_ptr, ls->piece_list, ls->row_counts, vt, ls->csr_ent, in_dev, src, L); break;
+        const int grid = ls->n_tiles < kNumSMs * 6 ? ls->n_tiles : kNumSMs * 6;
+        const size_t smem = (size_t)kRowsWin * LG * sizeof(float);
+        LCCRF_TRY(ensure_dyn_smem(ctx, k_splat_rows<4>, (int)((size_t)kRowsWin * 4 * sizeof(float))));
+        for (int lb = 0; lb < L; lb += LG) {
+            LCCRF_KERNEL(ctx, "k_splat_rows");
+            switch (LG) {
+                case 1: k_splat_rows<1><<<grid, kRowsThreads, smem, st>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
+                case 2: k_splat_rows<2><<<grid, kRowsThreads, smem, st>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
+                default: k_splat_rows<4><<<grid, kRowsThreads, smem, st>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
+            }
         }
     }
     // long rows (>= kLongRow entries): speculative parallel scan.  The lists live on the device, so the grids are

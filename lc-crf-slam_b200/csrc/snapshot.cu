@@ -23,6 +23,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "common.cuh"
 
 namespace {
@@ -85,6 +87,27 @@ Sections sections(int N, long long nnz, int nKF, int kf_bytes) {
     return s;
 }
 
+// Walk the frame records behind the file header.  Returns the byte offset behind the last COMPLETE, well-formed record;
+// anything after it (a record the writer died in, or bytes that do not parse as a record) sets *damaged.
+uint64_t scan_records(FILE *f, uint64_t size, std::vector<FrameHeader> *hdr, std::vector<uint64_t> *at, int *damaged) {
+    uint64_t pos = sizeof(FileHeader);
+    *damaged = 0;
+    while (pos + sizeof(FrameHeader) <= size) {
+        FrameHeader h;
+        fseek(f, (long)pos, SEEK_SET);
+        if (fread(&h, sizeof(h), 1, f) != 1) break;
+        if (h.magic != kFrameMagic || h.N < 0 || h.nKF < 0 || h.nnz < 0 ||
+            h.payload_bytes != sections(h.N, h.nnz, h.nKF, (h.flags & 1) ? 2 : 4).total)
+            break;  // not a record: everything from here on is unusable, the frames before it are intact
+        if (pos + sizeof(FrameHeader) + h.payload_bytes > size) break;  // the writer died inside this frame
+        if (hdr) hdr->push_back(h);
+        if (at) at->push_back(pos + sizeof(FrameHeader));
+        pos += sizeof(FrameHeader) + h.payload_bytes;
+    }
+    if (pos != size) *damaged = 1;
+    return pos;
+}
+
 }  // namespace
 
 struct lccrf_snapshot_writer {
@@ -117,7 +140,20 @@ int lccrf_snapshot_writer_open(const char *path, int append, lccrf_snapshot_writ
                 fclose(f);
                 return fail(LCCRF_ERR_ARG, std::string(path) + ": not a version-1 LCCRFSNP file");
             }
+            // continue behind the last complete record: a tail left by a crash (partial record) is cut off, otherwise
+            // the new record would land inside the partial one's declared payload and take the file down with it
             fseek(f, 0, SEEK_END);
+            const uint64_t size = (uint64_t)ftell(f);
+            int damaged = 0;
+            const uint64_t end = scan_records(f, size, nullptr, nullptr, &damaged);
+            if (damaged) {
+                fflush(f);
+                if (ftruncate(fileno(f), (off_t)end) != 0) {
+                    fclose(f);
+                    return fail(LCCRF_ERR_STATE, std::string(path) + ": cannot cut off the incomplete tail");
+                }
+            }
+            fseek(f, (long)end, SEEK_SET);
             fresh = false;
         }
     }
@@ -223,26 +259,9 @@ int lccrf_snapshot_reader_open(const char *path, lccrf_snapshot_reader **out) {
     const uint64_t size = (uint64_t)ftell(f);
     lccrf_snapshot_reader *r = new lccrf_snapshot_reader();
     r->f = f;
-    uint64_t pos = sizeof(FileHeader);
-    while (pos + sizeof(FrameHeader) <= size) {  // index the complete records
-        FrameHeader h;
-        fseek(f, (long)pos, SEEK_SET);
-        if (fread(&h, sizeof(h), 1, f) != 1) break;
-        if (h.magic != kFrameMagic || h.N < 0 || h.nKF < 0 || h.nnz < 0 ||
-            h.payload_bytes != sections(h.N, h.nnz, h.nKF, (h.flags & 1) ? 2 : 4).total) {
-            delete r;
-            fclose(f);
-            return fail(LCCRF_ERR_ARG, std::string(path) + ": corrupt frame record at byte " + std::to_string(pos));
-        }
-        if (pos + sizeof(FrameHeader) + h.payload_bytes > size) {  // the writer died inside this frame
-            r->truncated = 1;
-            break;
-        }
-        r->hdr.push_back(h);
-        r->at.push_back(pos + sizeof(FrameHeader));
-        pos += sizeof(FrameHeader) + h.payload_bytes;
-    }
-    if (pos != size && !r->truncated) r->truncated = 1;  // a partial record header
+    // index the complete records; a damaged tail (crash inside a frame, or bytes that do not parse) ends the index and
+    // is reported through lccrf_snapshot_truncated -- the frames in front of it stay readable
+    scan_records(f, size, &r->hdr, &r->at, &r->truncated);
     *out = r;
     return LCCRF_OK;
 }

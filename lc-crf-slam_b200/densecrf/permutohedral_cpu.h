@@ -6,6 +6,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#if defined(__SSE__)
+#include <xmmintrin.h>
+#endif
 
 #include "densecrf_base.h"
 
@@ -50,15 +53,20 @@ public:
 
     void init(const float *feature, int feature_size, int N) { rebuild(feature, feature_size, N); }
 
-    // default windowing only: no caller in the reference tree passes the offset/size arguments
-    void compute(float *out, const float *in, int value_size, int in_offset = 0, int out_offset = 0,
-                 int in_size = -1, int out_size = -1) const {
-        if (in_offset != 0 || out_offset != 0 || (in_size != -1 && in_size != N_) || (out_size != -1 && out_size != N_)) {
-            std::fprintf(stderr, "lccrf: PermutohedralLatticeCPU::compute windowing is not supported\n");
-            std::abort();
-        }
-        lccrf_detail::check(lccrf_lattice_filter(lat_, out, in, value_size), "lccrf_lattice_filter");
+    // compute(out, in, value_size, in_offset, out_offset, in_size, out_size)   permutohedral_cpu.h:634-699
+    void compute(float *out, const float *in, int value_size, int in_offset = 0, int out_offset = 0, int in_size = -1,
+                 int out_size = -1) const {
+        lccrf_detail::check(lccrf_lattice_filter_window(lat_, out, in, value_size, in_offset, out_offset, in_size, out_size),
+                            "lccrf_lattice_filter_window");
     }
+#if defined(__SSE__)
+    // the __m128 overload (permutohedral_cpu.h:572-633): value_size counts vectors of four floats
+    void compute(__m128 *out, const __m128 *in, int value_size, int in_offset = 0, int out_offset = 0, int in_size = -1,
+                 int out_size = -1) const {
+        compute(reinterpret_cast<float *>(out), reinterpret_cast<const float *>(in), 4 * value_size, in_offset, out_offset,
+                in_size, out_size);
+    }
+#endif
 
     // lccrf extensions (parity tests): reference-identical arrays
     int lccrfVertices() const { return M_; }

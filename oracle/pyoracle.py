@@ -252,6 +252,8 @@ class Ref:
         L.ref_lattice_V.argtypes = [C.c_void_p]
         L.ref_lattice_export.argtypes = [C.c_void_p, c_int_p, c_float_p, c_int_p]
         L.ref_lattice_filter.argtypes = [C.c_void_p, c_float_p, c_float_p, C.c_int]
+        if hasattr(L, "ref_lattice_filter_window"):
+            L.ref_lattice_filter_window.argtypes = [C.c_void_p, c_float_p, c_float_p, C.c_int] + [C.c_int] * 4
         L.ref_crf3d.argtypes = [C.c_int, C.c_int, c_float_p, c_short_p, C.c_float, C.c_int, C.POINTER(c_float_p),
                                 c_int_p, c_float_p, C.c_int, C.c_float, c_float_p, c_short_p]
         L.ref_slam_crf.argtypes = [C.c_int, c_float_p, c_float_p, c_float_p, c_short_p] + [C.c_float] * 7 + [
@@ -280,6 +282,15 @@ class Ref:
         L = x.size // max(lat["N"], 1) if lat["N"] else 1
         out = np.empty_like(x)
         self.lib.ref_lattice_filter(lat["handle"], _fp(out), _fp(x), L)
+        return out
+
+    def filter_window(self, lat, x: np.ndarray, L: int, in_offset=0, out_offset=0, in_size=-1, out_size=-1) -> np.ndarray:
+        """PermutohedralLatticeCPU::compute with its windowing arguments (permutohedral_cpu.h:634-637): x holds the
+        in_size input points, the result the out_size output points"""
+        x = _f32(x)
+        n_out = lat["N"] - out_offset if out_size == -1 else out_size
+        out = np.empty((n_out, L), dtype=np.float32)
+        self.lib.ref_lattice_filter_window(lat["handle"], _fp(out), _fp(x), L, in_offset, out_offset, in_size, out_size)
         return out
 
     def crf3d(self, L, feats, weights, iters, unary=None, label=None, conf=0.5, relax=1.0, with_map=True):

@@ -94,6 +94,11 @@ void ref_lattice_export(void *h, int *offset, float *bary, int *nbr) {
 void ref_lattice_filter(void *h, float *out, const float *in, int L) {
     static_cast<LatticeView *>(h)->compute(out, in, L);
 }
+// the windowing arguments of PermutohedralLatticeCPU::compute (permutohedral_cpu.h:634-637)
+void ref_lattice_filter_window(void *h, float *out, const float *in, int L, int in_offset, int out_offset, int in_size,
+                               int out_size) {
+    static_cast<LatticeView *>(h)->compute(out, in, L, in_offset, out_offset, in_size, out_size);
+}
 
 // DenseCRF3D<M> + PottsPotential3D<M,d>: generic unary / features (M in {2,3,4,21})
 int ref_crf3d(int N, int M, const float *unary, const short *label, float conf, int K,

@@ -263,3 +263,25 @@ def test_random_crf_shapes_vs_compiled_reference(oracle, ref):
         assert np.array_equal(mo, mr)
 
     run()
+
+
+def test_compute_window_is_zero_padding_plus_crop(oracle, ref):
+    """PermutohedralLatticeCPU::compute's windowing arguments (permutohedral_cpu.h:634-637) on the compiled reference
+    equal the full filter of a zero-padded input, cropped -- bit for bit, signed inputs included (a vertex sum starts
+    at +0 and is unchanged by +-0 addends).  This is what lccrf_lattice_filter_window relies on."""
+    rng = np.random.default_rng(12)
+    N, d = 1501, 2
+    f = rng.normal(0, 2.0, (N, d)).astype(np.float32)
+    lr, lo = ref.lattice(f), oracle.lattice(f)
+    for L, (io, oo, isz, osz) in ((1, (0, 0, -1, -1)), (2, (100, 0, 700, -1)), (3, (0, 37, -1, 900)), (21, (500, 1400, 1001, 101)),
+                                  (2, (1500, 0, 1, 1)), (4, (0, 0, 0, -1))):
+        n_in = N - io if isz == -1 else isz
+        x = rng.normal(0, 1, (n_in, L)).astype(np.float32)
+        got = ref.filter_window(lr, x, L, io, oo, isz, osz)
+        full = np.zeros((N, L), np.float32)
+        full[io:io + n_in] = x
+        n_out = N - oo if osz == -1 else osz
+        want = oracle.filter(lo, full)[oo:oo + n_out]
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), (L, io, oo, isz, osz)
+    ref.lattice_free(lr)
+    oracle.lattice_free(lo)

@@ -65,6 +65,26 @@ def test_truncated_file_keeps_complete_frames_and_corruption_is_detected(tmp_pat
     with pkg_mod.SnapshotReader(cut) as r:
         assert len(r) == len(frames) - 1 and r.truncated
         _same(r.read(0), frames[0])
+    # appending to the cut file continues behind the last complete frame (the partial record is cut off), so the file
+    # stays readable and the new frame follows the old ones
+    with pkg_mod.SnapshotWriter(cut, append=True) as w:
+        w.write(frames[-1], frame_id=99)
+    with pkg_mod.SnapshotReader(cut) as r:
+        assert len(r) == len(frames) and not r.truncated
+        _same(r.read(len(frames) - 2), frames[-2])
+        _same(r.read(len(frames) - 1), frames[-1])
+        assert r.info(len(frames) - 1).frame_id == 99
+    # a damaged record header in the middle ends the index there: the frames in front of it stay readable
+    import struct
+    hdr_hit = bytearray(blob)
+    payload0 = struct.unpack_from("<Q", blob, 32 + 40)[0]
+    off1 = 32 + 64 + payload0                      # header of the second record
+    hdr_hit[off1] ^= 0xFF
+    hp = str(tmp_path / "hdr.snp")
+    open(hp, "wb").write(bytes(hdr_hit))
+    with pkg_mod.SnapshotReader(hp) as r:
+        assert len(r) == 1 and r.truncated
+        _same(r.read(0), frames[0])
     # a flipped payload byte fails the checksum of that frame only
     bad = bytearray(blob)
     bad[32 + 64 + 200] ^= 0x40
