@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--impl", default="lccrf", choices=["lccrf", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c2", "c5"])
     ap.add_argument("--batch", type=int, default=0, help="problems per step per GPU (0 = workload default)")
-    ap.add_argument("--splat", default="tree", choices=["tree", "ordered"],
+    ap.add_argument("--splat", default="ordered", choices=["tree", "ordered"],
                     help="tree: fixed-shape tree reduction per lattice vertex (marginals within the 1e-4 gate); "
                          "ordered: point-ordered sums, bit-identical to the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -875,6 +875,24 @@ def run_gpu_arm(args):
         barrier()
         ms = ev0.elapsed_time(ev1)
         launches = ctx.kernel_launches - l0
+        # the same device-resident loop in the other splat mode (reported beside the headline, never as `value`)
+        ms_alt = 0.0
+        if not args.no_profile:
+            ctx.set_option("ordered_splat", 0 if args.splat == "ordered" else 1)
+            for _ in range(3):
+                F.run()
+            ctx.sync()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(args.steps):
+                F.run()
+            a1.record(stream)
+            torch.cuda.synchronize()
+            ms_alt = a0.elapsed_time(a1)
+            ctx.set_option("ordered_splat", 1 if args.splat == "ordered" else 0)
+            for _ in range(2):
+                F.run()
+            ctx.sync()
         # ---- end-to-end metric: host buffers in, host results out, every step, through the pipelined C-ABI call
         # (lccrf_frames_submit_* / lccrf_frames_wait): step i+1 uploads on the copy stream while step i computes
         outs = [(out_map, out_prob)]
@@ -964,10 +982,10 @@ def run_gpu_arm(args):
         clocks = sampler.stop() if sampler else None
         for m_, p_ in outs[:min(2, args.steps)]:
             assert np.array_equal(m_, ref_map) and np.array_equal(p_.view(np.int32), ref_prob.view(np.int32))
-    t_dev = torch.tensor([ms, ms_e2e, ms_flat, ms_indexed], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([ms, ms_e2e, ms_flat, ms_indexed, ms_alt], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)  # max over ranks
-    ms, ms_e2e, ms_flat, ms_indexed = (float(x) for x in t_dev.tolist())
+    ms, ms_e2e, ms_flat, ms_indexed, ms_alt = (float(x) for x in t_dev.tolist())
     total_problems = job_problems * args.steps
     value = total_problems / (ms * 1e-3)
     e2e_value = total_problems / (ms_e2e * 1e-3)
@@ -1024,6 +1042,12 @@ def run_gpu_arm(args):
             "value": total_problems / (ms_flat * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_flat,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms_flat / args.steps,
             "inputs": "flat snapshot: every observation carries its keypoint (uint16 keyframe index + float2), nothing resident"},
+        "other_splat_mode": None if not ms_alt else {
+            "value": total_problems / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt / args.steps,
+            "splat_mode": SPLAT_MODES["tree" if args.splat == "ordered" else "ordered"],
+            "note": "device-resident loop only; at the C3 shape the tree mode deviates from the reference's marginals by up to "
+                    "~7e-3 relative (the reference's own sequential rounding over rows of 10^4..10^5 entries; "
+                    "tests/test_gpu_tree_splat.py), so it is not the headline"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "blur": blur,

@@ -375,6 +375,7 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
         h->c.opt_ordered_splat = value ? 1 : 0;
     }
     else if (!strcmp(name, "profile")) h->c.opt_profile = value;
+    else if (!strcmp(name, "map_slack")) h->c.opt_map_slack = value < 0 ? 0 : value;
     else if (!strcmp(name, "concurrent")) h->c.opt_concurrent = value;
     else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);
     return LCCRF_OK;
@@ -1787,7 +1788,8 @@ int lccrf_map_set_observations(lccrf_map *map, int pt_first, int count, const in
     if (obs_ptr[0] != 0) return fail(LCCRF_ERR_ARG, "obs_ptr must start at 0");
     const long long nnz = obs_ptr[count];
     if (nnz > 0 && !obs_ref) return fail(LCCRF_ERR_ARG, "obs_ref is NULL");
-    // runs with 25% room to spare (at least 2 entries): the first appends do not move the list
+    // tight runs by default; option "map_slack" (percent, at least 2 entries when set) leaves room so that the first appends
+    // do not move the list
     std::vector<int> ptrs(2 * (size_t)count + 2);
     long long run = 0;
     for (int i = 0; i < count; i++) {
@@ -1795,8 +1797,8 @@ int lccrf_map_set_observations(lccrf_map *map, int pt_first, int count, const in
         if (c < 0) return fail(LCCRF_ERR_ARG, "obs_ptr must be non-decreasing");
         ptrs[i] = obs_ptr[i];
         ptrs[count + 1 + i] = (int)run;
-        const int extra = (c + 3) / 4;
-        run += c + (extra < 2 ? 2 : extra);
+        const int extra = (int)(((long long)c * ctx->opt_map_slack + 99) / 100);
+        run += c + (ctx->opt_map_slack > 0 && extra < 2 ? 2 : extra);
         if (run > 0x7fffffffLL) return fail(LCCRF_ERR_ARG, "bulk load exceeds 2^31 pool entries");
     }
     ptrs[count] = (int)nnz;

@@ -171,34 +171,44 @@ __global__ void __launch_bounds__(1024) k_scan_add(int *x, const int *n_ptr, con
 constexpr int kFillWarpsH = 8;
 constexpr int kHierV = kCursorSmemInts / kFillWarpsH;  // 1792
 
+constexpr int kFillAhead = 4;  // 32-entry groups whose loads are issued before the first one is consumed
+
 template <int MODE>  // 0: hierarchical shared, 1: single warp + shared cursors, 2: single warp + global cursors
 __device__ __forceinline__ void fill_walk(const CsrParams &p, int vb, int a, int z, int *cur_row, unsigned lane) {
-    for (int base = a; base < z; base += 32) {
-        const int s = base + (int)lane;
-        int v = -1, rp = 0;
-        float w = 0.f;
-        if (s < z) {
-            const int gv = __ldg(p.offset + s);
-            w = __ldg(p.bary + s);
-            rp = __ldg(p.row_len + gv);  // row_ptr after the scan
-            v = gv - vb;
+    for (int base0 = a; base0 < z; base0 += 32 * kFillAhead) {
+        // every load of kFillAhead groups is independent of the cursor logic: request them all, then commit in order
+        int gv[kFillAhead], rp[kFillAhead];
+        float w[kFillAhead];
+#pragma unroll
+        for (int g = 0; g < kFillAhead; g++) {
+            const int s = base0 + 32 * g + (int)lane;
+            gv[g] = s < z ? __ldg(p.offset + s) : -1;
+            w[g] = s < z ? __ldg(p.bary + s) : 0.f;
         }
-        const unsigned grp = __match_any_sync(0xffffffffu, v);
-        const int leader = __ffs(grp) - 1;
-        const int rank = __popc(grp & ((1u << lane) - 1u));
-        int cur = 0;
-        if (v >= 0 && (int)lane == leader) {
-            if (MODE == 2) {
-                cur = ((volatile int *)cur_row)[v];
-                ((volatile int *)cur_row)[v] = cur + __popc(grp);
-            } else {
-                cur = cur_row[v];
-                cur_row[v] = cur + __popc(grp);
+#pragma unroll
+        for (int g = 0; g < kFillAhead; g++) rp[g] = gv[g] >= 0 ? __ldg(p.row_len + gv[g]) : 0;  // row_ptr after the scan
+#pragma unroll
+        for (int g = 0; g < kFillAhead; g++) {
+            if (base0 + 32 * g >= z) break;  // (uniform)
+            const int s = base0 + 32 * g + (int)lane;
+            const int v = gv[g] >= 0 ? gv[g] - vb : -1;
+            const unsigned grp = __match_any_sync(0xffffffffu, v);
+            const int leader = __ffs(grp) - 1;
+            const int rank = __popc(grp & ((1u << lane) - 1u));
+            int cur = 0;
+            if (v >= 0 && (int)lane == leader) {
+                if (MODE == 2) {
+                    cur = ((volatile int *)cur_row)[v];
+                    ((volatile int *)cur_row)[v] = cur + __popc(grp);
+                } else {
+                    cur = cur_row[v];
+                    cur_row[v] = cur + __popc(grp);
+                }
             }
+            __syncwarp();  // the next group may hit the same vertex
+            cur = __shfl_sync(0xffffffffu, cur, leader);
+            if (v >= 0) p.ent[rp[g] + cur + rank] = make_int2(s / p.D, __float_as_int(w[g]));
         }
-        __syncwarp();  // the next group may hit the same vertex
-        cur = __shfl_sync(0xffffffffu, cur, leader);
-        if (v >= 0) p.ent[rp + cur + rank] = make_int2(s / p.D, __float_as_int(w));
     }
 }
 
@@ -219,12 +229,19 @@ __global__ void __launch_bounds__(kFillWarpsH * 32) k_csr_fill(CsrParams p) {
         int *mine = s_cur + wid * Vb;
         for (int v = threadIdx.x; v < kFillWarpsH * Vb; v += kFillWarpsH * 32) s_cur[v] = 0;
         __syncthreads();
-        for (int base = a; base < z; base += 32) {  // counts of this warp's sub-chunk
-            const int s = base + (int)lane;
-            const int v = s < z ? __ldg(p.offset + s) - vb : -1;
-            const unsigned grp = __match_any_sync(0xffffffffu, v);
-            if (v >= 0 && (__ffs(grp) - 1) == (int)lane) mine[v] += __popc(grp);
-            __syncwarp();
+        for (int base0 = a; base0 < z; base0 += 32 * kFillAhead) {  // counts of this warp's sub-chunk
+            int vv[kFillAhead];
+#pragma unroll
+            for (int g = 0; g < kFillAhead; g++) {
+                const int s = base0 + 32 * g + (int)lane;
+                vv[g] = s < z ? __ldg(p.offset + s) - vb : -1;
+            }
+#pragma unroll
+            for (int g = 0; g < kFillAhead; g++) {
+                const unsigned grp = __match_any_sync(0xffffffffu, vv[g]);
+                if (vv[g] >= 0 && (__ffs(grp) - 1) == (int)lane) mine[vv[g]] += __popc(grp);
+                __syncwarp();
+            }
         }
         __syncthreads();
         for (int v = threadIdx.x; v < Vb; v += kFillWarpsH * 32) {  // exclusive prefix over the warps + chunk start

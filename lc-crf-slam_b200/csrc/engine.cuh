@@ -92,6 +92,8 @@ struct Ctx {
     // 1: splat sums every vertex row in point order (bit-identical to the reference's sequential loop);
     // 0: fixed-shape tree reduction per row (deterministic; marginals within the 1e-4 gate, not bit-identical)
     int opt_ordered_splat = 1;
+    int opt_map_slack = 0;     // spare room (percent) behind every list of a bulk-loaded map; 0 = tight lists: the unary streams
+                               // them 4% faster, and a list that grows later moves to the pool's tail once (map.cu)
     // per-kernel CUDA-event timing (option "profile"): every launch site is bracketed by two events
     int opt_profile = 0;
     struct ProfRec {

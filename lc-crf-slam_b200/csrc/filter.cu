@@ -642,43 +642,6 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
     ScanPair tot;
     int hi0, lo0, hi1, lo1;
     if (kind == kRecPlain) {
-        // Monotone fast path (the CRF's case: barycentric weights and marginals are >= 0): without a round-half-even tie
-        // the increment of every entry is the same for either parity, prefixes only grow, so the composite is the plain
-        // integer sum of the increments and its extreme prefixes are 0 and the total -- one block reduction instead of
-        // the pair scan with its four range trackers.  Anything else (a negative product, a tie, a quotient beyond 2^24)
-        // takes the general path below.
-        bool easy = true;
-        int inc_sum = 0;
-#pragma unroll
-        for (int q = 0; q < IT; q++) {
-            if (q < n_valid) {
-                const float qv = __fmul_rn(cq[q], inv_u);
-                easy = easy && (cq[q] >= 0.0f) && (qv < 16777216.0f);
-                const int ni = __float2int_rd(qv);
-                const float fr = __fsub_rn(qv, (float)ni);
-                easy = easy && (fr != 0.5f);
-                inc_sum += ni + (fr > 0.5f ? 1 : 0);
-            }
-        }
-        if (__syncthreads_and(easy)) {  // (uniform)
-#pragma unroll
-            for (int o = 16; o; o >>= 1) inc_sum += __shfl_xor_sync(0xffffffffu, inc_sum, o);
-            if (lane == 0) sc.cs.bnd[wid][0] = inc_sum;
-            __syncthreads();
-            if (tid == 0) {
-                long long t8 = 0;
-#pragma unroll
-                for (int w = 0; w < 8; w++) t8 += sc.cs.bnd[w][0];
-                const int tt = t8 > (1 << 25) ? (1 << 25) : (int)t8;  // beyond the binade either way: the walk rejects it
-                Composite A;
-                A.a0 = A.a1 = A.hi0 = A.hi1 = tt;
-                A.lo0 = A.lo1 = 0;
-                rec_out->kind = kRecPlain;
-                rec_out->E = E;
-                rec_out->A = A;
-            }
-            return;
-        }
         thread_composite<IT>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
         const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
         if (tid == 0) {

@@ -109,8 +109,8 @@ def test_tree_slam_crf_gates(pkg, tree_ctx, oracle, N):
     print("tree splat N=%d: max rel marginal err %.3e (gate %.0e), MAP near-tie flips %d" % (N, worst, REL_TOL, flips))
 
 
-def test_tree_frames_batch_and_c3_pipeline(pkg, tree_ctx, oracle):
-    """the batched engine (C4 shape) and the map-snapshot pipeline (C3 shape, 20000 x 64) in tolerance mode; graphs on"""
+def test_tree_frames_batch(pkg, tree_ctx, oracle):
+    """the batched engine (C4 shape, graphs on) in tolerance mode: the 1e-4 gate and the near-tie rule hold"""
     ctx = tree_ctx
     prm_o, prm = oracle_params(), pkg.SlamParams.make()
     en = pkg.label_energies(2, prm.confidence)
@@ -131,25 +131,60 @@ def test_tree_frames_batch_and_c3_pipeline(pkg, tree_ctx, oracle):
             worst = max(worst, assert_marginals(pr[o:o + fr.n], Qo))
             assert_map(mp[o:o + fr.n], mo, Qo)
         o += fr.n
+    print("tree splat, batched frames: max rel marginal err %.3e" % worst)
     F.close()
-    snaps = [synth.map_snapshot(20000, 64, seed=70 + i) for i in range(2)]
-    cat2 = pkg.concat_frames(snaps)
-    F = pkg.Frames(ctx, [s.n for s in snaps], prm, en)
-    F.set_map_inputs(cat2["xyz"], cat2["obs_ptr"], cat2["obs_kf"], cat2["obs_uv"], cat2["kf_pose"], cat2["kf_intr"],
-                     cat2["kf_bounds"], cat2["kp2d"], cat2["kf_ptr"])
+
+
+def filter_f64(lat, x):
+    """splat / blur / slice of permutohedral_cpu.h:634-699 in double precision on the oracle's lattice arrays"""
+    off, bary, nbr, V, d = lat["offset"], lat["bary"].astype(np.float64), lat["nbr"], lat["V"], lat["d"]
+    val = np.zeros((V + 1, x.shape[1]))           # row V stands for an absent neighbour (-1)
+    for r in range(d + 1):
+        np.add.at(val, off[:, r], bary[:, r, None] * x.astype(np.float64))
+    for j in range(d + 1):
+        n1, n2 = nbr[j, :, 0], nbr[j, :, 1]
+        new = val.copy()
+        new[:V] = val[:V] + 0.5 * (val[np.where(n1 < 0, V, n1)] + val[np.where(n2 < 0, V, n2)])
+        val = new
+    alpha = 1.0 / (1.0 + 2.0 ** -d)
+    return sum((bary[:, r, None] * alpha) * val[off[:, r]] for r in range(d + 1))
+
+
+def test_tree_c3_shape_is_outside_the_gate_because_the_reference_rounds(pkg, tree_ctx, oracle):
+    """The C3 shape (every point has 64 observations, so the appearance lattice has ~30 vertices with rows of 10^4..10^5
+    entries) is where the tolerance mode does NOT meet north_star's 1e-4 against the reference -- and why: the
+    reference's own sequential fp32 sum over such a row is 1e-4..1e-3 away from the exact sum, the tree sum 1e-7.
+    Matching the reference there means reproducing its rounding, which is what the ordered kernels do (default mode;
+    bench.py's headline).  This test pins both facts: filter error against a float64 evaluation, and the resulting
+    marginal deviation of the whole pipeline, reported and bounded."""
+    ctx = tree_ctx
+    prm_o, prm = oracle_params(), pkg.SlamParams.make()
+    en = pkg.label_energies(2, prm.confidence)
+    snap = synth.map_snapshot(20000, 64, seed=70)
+    ob, er, de = oracle.map_point_unary(snap)
+    feat = np.stack([ob / np.float32(prm.stdev_beta), er / np.float32(prm.stdev_alpha)], 1).astype(np.float32)
+    lo, lg = oracle.lattice(feat), pkg.Lattice(ctx, feat)
+    x = np.random.default_rng(2).random((snap.n, 2)).astype(np.float32)
+    truth = filter_f64(lo, x)
+    e_ref = float((np.abs(oracle.filter(lo, x) - truth) / np.abs(truth)).max())
+    e_tree = float((np.abs(lg.filter(x) - truth) / np.abs(truth)).max())
+    print("C3-shaped appearance lattice (V=%d): filter error vs float64: reference order %.2e, tree %.2e" % (lo["V"], e_ref, e_tree))
+    assert e_tree < 2e-6 and e_tree < e_ref
+    oracle.lattice_free(lo)
+    lg.close()
+    F = pkg.Frames(ctx, [snap.n], prm, en)
+    F.set_map_inputs(snap.xyz, snap.obs_ptr, snap.obs_kf, snap.obs_uv, snap.kf_pose, snap.kf_intr, snap.kf_bounds, snap.kp2d)
     F.run()
     F.run()
     mp, pr = F.get_outputs()
-    dbg = F.get_debug()
-    o = 0
-    for s in snaps:
-        ob, er, de = oracle.map_point_unary(s)
-        lab = dbg["init_label"][o:o + s.n]
-        Qo, mo, _ = oracle.slam_crf(ob, er, s.kp2d, lab, en, prm_o)
-        worst = max(worst, assert_marginals(pr[o:o + s.n], Qo))
-        assert_map(mp[o:o + s.n], mo, Qo)
-        o += s.n
-    print("tree splat, batched frames + C3 pipeline: max rel marginal err %.3e" % worst)
+    lab = F.get_debug()["init_label"]
+    Qo, mo, _ = oracle.slam_crf(ob, er, snap.kp2d, lab, en, prm_o)
+    dev = float(rel_err(pr, Qo).max())
+    diff = np.nonzero(mp != mo)[0]
+    gap = np.abs(Qo[diff, 0] - Qo[diff, 1]) if diff.size else np.zeros(0)
+    print("C3 pipeline (20000 x 64), tree splat vs reference order: max rel marginal deviation %.2e (gate %.0e); "
+          "%d MAP differences, largest |dQ| among them %.2e" % (dev, REL_TOL, diff.size, gap.max() if diff.size else 0.0))
+    assert np.isfinite(pr).all() and dev < 5e-2 and (gap < 2e-2).all()
     F.close()
 
 
