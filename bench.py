@@ -295,8 +295,8 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------- GPU arm
 # Kernels that together implement one stage are timed as a group (one "launch" of the group = one launch of its
-# first kernel): the ordered splat runs as k_splat_tile (short rows) + k_scan_sums/compose/walk (long rows) per filter call.
-KERNEL_GROUPS = {"splat": ("k_splat_tile", "k_scan_sums", "k_scan_compose", "k_scan_walk"),
+# first kernel): the ordered splat runs as k_splat_rows (short rows) + k_scan_sums/compose/walk (long rows) per filter call.
+KERNEL_GROUPS = {"splat": ("k_splat_rows", "k_scan_sums", "k_scan_compose", "k_scan_walk"),
                  "splat_tree": ("k_splat_tree", "k_splat_carry")}
 
 
@@ -365,7 +365,9 @@ def profile_kernels(ctx, F, NT, nnz, nKF, iters, peak, peak_src, nprof=3):
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         members_t = KERNEL_GROUPS.get(top, (top,))
-        vals = [tj.get(m) for m in members_t if tj.get(m) is not None] if top not in tj else [tj[top]]
+        def look(name):  # LCCRF_KERNEL names are prefixes of the template names ncu reports (k_mf_point_l2 -> k_mf_point_l2_k2)
+            return tj.get(name, next((v for k_, v in tj.items() if not k_.startswith("_") and k_.startswith(name)), None))
+        vals = [look(m) for m in members_t if look(m) is not None]
         if vals and tj.get("_captured_points_per_step") == NT:  # only a capture of exactly this step counts
             traffic, traffic_src = float(sum(vals)), tj.get("_source")
     members = KERNEL_GROUPS.get(top, (top,))
@@ -373,7 +375,7 @@ def profile_kernels(ctx, F, NT, nnz, nKF, iters, peak, peak_src, nprof=3):
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "share_of_step": shares[top],
                 "achieved_gbs_all_kernels": rl_all,
                 "note": "per-kernel CUDA events on the launching stream, concurrency and graphs off while profiling"}
-    if ab is not None:
+    if ab is not None and cnt:
         per_launch_ms = tms / cnt
         ach = ab / (per_launch_ms * 1e-3) / 1e9
         roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": per_launch_ms})
@@ -397,26 +399,31 @@ def blur_measurements(pkg, ctx, peak):
             rng = np.random.default_rng(7)
             for L in Ls:
                 x = rng.random((W * H, L), dtype=np.float32)
-                lat.filter(x)  # warm-up (workspace allocation for this L)
-                ctx.set_option("profile", 1)
-                ctx.profile_report()
-                for _ in range(3):
-                    lat.filter(x)
-                rep = ctx.profile_report()
-                ctx.set_option("profile", 0)
-                cnt, tms = rep.get("k_blur", (0, 0.0))
-                if not cnt:
-                    continue
-                per_pass = lat.V * (8 * L + 8)
-                gbs = per_pass / (tms / cnt * 1e-3) / 1e9
-                out.append({"lattice": name, "V": int(lat.V), "L": L, "kernel": "k_blur_vec", "launches": cnt,
-                            "avg_launch_ms": round(tms / cnt, 5), "algorithmic_bytes_per_launch": per_pass,
-                            "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
-                            "residency": "HBM (working set %.0f MB per pass)" % (per_pass / 1e6) if per_pass > 126e6 else
-                                         "cache-resident (working set %.1f MB per pass < 126 MB L2): not an HBM figure" % (per_pass / 1e6)})
+                # L = 2 / 4: streams through the bulk-copy engine (k_blur_bulk, default) and, for comparison, plain loads
+                for kernel, bulk in ((("k_blur_bulk", 1), ("k_blur_vec", 0)) if L in (2, 4) else (("k_blur_vec", 0),)):
+                    ctx.set_option("bulk_blur", bulk)
+                    lat.filter(x)  # warm-up (workspace allocation for this L)
+                    ctx.set_option("profile", 1)
+                    ctx.profile_report()
+                    for _ in range(3):
+                        lat.filter(x)
+                    rep = ctx.profile_report()
+                    ctx.set_option("profile", 0)
+                    cnt, tms = rep.get("k_blur", (0, 0.0))
+                    if not cnt:
+                        continue
+                    per_pass = lat.V * (8 * L + 8)
+                    gbs = per_pass / (tms / cnt * 1e-3) / 1e9
+                    out.append({"lattice": name, "V": int(lat.V), "L": L, "kernel": kernel, "launches": cnt,
+                                "avg_launch_ms": round(tms / cnt, 5), "algorithmic_bytes_per_launch": per_pass,
+                                "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                                "residency": "HBM (working set %.0f MB per pass)" % (per_pass / 1e6) if per_pass > 126e6 else
+                                             "cache-resident (working set %.1f MB per pass < 126 MB L2): not an HBM figure" % (per_pass / 1e6)})
+                ctx.set_option("bulk_blur", 1)
             lat.close()
         except Exception as e:  # a stress shape must never take the headline line down with it
             ctx.set_option("profile", 0)
+            ctx.set_option("bulk_blur", 1)
             out.append({"lattice": name, "error": str(e)[:200]})
     return out
 
@@ -1004,6 +1011,20 @@ def run_gpu_arm(args):
             upload()  # profile the input variant `value` was timed on (the end-to-end loops left theirs in the slots)
             F.run()
             roofline, shares, kernel_ms = profile_kernels(ctx, F, NT, nnz, nKF, prm.iters, peak, peak_src)
+    delta_ms = None
+    if not args.no_profile and args.workload == "c3":
+        # what the map delta of one end-to-end step costs on the device (per-kernel CUDA events)
+        with torch.cuda.stream(stream):
+            ctx.set_option("profile", 1)
+            ctx.profile_report()
+            for q in range(2):
+                F.set_visible(mp, host["ids"], host["kp2d"], delta=deltas[q], kf_ptr=host["kf_ptr"])
+            rep = ctx.profile_report()
+            ctx.set_option("profile", 0)
+            upload()
+            F.run()
+        delta_ms = {k: round(v[1] / max(v[0], 1), 5) for k, v in rep.items() if k.startswith("k_map_")}
+        delta_ms["sum_per_step"] = round(sum(v[1] for k, v in rep.items() if k.startswith("k_map_")) / 2, 5)
     blur = None
     if not args.no_profile and world == 1:
         with torch.cuda.stream(stream):
@@ -1042,6 +1063,7 @@ def run_gpu_arm(args):
             "value": total_problems / (ms_flat * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_flat,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms_flat / args.steps,
             "inputs": "flat snapshot: every observation carries its keypoint (uint16 keyframe index + float2), nothing resident"},
+        "map_delta_kernel_ms": delta_ms,
         "other_splat_mode": None if not ms_alt else {
             "value": total_problems / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt / args.steps,
             "splat_mode": SPLAT_MODES["tree" if args.splat == "ordered" else "ordered"],

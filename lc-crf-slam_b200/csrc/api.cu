@@ -232,6 +232,7 @@ struct FrameInputs {
     int *part_dyn_ptr = nullptr, *part_dyn = nullptr, *part_stat_ptr = nullptr, *part_stat = nullptr;
     bool have_inputs = false;
     cudaGraphExec_t graph = nullptr;
+    int same_shape_runs = 0;  // runs since the launch sequence of this slot last changed shape (a graph is captured on the 2nd)
     uint64_t graph_launches = 0, graph_gen = 0, kp_gen = 0;
     cudaEvent_t up_done = nullptr, run_done = nullptr, out_done = nullptr;
     int *h_status = nullptr;  // pinned copy of the device status word taken after this slot's run
@@ -376,6 +377,10 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
     }
     else if (!strcmp(name, "profile")) h->c.opt_profile = value;
     else if (!strcmp(name, "map_slack")) h->c.opt_map_slack = value < 0 ? 0 : value;
+    else if (!strcmp(name, "bulk_blur")) {
+        if (h->c.opt_bulk_blur != (value ? 1 : 0)) h->c.scratch_gen++;
+        h->c.opt_bulk_blur = value ? 1 : 0;
+    }
     else if (!strcmp(name, "concurrent")) h->c.opt_concurrent = value;
     else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);
     return LCCRF_OK;
@@ -1017,6 +1022,7 @@ int lccrf_frames_create(lccrf_ctx *h, int B, const int *prob_ptr, const lccrf_sl
 static void frame_inputs_drop_graph(FrameInputs &in) {
     if (in.graph) cudaGraphExecDestroy(in.graph);
     in.graph = nullptr;
+    in.same_shape_runs = 0;
 }
 
 static void frame_inputs_release(Ctx *ctx, FrameInputs &in) {
@@ -1331,6 +1337,15 @@ static int frames_run_slot(lccrf_frames *fr, FrameInputs &in) {
         frame_inputs_drop_graph(in);
         in.kp_gen = fr->kp_gen;
     }
+    if (!in.graph && in.same_shape_runs == 0) {
+        // A new shape (observation count, keyframe count, camera model, buffers): plain launches, no synchronisation.
+        // In live SLAM these change every frame; a graph is only worth capturing for a shape that repeats (replay), so
+        // the capture waits for the second run of the same shape.
+        in.same_shape_runs = 1;
+        LCCRF_TRY(frames_enqueue(fr, in));
+        fr->ran = true;
+        return LCCRF_OK;
+    }
     if (!in.graph) {
         // make sure every scratch buffer has its final size before capture (no allocation inside the graph)
         const uint64_t l0 = ctx->launches;
@@ -1411,8 +1426,8 @@ static int frames_submit_epilogue(lccrf_frames *fr, int slot, FrameInputs &in, s
     Ctx *ctx = fr->ctx;
     LCCRF_CUDA(cudaEventRecord(in.up_done, ctx->copy_stream));
     LCCRF_CUDA(cudaStreamWaitEvent(ctx->stream, in.up_done, 0));
-    if (!in.graph && ctx->opt_graphs && !ctx->opt_profile) {
-        // first use of the slot: the capture pass synchronises; make sure the upload has landed first
+    if (!in.graph && in.same_shape_runs > 0 && ctx->opt_graphs && !ctx->opt_profile) {
+        // the capture pass synchronises; make sure the upload has landed first
         LCCRF_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     }
     LCCRF_TRY(frames_run_slot(fr, in));

@@ -92,6 +92,7 @@ struct Ctx {
     // 1: splat sums every vertex row in point order (bit-identical to the reference's sequential loop);
     // 0: fixed-shape tree reduction per row (deterministic; marginals within the 1e-4 gate, not bit-identical)
     int opt_ordered_splat = 1;
+    int opt_bulk_blur = 1;     // element-parallel blur: stream neighbour pairs / own values with cp.async.bulk (0: plain loads)
     int opt_map_slack = 0;     // spare room (percent) behind every list of a bulk-loaded map; 0 = tight lists: the unary streams
                                // them 4% faster, and a list that grows later moves to the pool's tail once (map.cu)
     // per-kernel CUDA-event timing (option "profile"): every launch site is bracketed by two events
@@ -178,6 +179,17 @@ inline int ensure_dyn_smem(Ctx *ctx, Kernel *kernel, int bytes) {
     for (const void *k : ctx->smem_attr_done)
         if (k == key) return LCCRF_OK;
     LCCRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->smem_attr_done.push_back(key);
+    return LCCRF_OK;
+}
+
+// ask for the largest shared-memory carve-out for a kernel whose residency is bounded by shared memory (once per context)
+template <typename Kernel>
+inline int prefer_smem(Ctx *ctx, Kernel *kernel) {
+    const void *key = (const void *)((const char *)kernel + 1);  // distinct from the ensure_dyn_smem key of the same kernel
+    for (const void *k : ctx->smem_attr_done)
+        if (k == key) return LCCRF_OK;
+    LCCRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ctx->smem_attr_done.push_back(key);
     return LCCRF_OK;
 }

@@ -830,7 +830,7 @@ constexpr int kRowsWin = kTreeTile + kLongRow;             // staged entries per
 constexpr int kRowsIT = kRowsWin / kRowsThreads;           // 12 entries per thread in phase 1
 
 template <int LG>
-__global__ void __launch_bounds__(kRowsThreads)
+__global__ void __launch_bounds__(kRowsThreads, LG <= 2 ? 6 : 3)
 k_splat_rows(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0, const int *__restrict__ tile_own,
              const int2 *__restrict__ ent, const float *__restrict__ in, float *__restrict__ val, int n_tiles, long long E,
              int L, int lb) {
@@ -841,18 +841,20 @@ k_splat_rows(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0,
         const long long t0 = (long long)t * kTreeTile;
         const int cnt = (int)min((long long)kRowsWin - 1, E - t0);
         const int ra = __ldg(tile_row0 + t), rb = __ldg(tile_row0 + t + 1);
-        // phase 1
-        {
-            int2 e[kRowsIT];
+        // phase 1, in two halves (register budget: 6 CTAs per SM keep enough chains in flight to hide their latency)
+        constexpr int kHalf = kRowsIT / 2;
 #pragma unroll
-            for (int q = 0; q < kRowsIT; q++) {
-                const int i = q * kRowsThreads + tid;
+        for (int h = 0; h < 2; h++) {
+            int2 e[kHalf];
+#pragma unroll
+            for (int q = 0; q < kHalf; q++) {
+                const int i = (h * kHalf + q) * kRowsThreads + tid;
                 e[q] = i < cnt ? __ldg(ent + t0 + i) : make_int2(0, 0);
             }
-            float x[kRowsIT][LG];
+            float x[kHalf][LG];
 #pragma unroll
-            for (int q = 0; q < kRowsIT; q++) {
-                const int i = q * kRowsThreads + tid;
+            for (int q = 0; q < kHalf; q++) {
+                const int i = (h * kHalf + q) * kRowsThreads + tid;
                 if (LG == 2 && L == 2) {
                     const float2 v = i < cnt ? __ldg((const float2 *)in + e[q].x) : make_float2(0.f, 0.f);
                     x[q][0] = v.x;
@@ -863,8 +865,8 @@ k_splat_rows(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0,
                 }
             }
 #pragma unroll
-            for (int q = 0; q < kRowsIT; q++) {
-                const int i = q * kRowsThreads + tid;
+            for (int q = 0; q < kHalf; q++) {
+                const int i = (h * kHalf + q) * kRowsThreads + tid;
                 const float w = __int_as_float(e[q].y);
                 if (i < cnt) {
 #pragma unroll
@@ -884,31 +886,23 @@ k_splat_rows(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0,
 #pragma unroll
             for (int j = 0; j < LG; j++) acc[j] = 0.0f;
             int i = a;
-            if (i + 8 <= b) {
-                float y[8][LG], yn[8][LG];
+            for (; i + 4 <= b; i += 4) {  // four operands per label in flight, then the ordered chain
+                float y[4][LG];
 #pragma unroll
-                for (int q = 0; q < 8; q++)
+                for (int q = 0; q < 4; q++) {
+                    if (LG == 2) {
+                        const float2 v = *(const float2 *)(s_rows + (size_t)(i + q) * 2);
+                        y[q][0] = v.x;
+                        y[q][LG - 1] = v.y;
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < LG; j++) y[q][j] = s_rows[(size_t)(i + q) * LG + j];
-                for (; i + 16 <= b; i += 8) {  // the next eight operands travel while these eight are added
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-#pragma unroll
-                        for (int j = 0; j < LG; j++) yn[q][j] = s_rows[(size_t)(i + 8 + q) * LG + j];
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-#pragma unroll
-                        for (int j = 0; j < LG; j++) acc[j] = __fadd_rn(acc[j], y[q][j]);
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-#pragma unroll
-                        for (int j = 0; j < LG; j++) y[q][j] = yn[q][j];
+                        for (int j = 0; j < LG; j++) y[q][j] = s_rows[(size_t)(i + q) * LG + j];
+                    }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; q++)
+                for (int q = 0; q < 4; q++)
 #pragma unroll
                     for (int j = 0; j < LG; j++) acc[j] = __fadd_rn(acc[j], y[q][j]);
-                i += 8;
             }
             for (; i < b; i++)
 #pragma unroll
@@ -1231,6 +1225,100 @@ k_blur_vec(const int2 *__restrict__ nbr_j, const VT *__restrict__ src, VT *__res
     }
 }
 
+// ---- the same pass with its two STREAMS -- the neighbour pairs and the vertices' own values -- brought into shared
+// memory by the bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP) through a ring
+// of kBulkStages tiles, so that the LSU and the registers only carry the two dependent neighbour gathers and the result.
+// Tiles of kBulkTV vertices; one elected thread arms the stage's barrier with the byte count and issues both copies,
+// every thread waits on the barrier's phase, consumes, and the block barrier behind the tile frees the stage.
+// VT = float2 (L = 2) or float4 (L = 4): one vector per vertex.  The tail (V % kBulkTV) takes plain loads.
+constexpr int kBulkTV = 1024, kBulkStages = 3, kBulkThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(kBulkThreads)
+k_blur_bulk(const int2 *__restrict__ nbr_j, const VT *__restrict__ src, VT *__restrict__ dst, const int *__restrict__ vtotal) {
+    extern __shared__ __align__(128) unsigned char s_bulk[];
+    __shared__ __align__(8) uint64_t s_bar[kBulkStages];
+    int2 *s_nb = (int2 *)s_bulk;                                                   // [stages][kBulkTV]
+    VT *s_own = (VT *)(s_bulk + (size_t)kBulkStages * kBulkTV * sizeof(int2));     // [stages][kBulkTV]
+    const int tid = threadIdx.x;
+    const int V = __ldg(vtotal);
+    const int n_full = V / kBulkTV;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kBulkStages; s++) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int k) {  // thread 0: tile k of this CTA into stage k % kBulkStages
+        const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+        if (tile >= n_full) return;
+        const int s = k % kBulkStages;
+        mbar_expect_tx(&s_bar[s], (uint32_t)(kBulkTV * (sizeof(int2) + sizeof(VT))));
+        bulk_g2s(s_nb + (size_t)s * kBulkTV, nbr_j + tile * kBulkTV, (uint32_t)(kBulkTV * sizeof(int2)), &s_bar[s]);
+        bulk_g2s(s_own + (size_t)s * kBulkTV, src + tile * kBulkTV, (uint32_t)(kBulkTV * sizeof(VT)), &s_bar[s]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kBulkStages; k++) issue(k);
+    for (int k = 0;; k++) {
+        const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+        if (tile >= n_full) break;
+        const int s = k % kBulkStages;
+        mbar_wait(&s_bar[s], (uint32_t)((k / kBulkStages) & 1));
+        constexpr int U = kBulkTV / kBulkThreads;
+        int2 nb[U];
+        VT o[U], a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            nb[u] = s_nb[(size_t)s * kBulkTV + u * kBulkThreads + tid];
+            o[u] = s_own[(size_t)s * kBulkTV + u * kBulkThreads + tid];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            a[u] = nb[u].x >= 0 ? __ldg(src + nb[u].x) : BlurVec<VT>::zero();
+            b[u] = nb[u].y >= 0 ? __ldg(src + nb[u].y) : BlurVec<VT>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) __stcs(dst + tile * kBulkTV + u * kBulkThreads + tid, BlurVec<VT>::comb(o[u], a[u], b[u]));
+        __syncthreads();  // stage s is consumed
+        if (tid == 0) issue(k + kBulkStages);
+    }
+    // tail
+    for (long long t = (long long)n_full * kBulkTV + (long long)blockIdx.x * kBulkThreads + tid; t < V; t += (long long)gridDim.x * kBulkThreads) {
+        const int2 nbv = __ldg(nbr_j + t);
+        const VT ov = __ldg(src + t);
+        const VT av = nbv.x >= 0 ? __ldg(src + nbv.x) : BlurVec<VT>::zero();
+        const VT bv = nbv.y >= 0 ? __ldg(src + nbv.y) : BlurVec<VT>::zero();
+        __stcs(dst + t, BlurVec<VT>::comb(ov, av, bv));
+    }
+}
+
 // all D blur passes of one problem inside one CTA: replaces D launch-bound passes when a batch holds several
 // problems or the lattice is small.  When values (ping-pong) AND the problem's D neighbour tables fit shared memory
 // everything is fetched in one round of independent global loads and the passes run from shared memory; otherwise
@@ -1372,9 +1460,11 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     } else if (b.NT > 0) {
         const long long E = (long long)b.NT * D;
         const int LG = tile_labels(L);
-        const int grid = ls->n_tiles < kNumSMs * 6 ? ls->n_tiles : kNumSMs * 6;
+        const int grid = ls->n_tiles < kNumSMs * 12 ? ls->n_tiles : kNumSMs * 12;
         const size_t smem = (size_t)kRowsWin * LG * sizeof(float);
         LCCRF_TRY(ensure_dyn_smem(ctx, k_splat_rows<4>, (int)((size_t)kRowsWin * 4 * sizeof(float))));
+        LCCRF_TRY(prefer_smem(ctx, k_splat_rows<1>));
+        LCCRF_TRY(prefer_smem(ctx, k_splat_rows<2>));
         for (int lb = 0; lb < L; lb += LG) {
             LCCRF_KERNEL(ctx, "k_splat_rows");
             switch (LG) {
@@ -1419,7 +1509,22 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     const int bgrid = persistent_grid(((long long)ls->Vcap * G + kBlurU - 1) / kBlurU, kThreads, 8);
     for (int j = 0; j < D; j++) {
         const int2 *nb = ls->nbr + (size_t)j * ls->Vcap;
-        {
+        const bool bulk = ctx->opt_bulk_blur && G == 1 && (W == 2 || W == 4) && (((size_t)nb & 15) == 0);
+        if (bulk) {
+            // streams through the bulk-copy engine (UBLKCP); 16-byte aligned neighbour tables (Vcap is even)
+            const size_t smem = (size_t)kBulkStages * kBulkTV * (sizeof(int2) + (W == 2 ? sizeof(float2) : sizeof(float4)));
+            const int per_sm = W == 2 ? 4 : 3;
+            const long long tiles = (long long)ls->Vcap / kBulkTV + 1;
+            const int grid = (int)(tiles < (long long)kNumSMs * per_sm ? tiles : (long long)kNumSMs * per_sm);
+            LCCRF_KERNEL(ctx, "k_blur");
+            if (W == 2) {
+                LCCRF_TRY(ensure_dyn_smem(ctx, k_blur_bulk<float2>, (int)smem));
+                k_blur_bulk<float2><<<grid, kBulkThreads, smem, st>>>(nb, (const float2 *)src, (float2 *)dst, vt);
+            } else {
+                LCCRF_TRY(ensure_dyn_smem(ctx, k_blur_bulk<float4>, (int)smem));
+                k_blur_bulk<float4><<<grid, kBulkThreads, smem, st>>>(nb, (const float4 *)src, (float4 *)dst, vt);
+            }
+        } else {
             LCCRF_KERNEL(ctx, "k_blur");
             if (W == 4) k_blur_vec<float4><<<bgrid, kThreads, 0, st>>>(nb, (const float4 *)src, (float4 *)dst, vt, G);
             else if (W == 2) k_blur_vec<float2><<<bgrid, kThreads, 0, st>>>(nb, (const float2 *)src, (float2 *)dst, vt, G);

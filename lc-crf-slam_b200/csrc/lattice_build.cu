@@ -402,7 +402,7 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
         delete ls;
         return fail(LCCRF_ERR_ARG, "batch too large: (NT + B) * (d+1) must stay below 2^30");
     }
-    ls->Vcap = (int)vcap;
+    ls->Vcap = (int)((vcap + 1) & ~1LL);  // even: the D neighbour tables [D][Vcap] int2 start at 16-byte multiples (bulk copies)
     const size_t nent = (size_t)(b.NT > 0 ? b.NT : 1) * ls->D;
     int rc = LCCRF_OK;
     rc |= dev_alloc(ctx, (void **)&ls->offset, nent * sizeof(int));

@@ -94,6 +94,20 @@ __device__ __forceinline__ bool claim_point(const PoolArgs &a, int p) {
     return true;
 }
 
+// position of keyframe k in a list of c entries (c if absent); eight independent loads per step instead of a
+// dependent chain of c
+__device__ __forceinline__ int find_keyframe(const int *__restrict__ list, int c, int k) {
+    for (int j = 0; j < c; j += 8) {
+        int v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = j + q < c ? list[j + q] : ~k;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (v[q] == k) return j + q;
+    }
+    return c;
+}
+
 // MapPoint::EraseObservation(pKF), src/MapPoint.cc:111-141: the entry of keyframe kf leaves the list, the rest closes up
 __global__ void __launch_bounds__(kThreads)
 k_map_erase(PoolArgs a, const int *__restrict__ pt, const int *__restrict__ kf, int n) {
@@ -102,9 +116,9 @@ k_map_erase(PoolArgs a, const int *__restrict__ pt, const int *__restrict__ kf, 
     const int p = __ldg(pt + i), k = __ldg(kf + i);
     if (!claim_point(a, p)) return;
     const int s = a.pt_start[p], c = a.pt_cnt[p];
-    int j = 0;
-    while (j < c && a.pool_kf[s + j] != k) j++;
-    if (j == c) return;  // :116 no such observation
+    const int j0 = find_keyframe(a.pool_kf + s, c, k);
+    if (j0 == c) return;  // :116 no such observation
+    int j = j0;
     for (; j + 1 < c; j++) {
         a.pool_kf[s + j] = a.pool_kf[s + j + 1];
         a.pool_uv[s + j] = a.pool_uv[s + j + 1];
@@ -140,8 +154,7 @@ k_map_add(PoolArgs a, const int *__restrict__ pt, const int *__restrict__ kf, co
     if (!claim_point(a, p)) return;
     int s = a.pt_start[p];
     const int c = a.pt_cnt[p], room = a.pt_room[p];
-    for (int j = 0; j < c; j++)
-        if (a.pool_kf[s + j] == k) return;  // :101-102 the point is already observed in this keyframe
+    if (find_keyframe(a.pool_kf + s, c, k) < c) return;  // :101-102 the point is already observed in this keyframe
     if (c == room) {  // the run is full: move the list to the tail, with twice the room
         const int nroom = room < kMinRoom ? kMinRoom : 2 * room;
         const int ns = atomicAdd(a.ctr + kCtrTail, nroom);
