@@ -183,17 +183,6 @@ inline int ensure_dyn_smem(Ctx *ctx, Kernel *kernel, int bytes) {
     return LCCRF_OK;
 }
 
-// ask for the largest shared-memory carve-out for a kernel whose residency is bounded by shared memory (once per context)
-template <typename Kernel>
-inline int prefer_smem(Ctx *ctx, Kernel *kernel) {
-    const void *key = (const void *)((const char *)kernel + 1);  // distinct from the ensure_dyn_smem key of the same kernel
-    for (const void *k : ctx->smem_attr_done)
-        if (k == key) return LCCRF_OK;
-    LCCRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    ctx->smem_attr_done.push_back(key);
-    return LCCRF_OK;
-}
-
 int dev_alloc(Ctx *ctx, void **p, size_t bytes, bool zero = false);
 void dev_free(Ctx *ctx, void *p);
 

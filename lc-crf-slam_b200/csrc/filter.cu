@@ -841,7 +841,8 @@ k_splat_rows(const int *__restrict__ row_ptr, const int *__restrict__ tile_row0,
         const long long t0 = (long long)t * kTreeTile;
         const int cnt = (int)min((long long)kRowsWin - 1, E - t0);
         const int ra = __ldg(tile_row0 + t), rb = __ldg(tile_row0 + t + 1);
-        // phase 1, in two halves (register budget: 6 CTAs per SM keep enough chains in flight to hide their latency)
+        // phase 1, in two halves (register budget: 39 registers, 5-6 CTAs per SM keep enough chains in flight; asking for the
+        // largest shared-memory carve-out on top of that was measured 1.7x SLOWER -- the gathers do live in L1)
         constexpr int kHalf = kRowsIT / 2;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -1227,11 +1228,16 @@ k_blur_vec(const int2 *__restrict__ nbr_j, const VT *__restrict__ src, VT *__res
 
 // ---- the same pass with its two STREAMS -- the neighbour pairs and the vertices' own values -- brought into shared
 // memory by the bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP) through a ring
-// of kBulkStages tiles, so that the LSU and the registers only carry the two dependent neighbour gathers and the result.
+// of 2-3 tiles, so that the LSU and the registers only carry the two dependent neighbour gathers and the result.
 // Tiles of kBulkTV vertices; one elected thread arms the stage's barrier with the byte count and issues both copies,
 // every thread waits on the barrier's phase, consumes, and the block barrier behind the tile frees the stage.
 // VT = float2 (L = 2) or float4 (L = 4): one vector per vertex.  The tail (V % kBulkTV) takes plain loads.
-constexpr int kBulkTV = 1024, kBulkStages = 3, kBulkThreads = 256;
+// (tile, stages, CTAs per SM) from a sweep on B200 (profiles/r02m_sweeps.txt, scripts/blur_probe.py; 2048 x 2048 stress lattice):
+// L = 2: (1024, 3, 3) 0.89-0.90 of the measured HBM peak, plain loads 0.78;  L = 4: (1024, 2, 3) 0.88, plain loads 0.86
+constexpr int kBulkTV = 1024, kBulkThreads = 256;
+template <typename VT> struct BulkCfg;
+template <> struct BulkCfg<float2> { static constexpr int kStages = 3, kPerSm = 3; };
+template <> struct BulkCfg<float4> { static constexpr int kStages = 2, kPerSm = 3; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -1262,6 +1268,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 template <typename VT>
 __global__ void __launch_bounds__(kBulkThreads)
 k_blur_bulk(const int2 *__restrict__ nbr_j, const VT *__restrict__ src, VT *__restrict__ dst, const int *__restrict__ vtotal) {
+    constexpr int kBulkStages = BulkCfg<VT>::kStages;
     extern __shared__ __align__(128) unsigned char s_bulk[];
     __shared__ __align__(8) uint64_t s_bar[kBulkStages];
     int2 *s_nb = (int2 *)s_bulk;                                                   // [stages][kBulkTV]
@@ -1463,8 +1470,6 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
         const int grid = ls->n_tiles < kNumSMs * 12 ? ls->n_tiles : kNumSMs * 12;
         const size_t smem = (size_t)kRowsWin * LG * sizeof(float);
         LCCRF_TRY(ensure_dyn_smem(ctx, k_splat_rows<4>, (int)((size_t)kRowsWin * 4 * sizeof(float))));
-        LCCRF_TRY(prefer_smem(ctx, k_splat_rows<1>));
-        LCCRF_TRY(prefer_smem(ctx, k_splat_rows<2>));
         for (int lb = 0; lb < L; lb += LG) {
             LCCRF_KERNEL(ctx, "k_splat_rows");
             switch (LG) {
@@ -1512,8 +1517,9 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
         const bool bulk = ctx->opt_bulk_blur && G == 1 && (W == 2 || W == 4) && (((size_t)nb & 15) == 0);
         if (bulk) {
             // streams through the bulk-copy engine (UBLKCP); 16-byte aligned neighbour tables (Vcap is even)
-            const size_t smem = (size_t)kBulkStages * kBulkTV * (sizeof(int2) + (W == 2 ? sizeof(float2) : sizeof(float4)));
-            const int per_sm = W == 2 ? 4 : 3;
+            const int stages = W == 2 ? BulkCfg<float2>::kStages : BulkCfg<float4>::kStages;
+            const int per_sm = W == 2 ? BulkCfg<float2>::kPerSm : BulkCfg<float4>::kPerSm;
+            const size_t smem = (size_t)stages * kBulkTV * (sizeof(int2) + (W == 2 ? sizeof(float2) : sizeof(float4)));
             const long long tiles = (long long)ls->Vcap / kBulkTV + 1;
             const int grid = (int)(tiles < (long long)kNumSMs * per_sm ? tiles : (long long)kNumSMs * per_sm);
             LCCRF_KERNEL(ctx, "k_blur");

@@ -109,22 +109,32 @@ __device__ __forceinline__ int find_keyframe(const int *__restrict__ list, int c
 }
 
 // MapPoint::EraseObservation(pKF), src/MapPoint.cc:111-141: the entry of keyframe kf leaves the list, the rest closes up
+// one atomic per warp on the live-observation counter (800k requests on one address would serialise in L2)
+__device__ __forceinline__ void live_add(int *ctr, int delta) {
+    const unsigned m = __activemask();
+    const int tot = __reduce_add_sync(m, delta);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && tot) atomicAdd(ctr, tot);
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_map_erase(PoolArgs a, const int *__restrict__ pt, const int *__restrict__ kf, int n) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const int p = __ldg(pt + i), k = __ldg(kf + i);
-    if (!claim_point(a, p)) return;
-    const int s = a.pt_start[p], c = a.pt_cnt[p];
-    const int j0 = find_keyframe(a.pool_kf + s, c, k);
-    if (j0 == c) return;  // :116 no such observation
-    int j = j0;
-    for (; j + 1 < c; j++) {
-        a.pool_kf[s + j] = a.pool_kf[s + j + 1];
-        a.pool_uv[s + j] = a.pool_uv[s + j + 1];
+    int gone = 0;
+    if (claim_point(a, p)) {
+        const int s = a.pt_start[p], c = a.pt_cnt[p];
+        int j = find_keyframe(a.pool_kf + s, c, k);
+        if (j < c) {  // (:116: nothing happens when the point has no observation in that keyframe)
+            for (; j + 1 < c; j++) {
+                a.pool_kf[s + j] = a.pool_kf[s + j + 1];
+                a.pool_uv[s + j] = a.pool_uv[s + j + 1];
+            }
+            a.pt_cnt[p] = c - 1;
+            gone = 1;
+        }
     }
-    a.pt_cnt[p] = c - 1;
-    atomicSub(a.ctr + kCtrLive, 1);
+    live_add(a.ctr + kCtrLive, -gone);
 }
 
 // MapPoint::SetBadFlag, src/MapPoint.cc:151-168: mObservations.clear()
@@ -138,7 +148,7 @@ k_map_bad(PoolArgs a, const int *__restrict__ pt, int n) {
         return;
     }
     const int c = atomicExch(a.pt_cnt + p, 0);
-    if (c) atomicSub(a.ctr + kCtrLive, c);
+    if (c) atomicSub(a.ctr + kCtrLive, c);  // (a few points per step)
 }
 
 // MapPoint::AddObservation(pKF, idx), src/MapPoint.cc:98-109
@@ -147,33 +157,37 @@ k_map_add(PoolArgs a, const int *__restrict__ pt, const int *__restrict__ kf, co
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const int p = __ldg(pt + i), k = __ldg(kf + i), f = __ldg(fid + i);
+    int added = 0;
     if ((unsigned)k >= (unsigned)a.n_kf || (unsigned)f >= (unsigned)a.kp_stride) {
         atomicOr(a.status, kStIndex);
-        return;
-    }
-    if (!claim_point(a, p)) return;
-    int s = a.pt_start[p];
-    const int c = a.pt_cnt[p], room = a.pt_room[p];
-    if (find_keyframe(a.pool_kf + s, c, k) < c) return;  // :101-102 the point is already observed in this keyframe
-    if (c == room) {  // the run is full: move the list to the tail, with twice the room
-        const int nroom = room < kMinRoom ? kMinRoom : 2 * room;
-        const int ns = atomicAdd(a.ctr + kCtrTail, nroom);
-        if ((long long)ns + nroom > (long long)a.ctr[kCtrCap]) {
-            atomicOr(a.status, kStPool);  // (the host keeps the pool ahead of demand; see map_prepare)
-            return;
+    } else if (claim_point(a, p)) {
+        int s = a.pt_start[p];
+        const int c = a.pt_cnt[p], room = a.pt_room[p];
+        bool ok = find_keyframe(a.pool_kf + s, c, k) == c;  // :101-102 no-op when the point is already observed in this keyframe
+        if (ok && c == room) {  // the run is full: move the list to the tail, with twice the room
+            const int nroom = room < kMinRoom ? kMinRoom : 2 * room;
+            const int ns = atomicAdd(a.ctr + kCtrTail, nroom);
+            if ((long long)ns + nroom > (long long)a.ctr[kCtrCap]) {
+                atomicOr(a.status, kStPool);  // (the host keeps the pool ahead of demand; see map_prepare)
+                ok = false;
+            } else {
+                for (int j = 0; j < c; j++) {
+                    a.pool_kf[ns + j] = a.pool_kf[s + j];
+                    a.pool_uv[ns + j] = a.pool_uv[s + j];
+                }
+                a.pt_start[p] = ns;
+                a.pt_room[p] = nroom;
+                s = ns;
+            }
         }
-        for (int j = 0; j < c; j++) {
-            a.pool_kf[ns + j] = a.pool_kf[s + j];
-            a.pool_uv[ns + j] = a.pool_uv[s + j];
+        if (ok) {
+            a.pool_kf[s + c] = k;
+            a.pool_uv[s + c] = __ldg(a.kp_tab + (size_t)k * a.kp_stride + f);
+            a.pt_cnt[p] = c + 1;
+            added = 1;
         }
-        a.pt_start[p] = ns;
-        a.pt_room[p] = nroom;
-        s = ns;
     }
-    a.pool_kf[s + c] = k;
-    a.pool_uv[s + c] = __ldg(a.kp_tab + (size_t)k * a.kp_stride + f);
-    a.pt_cnt[p] = c + 1;
-    atomicAdd(a.ctr + kCtrLive, 1);
+    live_add(a.ctr + kCtrLive, added);
 }
 
 // bulk load: points [first, first + count) get fresh runs of (count + slack) entries at the tail, in point order
