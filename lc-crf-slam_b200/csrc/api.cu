@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" boundary (include/lccrf.h) and the host-side engine objects.
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -159,6 +160,25 @@ static void batch_release(Ctx *ctx, Batch &b) {
 }  // namespace lccrf
 
 using namespace lccrf;
+
+// host-side phase timer of the pipelined submit path (option "trace": one line per submission on stderr)
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string line;
+    explicit PhaseTimer(bool enable) : on(enable), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s=%.0fus", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+    }
+    ~PhaseTimer() {
+        if (on) fprintf(stderr, "lccrf trace:%s\n", line.c_str());
+    }
+};
 
 // ------------------------------------------------------------------ opaque handle types
 struct lccrf_ctx {
@@ -377,6 +397,7 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
     }
     else if (!strcmp(name, "profile")) h->c.opt_profile = value;
     else if (!strcmp(name, "map_slack")) h->c.opt_map_slack = value < 0 ? 0 : value;
+    else if (!strcmp(name, "trace")) h->c.opt_trace = value;
     else if (!strcmp(name, "bulk_blur")) {
         if (h->c.opt_bulk_blur != (value ? 1 : 0)) h->c.scratch_gen++;
         h->c.opt_bulk_blur = value ? 1 : 0;
@@ -1284,8 +1305,7 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
     const float *observs = in.observs, *error = in.error, *depth = in.depth;
     if (in.visible) {
         DevMap *m = in.map;
-        LCCRF_TRY(unary_map_points_visible(ctx, NT, in.vis, m->pt_xyz, m->pt_start, m->pt_cnt, m->pool_kf, m->pool_uv,
-                                           m->kf_packed, in.kf_bucket, m->d_nkf, fr->observs, fr->error, fr->depth, b.prob_ptr,
+        LCCRF_TRY(unary_map_points_visible(ctx, NT, in.vis, m->d_hdr, in.kf_bucket, fr->observs, fr->error, fr->depth, b.prob_ptr,
                                            in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max,
                                            in.ucam ? in.cam8 : nullptr));
         observs = fr->observs;
@@ -1325,8 +1345,6 @@ static int frames_run_slot(lccrf_frames *fr, FrameInputs &in) {
         in.has_delta = false;
         LCCRF_TRY(map_apply_dev(in.map, in.delta, nullptr));
     }
-    if (in.visible && in.graph && in.map_gen != in.map->gen) frame_inputs_drop_graph(in);  // a map array moved
-    if (in.visible) in.map_gen = in.map->gen;
     if (!ctx->opt_graphs || ctx->opt_profile) {
         LCCRF_TRY(frames_enqueue(fr, in));
         fr->ran = true;
@@ -2030,9 +2048,14 @@ int lccrf_frames_set_visible(lccrf_frames *fr, lccrf_map *map, const lccrf_map_d
 int lccrf_frames_submit_visible(lccrf_frames *fr, int slot, lccrf_map *map, const lccrf_map_delta *delta, const int *point_id,
                                 const float *kp2d, const int *kf_ptr, short *map_out, float *prob_out) {
     FrameInputs *in = nullptr;
+    PhaseTimer tm(fr && fr->ctx->opt_trace);
     LCCRF_TRY(frames_submit_prologue(fr, slot, &in));
+    tm.mark("prologue");
     LCCRF_TRY(frames_upload_visible(fr, *in, fr->ctx->copy_stream, map, delta, point_id, kp2d, kf_ptr));
-    return frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
+    tm.mark("upload");
+    const int rc = frames_submit_epilogue(fr, slot, *in, map_out, prob_out);
+    tm.mark("apply+run+results");
+    return rc;
 }
 
 int lccrf_frames_set_prior(lccrf_frames *fr, int slot, const double *p4, const unsigned char *has_prior) {

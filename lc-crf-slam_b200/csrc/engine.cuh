@@ -92,6 +92,7 @@ struct Ctx {
     // 1: splat sums every vertex row in point order (bit-identical to the reference's sequential loop);
     // 0: fixed-shape tree reduction per row (deterministic; marginals within the 1e-4 gate, not bit-identical)
     int opt_ordered_splat = 1;
+    int opt_trace = 0;         // host-side phase times of the pipelined submissions on stderr
     int opt_bulk_blur = 1;     // element-parallel blur: stream neighbour pairs / own values with cp.async.bulk (0: plain loads)
     int opt_map_slack = 0;     // spare room (percent) behind every list of a bulk-loaded map; 0 = tight lists: the unary streams
                                // them 4% faster, and a list that grows later moves to the pool's tail once (map.cu)
@@ -195,14 +196,25 @@ struct KfPack {  // one keyframe as the unary kernel reads it: rows of [Rcw|tcw]
 // keyframes (pose, intrinsics, bounds, undistorted keypoints) and map points (world position + observation list).
 // Observation lists live in one pool: point p owns pool entries [pt_start[p], pt_start[p] + pt_cnt[p]) out of a
 // reserved run of pt_room[p]; a list that outgrows its run moves to the pool's tail with twice the room.
+// Device-side directory of the map's arrays.  Kernels that a captured graph replays read the arrays through it, so the
+// map may move its arrays (growth) or gain keyframes without invalidating the graph: only this block is rewritten.
+struct MapHeader {
+    const KfPack *kf_packed;
+    const float *pt_xyz;
+    const int *pt_start, *pt_cnt;
+    const int *pool_kf;
+    const float *pool_uv;
+    int n_kf;
+};
+
 struct DevMap {
     Ctx *ctx = nullptr;
+    MapHeader *d_hdr = nullptr;   // device copy, rewritten by map_publish()
     int kp_stride = 0;
     // keyframes
     int kf_cap = 0, n_kf = 0;
     KfPack *kf_packed = nullptr;  // [kf_cap]
     float *kp_tab = nullptr;      // [kf_cap][kp_stride] float2   KeyFrame::mvKeysUn
-    int *d_nkf = nullptr;         // device copy of n_kf (read by captured graphs)
     bool cam_set = false, ucam = true;
     float cam8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // map points
@@ -252,6 +264,7 @@ int map_prepare(DevMap *m, const lccrf_map_delta &h);
 int map_apply_dev(DevMap *m, const DeltaDev &d, const float *kp_host);
 int map_bulk_observations(DevMap *m, int pt_first, int count, const int *obs_ptr_dev, const int *obs_ref_dev, long long nnz,
                           int slack_percent);
+int map_publish(DevMap *m);  // rewrite the device-side directory after arrays moved / keyframes were added
 int map_reserve_pool(DevMap *m, long long entries);
 int map_reserve_points(DevMap *m, int n);
 int map_bulk_reserve(DevMap *m, long long need);
@@ -301,10 +314,9 @@ int unary_map_points_packed(Ctx *ctx, int N, int nKF, const float *xyz, const in
                             int obs_kf_bytes, const float *obs_uv, const void *kf_packed, float *observs, float *error, float *depth,
                             const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max, const float *cam8,
                             const float *kp_tab, int kp_stride);
-int unary_map_points_visible(Ctx *ctx, int N, const int *vis, const float *pt_xyz, const int *pt_start, const int *pt_cnt,
-                             const int *pool_kf, const float *pool_uv, const void *kf_packed, int n_kf_bucket,
-                             const int *nkf_dev, float *observs, float *error, float *depth, const int *prob_ptr,
-                             const int *kf_ptr, int B, int kf_slice_max, const float *cam8);
+int unary_map_points_visible(Ctx *ctx, int N, const int *vis, const MapHeader *map_hdr, int n_kf_bucket, float *observs,
+                             float *error, float *depth, const int *prob_ptr, const int *kf_ptr, int B, int kf_slice_max,
+                             const float *cam8);
 // kp_tab != nullptr: indexed observations -- obs_kf holds {keyframe, feature index} pairs (uint16 pairs when
 // obs_kf_bytes == 2, int32 pairs when 4), obs_uv is unused and the observed keypoint is kp_tab[kf*kp_stride + fid]
 int unary_map_points(Ctx *ctx, int N, const float *xyz, const int *obs_ptr, const int *obs_kf,

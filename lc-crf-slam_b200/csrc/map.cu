@@ -233,6 +233,7 @@ k_map_bulk_entries(PoolArgs a, int first, int count, const int *__restrict__ obs
 }
 
 __global__ void k_map_set_word(int *dst, int v) { *dst = v; }
+__global__ void k_map_set_header(MapHeader *dst, MapHeader h) { *dst = h; }
 
 // export of observation lists (tests / snapshot files): counts, then entries
 __global__ void __launch_bounds__(kThreads)
@@ -306,7 +307,7 @@ int reserve_keyframes(DevMap *m, int n) {
     LCCRF_TRY(grow_array(ctx, m->kp_tab, (size_t)m->kf_cap * m->kp_stride * 2, (size_t)cap * m->kp_stride * 2, true));
     m->kf_cap = (int)cap;
     m->gen++;
-    return LCCRF_OK;
+    return map_publish(m);
 }
 
 // refresh the host's view of the device counters if the last snapshot has landed; request a new one
@@ -329,7 +330,7 @@ int map_create(Ctx *ctx, int kp_stride, DevMap **out) {
     auto *m = new DevMap();
     m->ctx = ctx;
     m->kp_stride = kp_stride;
-    int rc = dev_alloc(ctx, (void **)&m->d_nkf, sizeof(int), true);
+    int rc = dev_alloc(ctx, (void **)&m->d_hdr, sizeof(MapHeader), true);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&m->d_ctr, 4 * sizeof(int), true);
     if (rc == LCCRF_OK && (cudaHostAlloc((void **)&m->h_ctr, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
                            cudaEventCreateWithFlags(&m->ctr_ev, cudaEventDisableTiming) != cudaSuccess))
@@ -350,7 +351,7 @@ void map_destroy(DevMap *m) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     dev_free(ctx, m->kf_packed);
     dev_free(ctx, m->kp_tab);
-    dev_free(ctx, m->d_nkf);
+    dev_free(ctx, m->d_hdr);
     dev_free(ctx, m->pt_xyz);
     dev_free(ctx, m->pt_start);
     dev_free(ctx, m->pt_cnt);
@@ -362,6 +363,21 @@ void map_destroy(DevMap *m) {
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     if (m->ctr_ev) cudaEventDestroy(m->ctr_ev);
     delete m;
+}
+
+int map_publish(DevMap *m) {
+    Ctx *ctx = m->ctx;
+    MapHeader h;
+    h.kf_packed = m->kf_packed;
+    h.pt_xyz = m->pt_xyz;
+    h.pt_start = m->pt_start;
+    h.pt_cnt = m->pt_cnt;
+    h.pool_kf = m->pool_kf;
+    h.pool_uv = m->pool_uv;
+    h.n_kf = m->n_kf;
+    { LCCRF_KERNEL(ctx, "k_map_set_header"); k_map_set_header<<<1, 1, 0, ctx->stream>>>(m->d_hdr, h); }
+    LCCRF_CUDA(cudaGetLastError());
+    return LCCRF_OK;
 }
 
 int map_reserve_points(DevMap *m, int n) {
@@ -377,7 +393,7 @@ int map_reserve_points(DevMap *m, int n) {
     LCCRF_TRY(grow_array(ctx, m->pt_stamp, (size_t)m->pt_cap, (size_t)cap, true));
     m->pt_cap = (int)cap;
     m->gen++;
-    return LCCRF_OK;
+    return map_publish(m);
 }
 
 // make the pool hold at least `entries` entries (stream-ordered move)
@@ -394,7 +410,7 @@ int map_reserve_pool(DevMap *m, long long entries) {
     { LCCRF_KERNEL(ctx, "k_map_set_word"); k_map_set_word<<<1, 1, 0, ctx->stream>>>(m->d_ctr + kCtrCap, (int)cap); }
     LCCRF_CUDA(cudaGetLastError());
     m->gen++;
-    return LCCRF_OK;
+    return map_publish(m);
 }
 
 int map_prepare(DevMap *m, const lccrf_map_delta &h) {
@@ -465,7 +481,7 @@ int map_apply_dev(DevMap *m, const DeltaDev &d, const float *kp_host) {
             LCCRF_CUDA(cudaMemcpyAsync(m->kp_tab + (size_t)d.kf_first * m->kp_stride * 2, kp_host, row * d.kf_count, cudaMemcpyHostToDevice, st));
         else if (d.kf_keypoints)
             LCCRF_CUDA(cudaMemcpyAsync(m->kp_tab + (size_t)d.kf_first * m->kp_stride * 2, d.kf_keypoints, row * d.kf_count, cudaMemcpyDeviceToDevice, st));
-        { LCCRF_KERNEL(ctx, "k_map_set_word"); k_map_set_word<<<1, 1, 0, st>>>(m->d_nkf, m->n_kf); }
+        LCCRF_TRY(map_publish(m));  // the keyframe count
     }
     if (d.n_pose > 0) {
         LCCRF_KERNEL(ctx, "k_map_set_pose");

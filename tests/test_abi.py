@@ -73,3 +73,19 @@ def test_dropin_headers_compile_with_reference_call_sites(tmp_path):
            "-Wl,-rpath," + os.path.join(ROOT, "lc-crf-slam_b200")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_map_mirror_binding_compiles_and_links(tmp_path):
+    """tests/cpp/map_mirror.cpp is the reference-side binding of the resident map (INTEGRATION.md 3.2) written out in full;
+    it must compile against include/lccrf.h and link against liblccrf.so.  Without a B200 the program stops at
+    lccrf_ctx_create with exit code 2 (no CPU fallback); tests/test_gpu_dropin.py runs it for real."""
+    exe = tmp_path / "map_mirror"
+    cmd = ["g++", "-O1", "-std=c++14", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", str(exe),
+           os.path.join(ROOT, "tests", "cpp", "map_mirror.cpp"), "-L" + os.path.join(ROOT, "lc-crf-slam_b200"), "-llccrf",
+           "-Wl,-rpath," + os.path.join(ROOT, "lc-crf-slam_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert run.returncode == 2 and "no CPU fallback" in run.stderr

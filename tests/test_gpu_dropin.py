@@ -192,3 +192,19 @@ int main(int argc, char **argv) {
     assert r.returncode == 0, r.stderr
     m = np.frombuffer(open(out, "rb").read(), dtype=np.int16)
     assert np.array_equal(m, g["map"]), int((m != g["map"]).sum())
+
+
+def test_map_mirror_binding_runs(tmp_path):
+    """the C++ binding of the resident map (tests/cpp/map_mirror.cpp) end to end on the device: two
+    keyframes, eight points, one frame through lccrf_frames_submit_visible; the two drifting points come out moving"""
+    exe = tmp_path / "map_mirror"
+    cmd = ["g++", "-O1", "-std=c++14", "-I" + os.path.join(ROOT, "include"), "-o", str(exe),
+           os.path.join(ROOT, "tests", "cpp", "map_mirror.cpp"), "-L" + os.path.join(ROOT, "lc-crf-slam_b200"), "-llccrf",
+           "-Wl,-rpath," + os.path.join(ROOT, "lc-crf-slam_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    assert "map: 2 keyframes, 8 points, 12 observations" in run.stdout
+    labels = [int(x) for x in run.stdout.strip().split("labels:")[1].split()]
+    assert len(labels) == 8 and set(labels) <= {0, 1}

@@ -474,3 +474,90 @@ def test_frames_prior_branch(pkg, ctx, oracle):
     F.run()
     assert np.array_equal(F.get_debug()["init_label"], l_no)
     F.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_map_random_delta_sequences(pkg, ctx, oracle, seed):
+    """forty random deltas on a small map (every mutator, random sizes incl. empty ones, several segments per delta,
+    erasing first / middle / last / absent entries, re-observing bad points): after each one the exported lists equal the
+    host model's; at the end a frame over all live points matches the flat-snapshot path and the oracle"""
+    rng = np.random.default_rng(100 + seed)
+    stride, P = 64, 300
+    hm, mp = HostMap(stride), pkg.Map(ctx, stride)
+
+    def new_kf(n, first):
+        pose, intr, bounds, _ = make_keyframes(rng, n, first=first)
+        kp = np.stack([rng.uniform(0, 640, (n, stride)), rng.uniform(0, 480, (n, stride))], axis=2).astype(np.float32)
+        return pose, intr, bounds, kp
+
+    pose, intr, bounds, kp = new_kf(3, 0)
+    hm.add_keyframes(pose, intr, bounds, kp)
+    xyz, _ = make_points(rng, P)
+    hm.set_xyz(np.arange(P), xyz)
+    mp.apply(kf_pose=pose, kf_intr=intr, kf_bounds=bounds, kf_keypoints=kp, xyz=xyz)
+    for step in range(40):
+        nk = hm.pose.shape[0]
+        kw = {}
+        n_new = int(rng.integers(0, 3))
+        if n_new:
+            kpose, kintr, kbounds, kkp = new_kf(n_new, nk)
+            hm.add_keyframes(kpose, kintr, kbounds, kkp)
+            kw.update(kf_first=nk, kf_pose=kpose, kf_intr=kintr, kf_bounds=kbounds, kf_keypoints=kkp)
+        n_kf = hm.pose.shape[0]
+        if rng.random() < 0.5:
+            ids = rng.permutation(n_kf)[: int(rng.integers(1, n_kf + 1))]
+            newp = hm.pose[ids] + rng.normal(0, 1e-3, (ids.size, 12)).astype(np.float32)
+            hm.pose[ids] = newp
+            kw.update(pose_kf=ids, pose=newp)
+        if rng.random() < 0.5:
+            grow = int(rng.integers(0, 4))
+            ids = np.concatenate([rng.permutation(len(hm.obs))[: int(rng.integers(0, 40))], np.arange(len(hm.obs), len(hm.obs) + grow)]).astype(np.int64)
+            if ids.size:
+                nx, _ = make_points(rng, ids.size)
+                hm.set_xyz(ids, nx)
+                kw.update(xyz_id=ids, xyz=nx)
+        # erase: up to 3 segments, each a random keyframe and a random set of points (with or without that keyframe)
+        er_pt, er_kf, er_seg = [], [], [0]
+        for _ in range(int(rng.integers(0, 4))):
+            k = int(rng.integers(0, n_kf))
+            pts = rng.permutation(len(hm.obs))[: int(rng.integers(0, 60))]
+            for p in pts:
+                hm.erase(int(p), k)
+            er_pt.append(pts)
+            er_kf.append(np.full(pts.size, k))
+            er_seg.append(er_seg[-1] + pts.size)
+        if er_pt:
+            kw.update(erase_pt=np.concatenate(er_pt), erase_kf=np.concatenate(er_kf), erase_seg_ptr=er_seg)
+        bad = rng.permutation(len(hm.obs))[: int(rng.integers(0, 5))] if rng.random() < 0.4 else np.zeros(0, np.int64)
+        for p in bad:
+            hm.bad(int(p))
+        if bad.size:
+            kw.update(bad_pt=bad)
+        ad_pt, ad_kf, ad_fid, ad_seg = [], [], [], [0]
+        for _ in range(int(rng.integers(0, 4))):
+            k = int(rng.integers(0, n_kf))
+            pts = rng.permutation(len(hm.obs))[: int(rng.integers(0, 120))]
+            fids = rng.integers(0, stride, pts.size)
+            for p, f in zip(pts, fids):
+                hm.add(int(p), k, int(f))
+            ad_pt.append(pts)
+            ad_kf.append(np.full(pts.size, k))
+            ad_fid.append(fids)
+            ad_seg.append(ad_seg[-1] + pts.size)
+        if ad_pt:
+            kw.update(add_pt=np.concatenate(ad_pt), add_kf=np.concatenate(ad_kf), add_fid=np.concatenate(ad_fid), add_seg_ptr=ad_seg)
+        mp.apply(**kw)
+        ids_all = np.arange(len(hm.obs), dtype=np.int32)
+        ptr, kf, uv, xyz_d = mp.export(ids_all)
+        want = hm.snapshot(ids_all, np.zeros((ids_all.size, 2), np.float32))
+        assert np.array_equal(ptr, want.obs_ptr) and np.array_equal(kf, want.obs_kf), step
+        assert np.array_equal(bits(uv), bits(want.obs_uv)) and np.array_equal(bits(xyz_d), bits(want.xyz)), step
+    sz = mp.sizes()
+    assert sz["n_obs"] == sum(len(o) for o in hm.obs) and sz["n_kf"] == hm.pose.shape[0] and sz["n_points"] == len(hm.obs)
+    live = np.array([p for p in range(len(hm.obs)) if hm.obs[p]], np.int32)
+    kp2d = np.stack([rng.uniform(0, 640, live.size), rng.uniform(0, 480, live.size)], axis=1).astype(np.float32)
+    F1, F2 = pkg.Frames(ctx, [live.size]), pkg.Frames(ctx, [live.size])
+    check_against_model(pkg, ctx, oracle, mp, hm, F1, F2, live, kp2d)
+    F1.close()
+    F2.close()
+    mp.close()
