@@ -94,16 +94,16 @@ __device__ __forceinline__ bool claim_point(const PoolArgs &a, int p) {
     return true;
 }
 
-// position of keyframe k in a list of c entries (c if absent); eight independent loads per step instead of a
-// dependent chain of c
+// position of keyframe k in a list of c entries (c if absent; a keyframe occurs at most once): eight independent loads per
+// step instead of a dependent chain of c, newest entries first (culling the newest keyframe's observations is O(1))
 __device__ __forceinline__ int find_keyframe(const int *__restrict__ list, int c, int k) {
-    for (int j = 0; j < c; j += 8) {
+    for (int j = c; j > 0; j -= 8) {
         int v[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = j + q < c ? list[j + q] : ~k;
+        for (int q = 0; q < 8; q++) v[q] = j - 1 - q >= 0 ? list[j - 1 - q] : ~k;
 #pragma unroll
         for (int q = 0; q < 8; q++)
-            if (v[q] == k) return j + q;
+            if (v[q] == k) return j - 1 - q;
     }
     return c;
 }
