@@ -1308,6 +1308,7 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
         LCCRF_TRY(unary_map_points_visible(ctx, NT, in.vis, m->d_hdr, in.kf_bucket, fr->observs, fr->error, fr->depth, b.prob_ptr,
                                            in.have_kf_ptr ? in.kf_ptr : nullptr, b.B, in.kf_slice_max,
                                            in.ucam ? in.cam8 : nullptr));
+        LCCRF_TRY(map_end_main_access(m));  // the map may change from here on (the next step's delta, on the map's stream)
         observs = fr->observs;
         error = fr->error;
         depth = fr->depth;
@@ -1341,10 +1342,18 @@ static int frames_enqueue(lccrf_frames *fr, FrameInputs &in) {
 static int frames_run_slot(lccrf_frames *fr, FrameInputs &in) {
     Ctx *ctx = fr->ctx;
     if (!in.have_inputs) return fail(LCCRF_ERR_STATE, "frames_run before set_inputs");
-    if (in.has_delta) {  // this step's map changes: plain launches in front of the (captured) frame sequence
+    if (in.has_delta) {
+        // this step's map changes: plain launches on the map's own stream, behind the upload and behind the previous
+        // step's unary -- they run beside that step's lattice builds and mean-field iterations
         in.has_delta = false;
-        LCCRF_TRY(map_apply_dev(in.map, in.delta, nullptr));
+        LCCRF_CUDA(cudaStreamWaitEvent(in.map->mstream, in.up_done, 0));
+        {
+            MapStreamScope on_map_stream(in.map);
+            LCCRF_TRY(map_apply_dev(in.map, in.delta, nullptr));
+        }
+        LCCRF_TRY(map_end_async_mut(in.map));
     }
+    if (in.visible) LCCRF_TRY(map_begin_main_access(in.map));
     if (!ctx->opt_graphs || ctx->opt_profile) {
         LCCRF_TRY(frames_enqueue(fr, in));
         fr->ran = true;
@@ -1798,6 +1807,7 @@ int lccrf_map_apply(lccrf_map *map, const lccrf_map_delta *delta) {
     DevMap *m = map->m;
     Ctx *ctx = m->ctx;
     LCCRF_CUDA(cudaSetDevice(ctx->device));
+    LCCRF_TRY(map_begin_main_access(m));  // behind the asynchronous mutations of earlier pipelined submissions
     LCCRF_TRY(map_prepare(m, *delta));
     LCCRF_TRY(delta_grow_points(m, *delta));
     void *stage = nullptr;
@@ -1837,6 +1847,7 @@ int lccrf_map_set_observations(lccrf_map *map, int pt_first, int count, const in
     ptrs[count] = (int)nnz;
     ptrs[2 * (size_t)count + 1] = (int)run;
     if ((long long)pt_first + count > 0x7fffffffLL) return fail(LCCRF_ERR_ARG, "point id overflow");
+    LCCRF_TRY(map_begin_main_access(m));
     LCCRF_TRY(map_reserve_points(m, pt_first + count));
     if (pt_first + count > m->n_pt) m->n_pt = pt_first + count;
     LCCRF_TRY(map_bulk_reserve(m, run));
@@ -1955,10 +1966,19 @@ static int frames_upload_visible(lccrf_frames *fr, FrameInputs &in, cudaStream_t
     if (NT > 0 && (!point_id || !kp2d)) return fail(LCCRF_ERR_ARG, "NULL argument");
     const bool pipelined = st != ctx->stream;
     bool regraph = false, fresh = false;
-    if (delta) {
-        // host-side bookkeeping + capacity growth (stream-ordered on the context's stream, before the delta's kernels)
+    if (delta && pipelined) {
+        // host-side bookkeeping + capacity growth, stream-ordered on the MAP's stream behind the last access of the
+        // context's stream (an array that moves is freed there, and the previous step's unary may still read it)
+        LCCRF_TRY(map_begin_async_mut(m));
+        MapStreamScope on_map_stream(m);
         LCCRF_TRY(map_prepare(m, *delta));
         LCCRF_TRY(delta_grow_points(m, *delta));
+    } else if (delta) {
+        LCCRF_TRY(map_begin_main_access(m));
+        LCCRF_TRY(map_prepare(m, *delta));
+        LCCRF_TRY(delta_grow_points(m, *delta));
+    }
+    if (delta) {
         const size_t need = delta_stage_bytes(*delta, m->kp_stride, true);
         if (need > in.stage_cap) {
             // rare (first steps): cudaFree waits for the device, so nothing still reads the old block

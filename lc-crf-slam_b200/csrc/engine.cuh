@@ -210,6 +210,14 @@ struct MapHeader {
 struct DevMap {
     Ctx *ctx = nullptr;
     MapHeader *d_hdr = nullptr;   // device copy, rewritten by map_publish()
+    // The pipelined submissions apply a step's delta on the map's own stream, so that it overlaps the lattice builds and
+    // mean-field iterations of the previous step (only that step's unary kernel reads the map):
+    //   ev_touch  recorded on the context's stream behind its last access to the map (the unary of a frame batch --
+    //             inside a captured graph as an external event-record node --, a synchronous mutation, an export)
+    //   ev_mut    recorded on the map's stream behind the last asynchronous mutation
+    // Asynchronous mutations wait for ev_touch; every access from the context's stream waits for ev_mut.
+    cudaStream_t mstream = nullptr;
+    cudaEvent_t ev_touch = nullptr, ev_mut = nullptr;
     int kp_stride = 0;
     // keyframes
     int kf_cap = 0, n_kf = 0;
@@ -265,6 +273,18 @@ int map_apply_dev(DevMap *m, const DeltaDev &d, const float *kp_host);
 int map_bulk_observations(DevMap *m, int pt_first, int count, const int *obs_ptr_dev, const int *obs_ref_dev, long long nnz,
                           int slack_percent);
 int map_publish(DevMap *m);  // rewrite the device-side directory after arrays moved / keyframes were added
+// ordering between the context's stream and the map's own stream (see DevMap)
+int map_begin_main_access(DevMap *m);   // context stream waits for the asynchronous mutations enqueued so far
+int map_end_main_access(DevMap *m);     // ... and marks the end of its access (external record node while capturing)
+int map_begin_async_mut(DevMap *m);     // map stream waits for the context stream's last access
+int map_end_async_mut(DevMap *m);
+// scope in which ctx->stream IS the map's stream: map.cu's launches, copies and allocations go there
+struct MapStreamScope {
+    Ctx *c;
+    cudaStream_t saved;
+    explicit MapStreamScope(DevMap *m) : c(m->ctx), saved(m->ctx->stream) { c->stream = m->mstream; }
+    ~MapStreamScope() { c->stream = saved; }
+};
 int map_reserve_pool(DevMap *m, long long entries);
 int map_reserve_points(DevMap *m, int n);
 int map_bulk_reserve(DevMap *m, long long need);

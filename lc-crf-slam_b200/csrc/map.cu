@@ -333,7 +333,10 @@ int map_create(Ctx *ctx, int kp_stride, DevMap **out) {
     int rc = dev_alloc(ctx, (void **)&m->d_hdr, sizeof(MapHeader), true);
     if (rc == LCCRF_OK) rc = dev_alloc(ctx, (void **)&m->d_ctr, 4 * sizeof(int), true);
     if (rc == LCCRF_OK && (cudaHostAlloc((void **)&m->h_ctr, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
-                           cudaEventCreateWithFlags(&m->ctr_ev, cudaEventDisableTiming) != cudaSuccess))
+                           cudaEventCreateWithFlags(&m->ctr_ev, cudaEventDisableTiming) != cudaSuccess ||
+                           cudaStreamCreateWithFlags(&m->mstream, cudaStreamNonBlocking) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&m->ev_touch, cudaEventDisableTiming) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&m->ev_mut, cudaEventDisableTiming) != cudaSuccess))
         rc = fail(LCCRF_ERR_CUDA, "map: pinned counters / event allocation failed");
     if (rc != LCCRF_OK) {
         map_destroy(m);
@@ -349,6 +352,7 @@ void map_destroy(DevMap *m) {
     Ctx *ctx = m->ctx;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (m->mstream) cudaStreamSynchronize(m->mstream);
     dev_free(ctx, m->kf_packed);
     dev_free(ctx, m->kp_tab);
     dev_free(ctx, m->d_hdr);
@@ -362,7 +366,36 @@ void map_destroy(DevMap *m) {
     dev_free(ctx, m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     if (m->ctr_ev) cudaEventDestroy(m->ctr_ev);
+    if (m->ev_touch) cudaEventDestroy(m->ev_touch);
+    if (m->ev_mut) cudaEventDestroy(m->ev_mut);
+    cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees above
+    if (m->mstream) cudaStreamDestroy(m->mstream);
     delete m;
+}
+
+int map_begin_main_access(DevMap *m) {
+    LCCRF_CUDA(cudaStreamWaitEvent(m->ctx->stream, m->ev_mut, 0));
+    return LCCRF_OK;
+}
+
+int map_end_main_access(DevMap *m) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    LCCRF_CUDA(cudaStreamIsCapturing(m->ctx->stream, &cs));
+    if (cs == cudaStreamCaptureStatusActive)  // every replay of the graph records the event behind the unary kernel
+        LCCRF_CUDA(cudaEventRecordWithFlags(m->ev_touch, m->ctx->stream, cudaEventRecordExternal));
+    else
+        LCCRF_CUDA(cudaEventRecord(m->ev_touch, m->ctx->stream));
+    return LCCRF_OK;
+}
+
+int map_begin_async_mut(DevMap *m) {
+    LCCRF_CUDA(cudaStreamWaitEvent(m->mstream, m->ev_touch, 0));
+    return LCCRF_OK;
+}
+
+int map_end_async_mut(DevMap *m) {
+    LCCRF_CUDA(cudaEventRecord(m->ev_mut, m->mstream));
+    return LCCRF_OK;
 }
 
 int map_publish(DevMap *m) {
@@ -548,6 +581,7 @@ int map_bulk_reserve(DevMap *m, long long need) {
 
 int map_export_dev(DevMap *m, int n, const int *ids_dev, int *cnt_dev) {
     Ctx *ctx = m->ctx;
+    LCCRF_TRY(map_begin_main_access(m));
     LCCRF_KERNEL(ctx, "k_map_export_counts");
     k_map_export_counts<<<cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(ids_dev, n, m->pt_cnt, m->pt_cap, cnt_dev, ctx->d_status);
     LCCRF_CUDA(cudaGetLastError());
@@ -567,6 +601,7 @@ int map_export_entries_dev(DevMap *m, int n, const int *ids_dev, const int *ptr_
 
 int map_counters(DevMap *m, long long *tail, long long *live) {  // synchronises
     Ctx *ctx = m->ctx;
+    LCCRF_CUDA(cudaStreamSynchronize(m->mstream));
     LCCRF_CUDA(cudaStreamSynchronize(ctx->stream));
     int h[4];
     LCCRF_CUDA(cudaMemcpy(h, m->d_ctr, sizeof(h), cudaMemcpyDeviceToHost));
