@@ -36,6 +36,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# every kernel of liblccrf.so is loaded when the library is: no lazy module load inside a timed region (a map that grows
+# or a keyframe bucket that changes launches kernels the warm-up has not seen)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 METRIC = "crf_problems_per_s"
 UNIT = "problems/s"
