@@ -56,8 +56,17 @@ int lccrf_ctx_set_stream(lccrf_ctx *ctx, void *cuda_stream);
 int lccrf_ctx_sync(lccrf_ctx *ctx);
 /* number of liblccrf kernels launched on this context so far (bench.py "gpu_launches") */
 uint64_t lccrf_ctx_kernel_launches(const lccrf_ctx *ctx);
-/* option knobs: "graphs" (0/1, CUDA-graph replay of lccrf_frames_run), "fused" (0/1, per-problem
- * fused mean-field kernel when the lattices fit shared memory) */
+/* option knobs (default):
+ *   "ordered_splat" (1)  1: every lattice vertex sums its contributions in point order -- marginals bit-identical to the
+ *                        reference; 0: fixed-shape tree reduction, 3x faster splat, marginals within 1e-4 of the reference
+ *                        at frame-sized problems but not at N = 100k x 64
+ *   "graphs" (1)         CUDA-graph replay of lccrf_frames_run / submit once a launch sequence repeats its shape
+ *   "concurrent" (1)     the two pairwise kernels of a frame batch on two graph branches
+ *   "fused" (1)          fused point pass (slice of all lattices + Potts apply + softmax) for two labels
+ *   "bulk_blur" (1)      element-parallel blur streams its operands with cp.async.bulk (0: plain vector loads)
+ *   "map_slack" (0)      spare room, in percent, behind every list of lccrf_map_set_observations
+ *   "profile" (0)        per-kernel CUDA-event timing, see lccrf_ctx_profile_report
+ *   "trace" (0)          host-side phase times of the pipelined submissions on stderr */
 int lccrf_ctx_set_option(lccrf_ctx *ctx, const char *name, int value);
 /* Per-kernel timing.  With option "profile" = 1 every kernel launch is bracketed by two CUDA events on
  * the launching stream (graphs are bypassed while profiling).  The report synchronises, writes one line

@@ -467,6 +467,9 @@ struct ComposeShared {
     ScanPair wtot[8];
     int bnd[8][4];
 };
+// MONO: every product of the chunk is >= 0 (block-uniform; the CRF's case -- barycentric weights and marginals are
+// non-negative), so prefixes only grow: the extreme prefix increments are 0 and the total, no range tracking needed.
+template <bool MONO>
 __device__ __forceinline__ Composite block_composite(ScanPair tot, int hi0, int lo0, int hi1, int lo1, bool active,
                                                      int tid, ComposeShared &sh) {
     const int lane = tid & 31, wid = tid >> 5;
@@ -505,6 +508,12 @@ __device__ __forceinline__ Composite block_composite(ScanPair tot, int hi0, int 
     Composite c;
     c.a0 = __shfl_sync(0xffffffffu, w.a0, 7);
     c.a1 = __shfl_sync(0xffffffffu, w.a1, 7);
+    if (MONO) {
+        c.lo0 = c.lo1 = 0;
+        c.hi0 = c.a0;
+        c.hi1 = c.a1;
+        return c;
+    }
     // safe range: for a start of parity p this thread begins at offset exc.a_p with parity (p + exc.a_p) & 1
     int b_lo0 = exc.a0 + ((exc.a0 & 1) ? lo1 : lo0), b_hi0 = exc.a0 + ((exc.a0 & 1) ? hi1 : hi0);
     int b_lo1 = exc.a1 + ((exc.a1 & 1) ? lo0 : lo1), b_hi1 = exc.a1 + ((exc.a1 & 1) ? hi0 : hi1);
@@ -539,7 +548,7 @@ __device__ __forceinline__ Composite block_composite(ScanPair tot, int hi0, int 
 }
 
 // per-thread composite of the products c[0..IT) under the binade with ulp 1/inv_u (same arithmetic as row_sum_exact)
-template <int IT>
+template <int IT, bool MONO>
 __device__ __forceinline__ void thread_composite(const float *c, int n_valid, float inv_u, ScanPair &tot, int &hi0,
                                                  int &lo0, int &hi1, int &lo1) {
     tot.a0 = tot.a1 = 0;
@@ -566,10 +575,12 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
                 a.a1 = ni + ((ni + 1) & 1);
                 tot = scan_combine(tot, a);
             }
-            hi0 = max(hi0, tot.a0);
-            lo0 = min(lo0, tot.a0);
-            hi1 = max(hi1, tot.a1);
-            lo1 = min(lo1, tot.a1);
+            if (!MONO) {
+                hi0 = max(hi0, tot.a0);
+                lo0 = min(lo0, tot.a0);
+                hi1 = max(hi1, tot.a1);
+                lo1 = min(lo1, tot.a1);
+            }
         }
     }
 }
@@ -577,6 +588,7 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
 struct ComposeScratch {
     double red[8];
     double wpre[8];
+    int wneg[8];  // warp w holds a negative product
     ComposeShared cs;
     double pred;
     int tcross;
@@ -599,29 +611,36 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
     if (tid == 0) sc.tcross = 256;
     // thread-local sums of the products (double: a prediction of where the sum crosses the binade)
     double lsum = 0.0;
-    bool my_zero = true;
+    bool my_zero = true, my_neg = false;
 #pragma unroll
     for (int q = 0; q < IT; q++) {
         if (q < n_valid) lsum += (double)cq[q];
         my_zero = my_zero && (q >= n_valid || cq[q] == 0.0f);
+        my_neg = my_neg || (q < n_valid && !(cq[q] >= 0.0f));  // NaN counts as negative: full tracking
     }
+    const bool warp_neg = __any_sync(0xffffffffu, my_neg);
     double incl = lsum;  // inclusive prefix of the thread sums over the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const double y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
     }
-    if (lane == 31) sc.wpre[wid] = incl;
+    if (lane == 31) {
+        sc.wpre[wid] = incl;
+        sc.wneg[wid] = warp_neg;
+    }
     if (__syncthreads_and(my_zero)) {  // (uniform) every product is +-0: the chunk is the identity
         if (tid == 0) rec_out->kind = kRecZero;
         return;
     }
     double sp = 0.0, wbase = 0.0, total = 0.0;
+    int any_neg = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         sp += sc.red[w];
         if (w < wid) wbase += sc.wpre[w];
         total += sc.wpre[w];
+        any_neg |= sc.wneg[w];
     }
     const double p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
     total += sp;                                    // predicted running sum at the end of the chunk
@@ -642,8 +661,14 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
     ScanPair tot;
     int hi0, lo0, hi1, lo1;
     if (kind == kRecPlain) {
-        thread_composite<IT>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
-        const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
+        Composite A;
+        if (any_neg) {  // (uniform)
+            thread_composite<IT, false>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
+            A = block_composite<false>(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
+        } else {
+            thread_composite<IT, true>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
+            A = block_composite<true>(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
+        }
         if (tid == 0) {
             rec_out->kind = kRecPlain;
             rec_out->E = E;
@@ -658,9 +683,16 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
     int tw = sc.tcross - 1;  // window = threads [tw, tw + kWinThreads)
     tw = max(0, min(tw, 256 - kWinThreads));
     const bool inA = tid < tw, inB = tid >= tw + kWinThreads;
-    thread_composite<IT>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
-    const Composite A = block_composite(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
-    const Composite Bc = block_composite(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+    Composite A, Bc;
+    if (any_neg) {  // (uniform)
+        thread_composite<IT, false>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
+        A = block_composite<false>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
+        Bc = block_composite<false>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+    } else {
+        thread_composite<IT, true>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
+        A = block_composite<true>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
+        Bc = block_composite<true>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+    }
     if (!inA && !inB) {
 #pragma unroll
         for (int q = 0; q < IT; q++) rec_out->win[(tid - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;

@@ -147,7 +147,10 @@ def test_filter_large_lattice_vector_blur(pkg, ctx, oracle):
     rng = np.random.default_rng(99)
     for L in (1, 2, 3, 4, 6, 8, 12):
         x = (rng.random((W * H, L)) * 3 - 1).astype(np.float32)
-        assert_bit_exact(lg.filter(x), oracle.filter(lo, x), what="vector blur L=%d" % L)
+        for bulk in (1, 0):   # L = 2, 4: operands streamed by cp.async.bulk (k_blur_bulk) / by plain vector loads
+            ctx.set_option("bulk_blur", bulk)
+            assert_bit_exact(lg.filter(x), oracle.filter(lo, x), what="vector blur L=%d bulk=%d" % (L, bulk))
+    ctx.set_option("bulk_blur", 1)
     oracle.lattice_free(lo)
     lg.close()
 
