@@ -298,8 +298,8 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------- GPU arm
 # Kernels that together implement one stage are timed as a group (one "launch" of the group = one launch of its
-# first kernel): the ordered splat runs as k_splat_rows (short rows) + k_scan_sums/compose/walk (long rows) per filter call.
-KERNEL_GROUPS = {"splat": ("k_splat_rows", "k_scan_sums", "k_scan_compose", "k_scan_walk"),
+# first kernel): the ordered splat runs as k_splat_rows (short rows) + k_scan_compose/walk (long rows) per filter call.
+KERNEL_GROUPS = {"splat": ("k_splat_rows", "k_scan_compose", "k_scan_walk"),
                  "splat_tree": ("k_splat_tree", "k_splat_carry")}
 
 

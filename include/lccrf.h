@@ -62,6 +62,7 @@ uint64_t lccrf_ctx_kernel_launches(const lccrf_ctx *ctx);
  *                        at frame-sized problems but not at N = 100k x 64
  *   "graphs" (1)         CUDA-graph replay of lccrf_frames_run / submit once a launch sequence repeats its shape
  *   "concurrent" (1)     the two pairwise kernels of a frame batch on two graph branches
+ *   "split_splat" (1)    with "concurrent": a lattice's short-row splat runs beside its long-row scan kernels
  *   "fused" (1)          fused point pass (slice of all lattices + Potts apply + softmax) for two labels
  *   "bulk_blur" (1)      element-parallel blur streams its operands with cp.async.bulk (0: plain vector loads)
  *   "map_slack" (0)      spare room, in percent, behind every list of lccrf_map_set_observations

@@ -317,6 +317,13 @@ int lccrf_ctx_create(int device, lccrf_ctx **out) {
         delete h;
         return fail(LCCRF_ERR_CUDA, "aux stream / event creation failed");
     }
+    for (int i = 0; i < 2; i++)
+        if (cudaStreamCreateWithFlags(&h->c.sub_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->c.ev_sub_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->c.ev_sub_join[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete h;
+            return fail(LCCRF_ERR_CUDA, "sub stream / event creation failed");
+        }
     // keep freed blocks cached in the stream-ordered pool: per-frame CRF objects allocate and free constantly
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -359,6 +366,11 @@ void lccrf_ctx_destroy(lccrf_ctx *h) {
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < 2; i++) {
+        if (c->sub_stream[i]) cudaStreamDestroy(c->sub_stream[i]);
+        if (c->ev_sub_fork[i]) cudaEventDestroy(c->ev_sub_fork[i]);
+        if (c->ev_sub_join[i]) cudaEventDestroy(c->ev_sub_join[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete h;
 }
@@ -402,7 +414,14 @@ int lccrf_ctx_set_option(lccrf_ctx *h, const char *name, int value) {
         if (h->c.opt_bulk_blur != (value ? 1 : 0)) h->c.scratch_gen++;
         h->c.opt_bulk_blur = value ? 1 : 0;
     }
-    else if (!strcmp(name, "concurrent")) h->c.opt_concurrent = value;
+    else if (!strcmp(name, "concurrent")) {
+        if (h->c.opt_concurrent != value) h->c.scratch_gen++;  // captured graphs hold the other branch structure
+        h->c.opt_concurrent = value;
+    }
+    else if (!strcmp(name, "split_splat")) {
+        if (h->c.opt_split_splat != (value ? 1 : 0)) h->c.scratch_gen++;
+        h->c.opt_split_splat = value ? 1 : 0;
+    }
     else return fail(LCCRF_ERR_ARG, std::string("unknown option ") + name);
     return LCCRF_OK;
 }

@@ -407,7 +407,7 @@ int csr_create(Ctx *ctx, const Batch &b, LatticeSet *ls) {
     rc |= dev_alloc(ctx, (void **)&ls->row_list_long, ((size_t)ls->max_long + 1) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->long_chunk0, ((size_t)ls->max_long + 2) * 4);
     rc |= dev_alloc(ctx, (void **)&ls->chunk_desc, ((size_t)ls->max_chunks + 1) * 16);
-    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 8 * 4);
+    rc |= dev_alloc(ctx, (void **)&ls->row_counts, 16 * 4, true);  // [8..15] live across lattice builds (filter.cu)
     ls->max_pieces = (int)(((long long)b.NT * D) / kTileGranule + ((long long)b.NT * D) / kLongRow + 2);
     rc |= dev_alloc(ctx, (void **)&ls->piece_list, (size_t)ls->max_pieces * 4);
     ls->n_tiles = (int)(((long long)b.NT * D + kTreeTile - 1) / kTreeTile);

@@ -43,7 +43,7 @@ struct LatticeSet {
     int *row_counts = nullptr;      // [8] device: #long rows, #chunks, #pieces, compose ticket, 4 walk diagnostics
     int *long_chunk0 = nullptr;     // [max_long+1] first chunk of each long row
     void *chunk_desc = nullptr;     // [max_chunks] int4 {first entry, end entry, first chunk of the row, long-list index}
-    float *chunk_sum = nullptr;     // [max_chunks*Lmax] unordered chunk sums (per filter call)
+    unsigned long long *chunk_sum = nullptr;  // [max_chunks*Lmax] {call tag, unordered fp32 chunk sum}: published and polled inside k_scan_compose
     void *chunk_rec = nullptr;      // [max_chunks*Lmax] ChunkRec (per filter call)
     int max_long = 0, max_chunks = 0;
     // pieces of k_splat_tile: first rows of the maximal runs of short rows that start in one kTileGranule granule
@@ -119,6 +119,11 @@ struct Ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_concurrent = 1;
     int branch = 0;  // 0 = launches go to `stream`, 1 = to `aux_stream` (see AuxScope)
+    // second level, inside one filter call: the short-row splat of a lattice runs beside its long-row scan kernels
+    // (disjoint vertex rows; one sub-stream per branch)
+    cudaStream_t sub_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_sub_fork[2] = {nullptr, nullptr}, ev_sub_join[2] = {nullptr, nullptr};
+    int opt_split_splat = 1;
     // kernels whose opt-in dynamic shared memory limit has been raised on this context's device (function attributes
     // are per device, and a context belongs to one host thread: no process-wide flag)
     std::vector<const void *> smem_attr_done;

@@ -419,46 +419,24 @@ __device__ __forceinline__ void gather_labels(const float *__restrict__ in, int 
     }
 }
 
-template <int LG>
-__global__ void __launch_bounds__(256)
-k_scan_sums(const int2 *__restrict__ ent, const float *__restrict__ in, int *counts, const int4 *__restrict__ chunk_desc,
-            float *__restrict__ chunk_sum, int L) {
-    __shared__ float s_w[8][LG];
-    const int ngrp = (L + LG - 1) / LG;
-    const long long n = (long long)counts[1] * ngrp;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts[3] = 0;  // ticket counter of the k_scan_compose launch that follows
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (long long k = blockIdx.x; k < n; k += gridDim.x) {
-        const int c = (int)(k / ngrp), lb = (int)(k % ngrp) * LG;
-        const int4 g = __ldg(chunk_desc + c);
-        int2 t[kScanIT];
-        float x[kScanIT][LG];
-#pragma unroll
-        for (int q = 0; q < kScanIT; q++) {
-            const int e = g.x + q * 256 + tid;
-            t[q] = e < g.y ? __ldg(ent + e) : make_int2(0, 0);
-        }
-#pragma unroll
-        for (int q = 0; q < kScanIT; q++) gather_labels<LG>(in, t[q].x, L, lb, g.x + q * 256 + tid < g.y, x[q]);
-        float acc[LG];
-#pragma unroll
-        for (int j = 0; j < LG; j++) {
-            acc[j] = 0.0f;
-#pragma unroll
-            for (int q = 0; q < kScanIT; q++) acc[j] += __int_as_float(t[q].y) * x[q][j];  // a prediction: any order will do
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-            if (lane == 0) s_w[wid][j] = acc[j];
-        }
-        __syncthreads();
-        if (tid < LG && lb + tid < L) {
-            float tot = 0.0f;
-#pragma unroll
-            for (int w = 0; w < 8; w++) tot += s_w[w][tid];
-            chunk_sum[(size_t)c * L + lb + tid] = tot;
-        }
-        __syncthreads();
+// Unordered fp32 sums of the chunks (predictions of where the running sum of a row stands at a chunk start) are exchanged
+// between the CTAs of ONE k_scan_compose launch: every task publishes the sum of its chunk as {call tag, sum} in one 64-bit
+// word before it looks at anybody else's, and polls the words of the chunks in front of it in its row.  Tickets are handed
+// out in chunk order and a task publishes before it waits, so a waiting CTA only ever waits for CTAs that are running.
+// The tag (counts[8] + 1, bumped by k_scan_walk behind every compose launch) tells this call's words from stale ones; a
+// stale or wrapped tag could only spoil a prediction, never a result (k_scan_walk verifies every record it applies).
+__device__ __forceinline__ void publish_sum(unsigned long long *p, unsigned tag, float sum) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(sum);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ float poll_sum(const unsigned long long *p, unsigned tag) {
+    unsigned long long w;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+        if ((unsigned)(w >> 32) == tag) break;
+        __nanosleep(64);
     }
+    return __uint_as_float((unsigned)w);
 }
 
 // block-wide composite of the per-thread composites of the threads in [t_lo, t_hi) (others contribute the identity):
@@ -598,12 +576,12 @@ struct ComposeScratch {
 // chunk), n_valid of them inside the chunk.  Called by all 256 threads (barriers inside).
 template <int IT>
 __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, const int4 g, int c, int l, int L,
-                                            const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec_out, int tid,
-                                            ComposeScratch &sc) {
+                                            const unsigned long long *chunk_sum, unsigned tag,
+                                            ChunkRec *__restrict__ rec_out, int tid, ComposeScratch &sc) {
     const int lane = tid & 31, wid = tid >> 5;
-    // predicted running sum at the start of the chunk = sum of the previous chunks of the row
+    // predicted running sum at the start of the chunk = sum of the previous chunks of the row (published by their tasks)
     double part = 0.0;
-    for (int j = g.z + tid; j < c; j += 256) part += (double)__ldg(chunk_sum + (size_t)j * L + l);
+    for (int j = g.z + tid; j < c; j += 256) part += (double)poll_sum(chunk_sum + (size_t)j * L + l, tag);
 #pragma unroll
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     __syncthreads();  // the previous use of the scratch is over
@@ -709,20 +687,23 @@ template <int LG>
 __global__ void __launch_bounds__(256)
 k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
                const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
-               const int4 *__restrict__ chunk_desc, const float *__restrict__ chunk_sum, ChunkRec *__restrict__ rec, int L) {
+               const int4 *__restrict__ chunk_desc, unsigned long long *chunk_sum, ChunkRec *__restrict__ rec, int L) {
     constexpr int IT = kScanIT;
     __shared__ ComposeScratch s_sc;
     __shared__ ScanShared<1> sh1[8];
+    __shared__ float s_w[8][LG];
     __shared__ int s_ticket;
     const int ngrp = (L + LG - 1) / LG;
     const long long n = (long long)counts[1] * ngrp;
+    const int nlong = counts[0];
+    const unsigned tag = (unsigned)counts[8] + 1u;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // Row heads first: the start value (0) is known, so the exact sum of a row's first chunk is computed right here,
+    // Row heads: the start value (0) is known, so the exact sum of a row's first chunk is computed right here,
     // in parallel with everything else, one head per WARP (warp-level re-scans are cheap, and binade crossings are
     // dense at a row start).  The first CTAs of the grid take the heads, 8 per CTA; they are resident from the start
     // of the launch, so the long head tasks overlap with all the short composite tasks.
     {
-        const long long nheads = (long long)counts[0] * L;
+        const long long nheads = (long long)nlong * L;
         for (long long hk = (long long)blockIdx.x * 8 + wid; hk < nheads; hk += (long long)gridDim.x * 8) {
             const int i = (int)(hk / L), l = (int)(hk % L);
             const int v = __ldg(list + i);
@@ -735,7 +716,8 @@ k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, co
             }
         }
     }
-    // all other chunks: dynamic tickets (counts[3], zeroed by k_scan_sums) keep the CTAs that did heads from lagging
+    // all other chunks: dynamic tickets (counts[3], zeroed by the lattice build and by k_scan_walk) keep the CTAs that
+    // did heads from lagging
     for (;;) {
         __syncthreads();
         if (tid == 0) s_ticket = atomicAdd(counts + 3, 1);
@@ -744,7 +726,6 @@ k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, co
         if (k >= n) break;
         const int c = (int)(k / ngrp), lb = (int)(k % ngrp) * LG;
         const int4 g = __ldg(chunk_desc + c);
-        if (c == g.z) continue;  // a row head (done above)
         // entries of this chunk (thread-contiguous: thread t owns entries [t*IT, (t+1)*IT) of the chunk)
         int2 t[IT];
         float x[IT][LG];
@@ -756,13 +737,33 @@ k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, co
 #pragma unroll
         for (int q = 0; q < IT; q++) gather_labels<LG>(in, t[q].x, L, lb, g.x + tid * IT + q < g.y, x[q]);
         const int n_valid = max(0, min(IT, g.y - (g.x + tid * IT)));
+        {   // this chunk's unordered sums, published before the composites wait for the chunks in front
+            float acc[LG];
+#pragma unroll
+            for (int j = 0; j < LG; j++) {
+                acc[j] = 0.0f;
+#pragma unroll
+                for (int q = 0; q < IT; q++) acc[j] += __int_as_float(t[q].y) * x[q][j];  // (out-of-range entries are 0 * 0)
+#pragma unroll
+                for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+                if (lane == 0) s_w[wid][j] = acc[j];
+            }
+            __syncthreads();
+            if (tid < LG && lb + tid < L) {
+                float tot = 0.0f;
+#pragma unroll
+                for (int w = 0; w < 8; w++) tot += s_w[w][tid];
+                publish_sum(chunk_sum + (size_t)c * L + lb + tid, tag, tot);
+            }
+        }
+        if (c == g.z) continue;  // a row head: its exact sum is computed above, only the prediction was missing
 #pragma unroll
         for (int j = 0; j < LG; j++) {
             if (lb + j < L) {  // (uniform)
                 float cq[IT];
 #pragma unroll
                 for (int q = 0; q < IT; q++) cq[q] = __fmul_rn(__int_as_float(t[q].y), x[q][j]);
-                compose_one<IT>(cq, n_valid, g, c, lb + j, L, chunk_sum, rec + (size_t)c * L + lb + j, tid, s_sc);
+                compose_one<IT>(cq, n_valid, g, c, lb + j, L, chunk_sum, tag, rec + (size_t)c * L + lb + j, tid, s_sc);
             }
         }
     }
@@ -791,6 +792,10 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
     const long long n = (long long)counts[0] * L;
     int n_fast = 0, n_cross = 0, n_fall = 0, n_zero = 0;  // diagnostics (counts[4..7])
     const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) {  // the compose launch in front is over: reset its tickets, retire its tag
+        counts[3] = 0;
+        counts[8] = counts[8] + 1;
+    }
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
         const int i = (int)(k / L), l = (int)(k % L);
         const int v = __ldg(list + i);
@@ -1480,6 +1485,8 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     const int D = ls->D;
     const int *vt = ls->vbase + ls->B;
     float *src = ls->valA, *dst = ls->valB;
+    const bool split = b.NT > 0 && ctx->opt_ordered_splat && ctx->opt_split_splat && ls->max_chunks > 0 &&
+                       ctx_concurrent(ctx) && ctx->sub_stream[ctx->branch];
     if (b.NT > 0 && !ctx->opt_ordered_splat) {
         // tree splat: one streaming pass over the sorted entries per label group + the cross-tile carries
         const long long E = (long long)b.NT * D;
@@ -1502,12 +1509,20 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
         const int grid = ls->n_tiles < kNumSMs * 12 ? ls->n_tiles : kNumSMs * 12;
         const size_t smem = (size_t)kRowsWin * LG * sizeof(float);
         LCCRF_TRY(ensure_dyn_smem(ctx, k_splat_rows<4>, (int)((size_t)kRowsWin * 4 * sizeof(float))));
+        // the short rows and the long rows of a lattice are disjoint sets of vertex rows: the short-row kernel (bound by
+        // L2 gathers) runs beside the long-row scan kernels (bound by instruction issue) on the branch's sub-stream
+        cudaStream_t rs = st;
+        if (split) {
+            rs = ctx->sub_stream[ctx->branch];
+            LCCRF_CUDA(cudaEventRecord(ctx->ev_sub_fork[ctx->branch], st));
+            LCCRF_CUDA(cudaStreamWaitEvent(rs, ctx->ev_sub_fork[ctx->branch], 0));
+        }
         for (int lb = 0; lb < L; lb += LG) {
             LCCRF_KERNEL(ctx, "k_splat_rows");
             switch (LG) {
-                case 1: k_splat_rows<1><<<grid, kRowsThreads, smem, st>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
-                case 2: k_splat_rows<2><<<grid, kRowsThreads, smem, st>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
-                default: k_splat_rows<4><<<grid, kRowsThreads, smem, st>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
+                case 1: k_splat_rows<1><<<grid, kRowsThreads, smem, rs>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
+                case 2: k_splat_rows<2><<<grid, kRowsThreads, smem, rs>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
+                default: k_splat_rows<4><<<grid, kRowsThreads, smem, rs>>>(ls->row_ptr, ls->tile_row0, ls->tile_own, ls->csr_ent, in_dev, src, ls->n_tiles, E, L, lb); break;
             }
         }
     }
@@ -1515,21 +1530,22 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
     // sized for the worst case a lattice set can hold and capped at a few waves (grid-stride inside).
     if (b.NT > 0 && ls->max_chunks > 0 && ctx->opt_ordered_splat) {
         const long long maxc = (long long)ls->max_chunks * ((L + 1) / 2), maxr = (long long)ls->max_long * L;
-        const int gc = (int)(maxc < kNumSMs * 16 ? maxc : kNumSMs * 16);
         const int gk = (int)(maxc < kNumSMs * 3 ? maxc : kNumSMs * 3);  // compose: persistent, one resident wave
         const int gr = (int)(maxr < kNumSMs * 8 ? maxr : kNumSMs * 8);
         const int4 *desc = (const int4 *)ls->chunk_desc;
         if (scan_labels(L) == 1) {
-            { LCCRF_KERNEL(ctx, "k_scan_sums"); k_scan_sums<1><<<gc, 256, 0, st>>>(ls->csr_ent, in_dev, ls->row_counts, desc, ls->chunk_sum, L); }
-            { LCCRF_KERNEL(ctx, "k_scan_compose");
-              k_scan_compose<1><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L); }
+            LCCRF_KERNEL(ctx, "k_scan_compose");
+            k_scan_compose<1><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
         } else {
-            { LCCRF_KERNEL(ctx, "k_scan_sums"); k_scan_sums<2><<<gc, 256, 0, st>>>(ls->csr_ent, in_dev, ls->row_counts, desc, ls->chunk_sum, L); }
-            { LCCRF_KERNEL(ctx, "k_scan_compose");
-              k_scan_compose<2><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L); }
+            LCCRF_KERNEL(ctx, "k_scan_compose");
+            k_scan_compose<2><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
         }
         { LCCRF_KERNEL(ctx, "k_scan_walk");
           k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, L); }
+    }
+    if (split) {
+        LCCRF_CUDA(cudaEventRecord(ctx->ev_sub_join[ctx->branch], ctx->sub_stream[ctx->branch]));
+        LCCRF_CUDA(cudaStreamWaitEvent(st, ctx->ev_sub_join[ctx->branch], 0));
     }
     if (b.B >= 2 || b.maxN <= 32768) {  // one CTA per problem runs all D passes
         LCCRF_TRY(ensure_dyn_smem(ctx, k_blur_fused, kBlurFusedBytes + 16));

@@ -421,7 +421,7 @@ int lattice_set_create(Ctx *ctx, const Batch &b, int d, float w, int Lmax, Latti
         const long long E = (long long)b.NT * ls->D;
         const size_t mc = (size_t)(E / kScanChunk + E / kLongRow) + 1;
         if (Lmax > 0) {
-            rc |= dev_alloc(ctx, (void **)&ls->chunk_sum, mc * Lmax * sizeof(float));
+            rc |= dev_alloc(ctx, (void **)&ls->chunk_sum, mc * Lmax * sizeof(unsigned long long), true);
             rc |= dev_alloc(ctx, (void **)&ls->chunk_rec, mc * Lmax * kChunkRecBytes);
         }
     }
@@ -477,7 +477,7 @@ int lattice_set_ensure_L(Ctx *ctx, LatticeSet *ls, int L) {
     int rc = LCCRF_OK;
     {
         const size_t mc = (size_t)ls->max_chunks + 1;
-        rc |= dev_alloc(ctx, (void **)&ls->chunk_sum, mc * L * sizeof(float));
+        rc |= dev_alloc(ctx, (void **)&ls->chunk_sum, mc * L * sizeof(unsigned long long), true);
         rc |= dev_alloc(ctx, (void **)&ls->chunk_rec, mc * L * kChunkRecBytes);
     }
     rc |= dev_alloc(ctx, (void **)&ls->valA, (size_t)ls->Vcap * L * sizeof(float));

@@ -300,7 +300,7 @@ def _mock_device(monkeypatch):
             pass
 
         def profile_report(self):
-            return {"k_splat_rows": (36, 1.2), "k_scan_sums": (36, 0.3), "k_scan_compose": (36, 1.0), "k_scan_walk": (40, 0.4),
+            return {"k_splat_rows": (36, 1.2), "k_scan_compose": (36, 1.0), "k_scan_walk": (40, 0.4),
                     "k_map_point_unary": (3, 2.0), "k_mf_point_l2": (15, 0.6), "k_blur": (9, 0.5)}
 
     class FakeFrames:
@@ -443,8 +443,8 @@ def test_bench_c3_gpu_arm_against_a_mock_device(monkeypatch, capsys):
     assert d["e2e"]["d2h_bytes_per_step"] == 4500 * (2 + 8)
     assert calls["map_apply"] == 1 and calls["map_bulk"] == 1 and calls["visible"] == 4 + 4
     assert calls["table"] == 1 and calls["indexed"] == 4 + 4 and calls["flat"] == 4 + 4
-    assert d["roofline"]["kernel"] == "k_splat_rows+k_scan_sums+k_scan_compose+k_scan_walk"
-    assert abs(d["roofline"]["share_of_step"] - 2.9 / 6.0) < 1e-3 and d["roofline"]["bound"] == "hbm"
+    assert d["roofline"]["kernel"] == "k_splat_rows+k_scan_compose+k_scan_walk"
+    assert abs(d["roofline"]["share_of_step"] - 2.6 / 5.7) < 1e-3 and d["roofline"]["bound"] == "hbm"
     assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["cpu_baseline"]["value"] > 0
 
 
