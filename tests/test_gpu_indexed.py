@@ -68,7 +68,7 @@ def test_indexed_matches_flat_and_oracle(pkg, ctx, oracle, dtype, stride):
 
 def test_indexed_mixed_cameras_small_table(pkg, ctx, oracle):
     """Keyframes with different intrinsics (no uniform-camera shortcut) and a table that fits the whole-table
-    shared-memory mode (nKF <= 640)."""
+    shared-memory mode (nKF <= 384)."""
     prm = pkg.SlamParams.make()
     s = synth.map_snapshot(3001, 16, seed=21, n_kf=40, ragged=True)
     s.kf_intr = s.kf_intr.copy()

@@ -261,7 +261,7 @@ def test_map_incremental_deltas_against_host_model(pkg, ctx, oracle, n_pts, mixe
 
 
 def test_map_batch_with_keyframe_slices(pkg, ctx, oracle):
-    """four independent problems in one batch, 200 keyframes each (800 > the 640 that fit shared memory): the unary
+    """four independent problems in one batch, 200 keyframes each (800 > the 384 that fit shared memory): the unary
     kernel keeps the current problem's keyframe slice in shared memory (kf_ptr), C3's shape at reduced size"""
     snaps = [synth.map_snapshot(4000 + 7 * i, 24, seed=60 + i, n_kf=200) for i in range(4)]
     cat = pkg.concat_frames(snaps)

@@ -644,7 +644,7 @@ def test_frames_map_batch_keyframe_slices(pkg, ctx, oracle):
              enumerate(((2500, 64, False), (130, 7, True), (4000, 20, True), (31, 64, False)))]
     sys_path_bench = importlib.import_module("bench")
     cat = sys_path_bench.concat_snapshots(snaps)
-    assert cat["kf_pose"].shape[0] == 1200  # > 640: the whole table does not fit shared memory
+    assert cat["kf_pose"].shape[0] == 1200  # > 384: the whole table does not fit shared memory
     F = pkg.Frames(ctx, [s.n for s in snaps], prm, en)
     outs = []
     for kf_ptr in (cat["kf_ptr"], None):
