@@ -709,8 +709,13 @@ def run_gpu_arm_replay(args):
         lab = dbg["init_label"][a:b]
         parity["init_label_mismatches"] += int((o.rough_classify(ob, er, de, prm_o) != lab).sum())
         Qo, mo, _ = o.slam_crf(ob, er, snap.kp2d, lab, en, prm_o)
-        rel = np.abs(pr_out[a:b].astype(np.float64) - Qo) / np.maximum(np.abs(Qo), 1e-300)
+        fin = np.isfinite(Qo) & np.isfinite(pr_out[a:b])
+        parity["non_finite_marginals"] = parity.get("non_finite_marginals", 0) + int((~fin).sum())
+        with np.errstate(invalid="ignore", over="ignore"):
+            rel = np.abs(pr_out[a:b].astype(np.float64) - Qo) / np.maximum(np.abs(Qo), 1e-300)
         rel[(Qo == 0) & (pr_out[a:b] == 0)] = 0
+        # a non-finite marginal counts as a mismatch unless both sides hold the same bit pattern
+        rel[~fin] = np.where(pr_out[a:b].view(np.int32)[~fin] == Qo.astype(np.float32).view(np.int32)[~fin], 0.0, np.inf)
         parity["max_rel_marginal_err"] = max(parity["max_rel_marginal_err"], float(rel.max()))
         diff = np.nonzero(mp_out[a:b] != mo)[0]
         parity["map_mismatches"] += int(diff.size)

@@ -1,8 +1,9 @@
 #!/bin/bash
 # One GPU-box visit of round 2: bench lines of every workload, ncu launch list of the default bench command, one
 # `ncu --set full` capture of the hot kernels of a C3 step (batch 32), exported as CSV (the .ncu-rep is too large to travel).
-# Usage (from the repo root, under gpurun): bash scripts/gpu_round2.sh [tag]
+# Usage (from the repo root, under gpurun): bash scripts/gpu_round2.sh [tag] [full-capture launches]
 TAG=${1:-r02}
+NFULL=${2:-48}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi > $OUT/nvidia_smi.txt 2>&1
@@ -18,9 +19,9 @@ echo "== ncu launch list (default bench command, first 700 launches after the se
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-profile > $OUT/ncu_launch_bench.log 2>&1; echo "ncu launches rc=$?"
 gzip -f $OUT/launches.csv
-echo "== ncu full (hot kernels of two C3 steps)"
-timeout 1500 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_map_point_unary|k_splat_rows|k_scan_sums|k_scan_compose|k_scan_walk|k_mf_point_l2|k_embed|k_csr_fill|k_csr_count|k_blur_fused|k_splat_tree|k_splat_carry|k_map_add|k_map_erase|k_map_set_xyz' \
-    -c 160 -o /tmp/prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu full (hot kernels of the first C3 step: $NFULL launches)"
+timeout 1200 ncu --set full --clock-control none --import-source on \
+    -k regex:'k_map_point_unary|k_splat_rows|k_scan_compose|k_scan_walk|k_mf_point_l2|k_embed|k_csr_fill|k_csr_count' \
+    -c $NFULL -o /tmp/prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/prof.ncu-rep --page raw --csv > $OUT/prof_raw.csv 2> $OUT/prof.err; gzip -f $OUT/prof_raw.csv
 ls -la $OUT

@@ -29,5 +29,5 @@ for _ in range(3):
     F.run()
 rep = ctx.profile_report(); ctx.set_option("profile", 0)
 tot = sum(v[1] for v in rep.values()) / 3
-keys = ("k_scan_compose", "k_scan_walk", "k_splat_rows", "k_map_point_unary", "k_csr_fill", "k_csr_count", "k_embed", "k_mf_point_l2")
+keys = ("k_scan_compose", "k_splat_rows", "k_map_point_unary", "k_csr_fill", "k_csr_count", "k_csr_prefix", "k_csr_zero", "k_embed")
 print("step %.3f ms (%d problems) | kernel sum %.3f ms |" % (ms, B, tot), " ".join("%s %.4f" % (k, rep[k][1] / rep[k][0]) for k in keys if k in rep), flush=True)
