@@ -46,7 +46,7 @@ struct LatticeSet {
     unsigned long long *chunk_sum = nullptr;  // [max_chunks*Lmax] {call tag, unordered fp32 chunk sum}: published and polled inside k_scan_compose
     void *chunk_rec = nullptr;      // [max_chunks*Lmax] ChunkRec (per filter call)
     int max_long = 0, max_chunks = 0;
-    // pieces of k_splat_tile: first rows of the maximal runs of short rows that start in one kTileGranule granule
+    // pieces (diagnostic, lccrf_frames debug counters): first rows of the maximal runs of short rows that start in one kTileGranule granule
     int *piece_list = nullptr;      // [max_pieces]
     int max_pieces = 0;
     // tree splat (option "ordered_splat" = 0): fixed tiles of kTreeTile sorted entries
@@ -64,7 +64,7 @@ constexpr int kCsrChunkPoints = 4096;  // points per chunk of the parallel stabl
 constexpr int kLongRow = 1024;    // rows at least this long leave the staged lane-sequential kernel for the exact scan
 constexpr int kScanChunk = 2048;  // entries per chunk of a long row
 constexpr int kChunkRecBytes = 16 + 2 * 24 + 4 * (kScanChunk / 256) * 4;  // sizeof(ChunkRec) of filter.cu
-constexpr int kTileGranule = 2048;  // entry granularity of the k_splat_tile windows
+constexpr int kTileGranule = 2048;  // entry granularity of the row pieces
 constexpr int kTreeTile = 2048;     // entries per tile of the tree splat (filter.cu: k_splat_tree)
 
 struct Batch {

@@ -20,117 +20,13 @@ namespace {
 // ---------------------------------------------------------------- splat
 // Segmented reduction over the vertex-sorted entries (csr.cu).  values[v][l] = (((0 + w0*x0) + w1*x1) + ...)
 // over the row of v in point order, every product and sum individually rounded -- the reference's splat loop
-// (:653-661) bit for bit.  Two kernels, both gathering in[point] themselves (no intermediate product array):
-//   k_splat_tile   rows shorter than kLongRow.  A CTA owns a piece = a run of consecutive short rows that start in one
-//                  granule of kTileGranule entries.  Phase 1: all threads stream the piece's entries (coalesced),
-//                  gather in[point] and park the products in shared memory -- every load is independent, so the
-//                  piece costs about two memory round trips.  Phase 2: lane (row, label) adds its row front to
-//                  back from shared memory: the ordered FADD chain never waits on DRAM.
-//   k_splat_scan   rows of kLongRow entries and more: exact parallel scan (below), one CTA per (row, label)
-constexpr int kTileRows = 1024;         // rows per staging round
-constexpr int kTileThreads = 256;
-constexpr int kTileBatch = 12;          // entries per thread whose loads are issued before the first use
-static_assert(kTileBatch * kTileThreads >= kTileGranule + kLongRow, "one batch covers a piece");
+// (:653-661) bit for bit.  The kernels gather in[point] themselves (no intermediate product array):
+//   k_splat_rows                 rows shorter than kLongRow, by tiles of kTreeTile sorted entries (further down)
+//   k_scan_compose, k_scan_walk  rows of kLongRow entries and more: exact parallel scan (next section)
+//   k_splat_tree, k_splat_carry  tolerance mode (option "ordered_splat" = 0): fixed-shape tree per row
 
 // labels staged per pass
 static inline int tile_labels(int L) { return L <= 2 ? L : 4; }
-
-// A piece (csr.cu: k_row_classify) = a maximal run of consecutive short rows whose first entries lie in one
-// granule of kTileGranule entries: at most kTileGranule + kLongRow - 1 entries, any number of rows.
-template <int LG>  // labels per pass (1, 2 or 4)
-__global__ void __launch_bounds__(kTileThreads)
-k_splat_tile(const int *__restrict__ row_ptr, const int *__restrict__ piece_list, const int *__restrict__ counts,
-             const int *__restrict__ vtotal, const int2 *__restrict__ ent, const float *__restrict__ in,
-             float *__restrict__ val, int L) {
-    extern __shared__ float s_prod[];          // [entry][LG]
-    __shared__ int s_rp[kTileRows + 1];        // row starts of the current round
-    __shared__ int s_first_end;
-    const int tid = threadIdx.x;
-    const int V = __ldg(vtotal);
-    const int npieces = __ldg(counts + 2);
-    for (int pc = blockIdx.x; pc < npieces; pc += gridDim.x) {
-        int vcur = __ldg(piece_list + pc);
-        const int gran = __ldg(row_ptr + vcur) / kTileGranule;
-        for (;;) {  // rounds of at most kTileRows rows (usually one)
-            const int nr_try = min(kTileRows, V - vcur);
-            if (tid == 0) s_first_end = nr_try;
-            __syncthreads();
-            for (int r = tid; r <= nr_try; r += kTileThreads) s_rp[r] = __ldg(row_ptr + vcur + r);
-            __syncthreads();
-            for (int r = tid; r < nr_try; r += kTileThreads)
-                if (s_rp[r + 1] - s_rp[r] >= kLongRow || s_rp[r] / kTileGranule != gran) atomicMin(&s_first_end, r);
-            __syncthreads();
-            const int nr = s_first_end;
-            if (nr == 0) break;  // (uniform) the piece ended exactly at a round boundary
-            const int eb = s_rp[0], cnt = s_rp[nr] - eb;  // cnt < kTileGranule + kLongRow
-            for (int lb = 0; lb < L; lb += LG) {
-                // phase 1: products of the round's entries -> shared memory, every load independent
-                {
-                    int2 t[kTileBatch];
-#pragma unroll
-                    for (int q = 0; q < kTileBatch; q++) {
-                        const int i = q * kTileThreads + tid;
-                        t[q] = i < cnt ? __ldg(ent + eb + i) : make_int2(0, 0);
-                    }
-                    if (LG == 2) {
-                        float2 x[kTileBatch];
-#pragma unroll
-                        for (int q = 0; q < kTileBatch; q++) {
-                            const int i = q * kTileThreads + tid;
-                            x[q] = i < cnt ? __ldg((const float2 *)(in + (size_t)t[q].x * L + lb)) : make_float2(0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int q = 0; q < kTileBatch; q++) {
-                            const int i = q * kTileThreads + tid;
-                            const float w = __int_as_float(t[q].y);
-                            if (i < cnt) ((float2 *)s_prod)[i] = make_float2(__fmul_rn(w, x[q].x), __fmul_rn(w, x[q].y));
-                        }
-                    } else {
-                        float x[kTileBatch][LG];
-#pragma unroll
-                        for (int q = 0; q < kTileBatch; q++) {
-                            const int i = q * kTileThreads + tid;
-#pragma unroll
-                            for (int j = 0; j < LG; j++)
-                                x[q][j] = (i < cnt && lb + j < L) ? __ldg(in + (size_t)t[q].x * L + lb + j) : 0.0f;
-                        }
-#pragma unroll
-                        for (int q = 0; q < kTileBatch; q++) {
-                            const int i = q * kTileThreads + tid;
-                            const float w = __int_as_float(t[q].y);
-                            if (i < cnt) {
-#pragma unroll
-                                for (int j = 0; j < LG; j++) s_prod[(size_t)i * LG + j] = __fmul_rn(w, x[q][j]);
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
-                // phase 2: ordered accumulation, one lane per (row, label)
-                for (int idx = tid; idx < nr * LG; idx += kTileThreads) {
-                    const int r = idx / LG, j = idx - r * LG;
-                    if (lb + j >= L) continue;
-                    const int a = s_rp[r] - eb, z = s_rp[r + 1] - eb;
-                    float acc = 0.0f;
-                    int e = a;
-                    for (; e + 8 <= z; e += 8) {  // independent shared loads first, then the ordered chain
-                        float y[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) y[q] = s_prod[(size_t)(e + q) * LG + j];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, y[q]);
-                    }
-                    for (; e < z; e++) acc = __fadd_rn(acc, s_prod[(size_t)e * LG + j]);
-                    val[(size_t)(vcur + r) * L + lb + j] = acc;
-                }
-                __syncthreads();
-            }
-            vcur += nr;
-            if (nr < nr_try || vcur >= V) break;  // a boundary (long row / next granule / end) closed the piece
-        }
-        __syncthreads();
-    }
-}
 
 // ---------------------------------------------------------------- exact ordered scan for long rows
 // A lane-sequential walk costs one dependent FADD (4 cycles) plus load latency per entry, which is too slow for
@@ -857,9 +753,8 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
 }
 
 // ---------------------------------------------------------------- ordered splat, short rows, by entry tiles
-// Same result as k_splat_tile (every row summed front to back), organised by fixed tiles of kTreeTile sorted entries instead
-// of pieces: a CTA owns the short rows that START in its tile and stages the tile plus the kLongRow - 1 entries a short
-// row can reach beyond it.  Phase 1: coalesced entry stream, gather in[point], products to shared memory.  Phase 2: row
+// Every row summed front to back, organised by fixed tiles of kTreeTile sorted entries: a CTA owns the short rows that
+// START in its tile and stages the tile plus the kLongRow - 1 entries a short row can reach beyond it.  Phase 1: coalesced entry stream, gather in[point], products to shared memory.  Phase 2: row
 // ra + i of the tile is walked by thread i -- one FADD chain per (row, label), operands prefetched eight entries ahead so
 // that the chain runs at the adder's latency.  No row pointer staging, no atomics; rows >= kLongRow are left to the scan.
 constexpr int kRowsThreads = 256;
