@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(kFillWarpsH * 32) k_csr_fill(CsrParams p) {
 }
 
 // rows by length class: long rows (>= kLongRow entries) go to the speculative scan; the short ones are grouped
-// into pieces (a diagnostic of the row structure since k_splat_rows works by fixed entry tiles) -- a piece starts at a short row that is the first row, follows a long row, or is the
-// first to start in its granule of kTileGranule entries.  List order is irrelevant: rows / pieces are independent.
+// into pieces (a diagnostic of the row structure since k_splat_rows works by fixed entry tiles) -- a piece starts at a
+// short row that is the first row, follows a long row, or is the first to start in its granule of kTileGranule
+// entries.  List order is irrelevant: rows / pieces are independent.
 __global__ void __launch_bounds__(kThreads)
 k_row_classify(const int *__restrict__ row_ptr, const int *__restrict__ vtotal, int *__restrict__ lng,
                int *__restrict__ counts, int *__restrict__ piece_list) {
