@@ -261,9 +261,9 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__rest
 // sum only through its binade (the ulp) and its parity.  The binade at the start of every chunk is predictable from
 // plain (unordered) chunk sums, so ALL chunks of ALL long rows are composed in parallel, and the sequential part
 // shrinks to one O(1) step per chunk:
-//   k_scan_sums     per (chunk, label): unordered fp32 sum of the chunk's products            (parallel)
-//   k_scan_compose  per (chunk, label): predicted start sum -> binade E; composite (a0, a1) of the chunk under that
-//                   binade and the range of start values for which no prefix leaves the binade (parallel)
+//   k_scan_compose  per (chunk, label): unordered fp32 sum of the chunk's products, published to the chunks behind it;
+//                   predicted start sum -> binade E; composite (a0, a1) of the chunk under that binade and the range
+//                   of start values for which no prefix leaves the binade (parallel)
 //   k_scan_walk     per (row, label): walks the chunk records; a record applies iff the true running sum is in
 //                   the predicted binade and inside the record's safe range -- then s <- (m + a_parity) * ulp,
 //                   exactly what the entry-by-entry additions would give.  Otherwise (the chunk that contains a
