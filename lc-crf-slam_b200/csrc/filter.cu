@@ -424,9 +424,10 @@ __device__ __forceinline__ Composite block_composite(ScanPair tot, int hi0, int 
 // per-thread composite of the products c[0..IT) under the binade with ulp 1/inv_u (same arithmetic as row_sum_exact)
 template <int IT, bool MONO>
 __device__ __forceinline__ void thread_composite(const float *c, int n_valid, float inv_u, ScanPair &tot, int &hi0,
-                                                 int &lo0, int &hi1, int &lo1) {
+                                                 int &lo0, int &hi1, int &lo1, bool &tie) {
     tot.a0 = tot.a1 = 0;
     hi0 = lo0 = hi1 = lo1 = 0;
+    tie = false;
 #pragma unroll
     for (int q = 0; q < IT; q++) {
         if (q < n_valid) {
@@ -444,6 +445,7 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
                 tot.a0 += inc1;
                 tot.a1 += inc1;
             } else {           // tie: round half to even
+                tie = true;
                 ScanPair a;
                 a.a0 = ni + (ni & 1);
                 a.a1 = ni + ((ni + 1) & 1);
@@ -460,43 +462,67 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
 }
 
 struct ComposeScratch {
-    double red[8];
-    double wpre[8];
+    float red[8];
+    float wpre[8];
     int wneg[8];  // warp w holds a negative product
+    int wsum[2][8];
     ComposeShared cs;
-    double pred;
     int tcross;
 };
 
+// Sums of the thread totals over the threads with inA / inB (block-wide, both at once): the composite of a chunk without
+// ties and without negative products is just the sum of its increments (a0 == a1, prefixes grow from 0 to the total).
+__device__ __forceinline__ void block_sums(int v, bool inA, bool inB, int tid, ComposeScratch &sc, Composite &A, Composite &B) {
+    const int lane = tid & 31, wid = tid >> 5;
+    const int sa = __reduce_add_sync(0xffffffffu, inA ? v : 0), sb = __reduce_add_sync(0xffffffffu, inB ? v : 0);
+    if (lane == 0) {
+        sc.wsum[0][wid] = sa;
+        sc.wsum[1][wid] = sb;
+    }
+    __syncthreads();
+    int ta = 0, tb = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        ta += sc.wsum[0][w];
+        tb += sc.wsum[1][w];
+    }
+    A.a0 = A.a1 = A.hi0 = A.hi1 = ta;
+    A.lo0 = A.lo1 = 0;
+    B.a0 = B.a1 = B.hi0 = B.hi1 = tb;
+    B.lo0 = B.lo1 = 0;
+}
+
 // composite record of one (chunk, label): cq = this thread's products (thread t owns entries [t*IT, (t+1)*IT) of the
-// chunk), n_valid of them inside the chunk.  Called by all 256 threads (barriers inside).
+// chunk), n_valid of them inside the chunk.  Called by all 256 threads (barriers inside).  Everything up to the choice of
+// the binade is a PREDICTION (fp32 sums in tree order are plenty: the margins below are 1e-4 and 2e-5, and a record
+// that was built on a wrong prediction is rejected by k_scan_walk).
 template <int IT>
 __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, const int4 g, int c, int l, int L,
                                             const unsigned long long *chunk_sum, unsigned tag,
                                             ChunkRec *__restrict__ rec_out, int tid, ComposeScratch &sc) {
     const int lane = tid & 31, wid = tid >> 5;
     // predicted running sum at the start of the chunk = sum of the previous chunks of the row (published by their tasks)
-    double part = 0.0;
-    for (int j = g.z + tid; j < c; j += 256) part += (double)poll_sum(chunk_sum + (size_t)j * L + l, tag);
+    float part = 0.0f;
+    for (int j = g.z + tid; j < c; j += 256) part += poll_sum(chunk_sum + (size_t)j * L + l, tag);
 #pragma unroll
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     __syncthreads();  // the previous use of the scratch is over
     if (lane == 0) sc.red[wid] = part;
     if (tid == 0) sc.tcross = 256;
-    // thread-local sums of the products (double: a prediction of where the sum crosses the binade)
-    double lsum = 0.0;
+    // thread-local sums of the products (a prediction of where the sum crosses the binade)
+    float lsum = 0.0f;
     bool my_zero = true, my_neg = false;
 #pragma unroll
     for (int q = 0; q < IT; q++) {
-        if (q < n_valid) lsum += (double)cq[q];
+        if (q < n_valid) lsum += cq[q];
         my_zero = my_zero && (q >= n_valid || cq[q] == 0.0f);
         my_neg = my_neg || (q < n_valid && !(cq[q] >= 0.0f));  // NaN counts as negative: full tracking
     }
     const bool warp_neg = __any_sync(0xffffffffu, my_neg);
-    double incl = lsum;  // inclusive prefix of the thread sums over the warp
+    float incl = lsum;  // inclusive prefix of the thread sums over the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        const float y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
     }
     if (lane == 31) {
@@ -507,7 +533,7 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
         if (tid == 0) rec_out->kind = kRecZero;
         return;
     }
-    double sp = 0.0, wbase = 0.0, total = 0.0;
+    float sp = 0.0f, wbase = 0.0f, total = 0.0f;
     int any_neg = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
@@ -516,71 +542,63 @@ __device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, 
         total += sc.wpre[w];
         any_neg |= sc.wneg[w];
     }
-    const double p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
-    total += sp;                                    // predicted running sum at the end of the chunk
-    const float spf = (float)sp;
-    const int E = ((__float_as_int(spf) >> 23) & 0xff) - 127;
-    const bool regular = (spf > 0.0f) && E >= -100 && E <= 100;
-    const double top = (double)__int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
+    const float p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
+    total += sp;                                   // predicted running sum at the end of the chunk
+    const int E = ((__float_as_int(sp) >> 23) & 0xff) - 127;
+    const bool regular = (sp > 0.0f) && E >= -100 && E <= 100;
+    const float top = __int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
     int kind = kRecNone;
     if (regular) {
-        if (total < top * (1.0 - 1e-4)) kind = kRecPlain;
-        else if (total < 2.0 * top * (1.0 - 1e-4)) kind = kRecCross;
+        if (total < top * (1.0f - 1e-4f)) kind = kRecPlain;
+        else if (total < 2.0f * top * (1.0f - 1e-4f)) kind = kRecCross;
     }
     if (kind == kRecNone) {  // (uniform)
         if (tid == 0) rec_out->kind = kRecNone;
         return;
     }
     const float inv_u = __int_as_float((23 - E + 127) << 23);
+    int tw = 0;
+    bool inA = true, inB = false;
+    if (kind == kRecCross) {  // (uniform)
+        // crossing: the first thread behind whose entries the predicted sum reaches 2^(E+1) (with a small safety
+        // margin: the true fp32 running sum differs from the prediction by rounding noise only)
+        if (p_end_thread >= top * (1.0f - 2e-5f)) atomicMin(&sc.tcross, tid);
+        __syncthreads();
+        tw = max(0, min(sc.tcross - 1, 256 - kWinThreads));  // window = threads [tw, tw + kWinThreads)
+        inA = tid < tw;
+        inB = tid >= tw + kWinThreads;
+    }
     ScanPair tot;
     int hi0, lo0, hi1, lo1;
-    if (kind == kRecPlain) {
-        Composite A;
-        if (any_neg) {  // (uniform)
-            thread_composite<IT, false>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
-            A = block_composite<false>(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
-        } else {
-            thread_composite<IT, true>(cq, n_valid, inv_u, tot, hi0, lo0, hi1, lo1);
-            A = block_composite<true>(tot, hi0, lo0, hi1, lo1, true, tid, sc.cs);
-        }
-        if (tid == 0) {
-            rec_out->kind = kRecPlain;
-            rec_out->E = E;
-            rec_out->A = A;
-        }
-        return;
-    }
-    // crossing: the first thread behind whose entries the predicted sum reaches 2^(E+1) (with a small safety
-    // margin: the true fp32 running sum differs from the prediction by rounding noise only)
-    if (p_end_thread >= top * (1.0 - 2e-5)) atomicMin(&sc.tcross, tid);
-    __syncthreads();
-    int tw = sc.tcross - 1;  // window = threads [tw, tw + kWinThreads)
-    tw = max(0, min(tw, 256 - kWinThreads));
-    const bool inA = tid < tw, inB = tid >= tw + kWinThreads;
+    bool tie;
     Composite A, Bc;
     if (any_neg) {  // (uniform)
-        thread_composite<IT, false>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
+        thread_composite<IT, false>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1, tie);
         A = block_composite<false>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
-        Bc = block_composite<false>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+        if (kind == kRecCross) Bc = block_composite<false>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
     } else {
-        thread_composite<IT, true>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1);
-        A = block_composite<true>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
-        Bc = block_composite<true>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+        thread_composite<IT, true>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1, tie);
+        if (__syncthreads_or(tie)) {  // (uniform) round-half-even somewhere in the chunk: parity-dependent composites
+            A = block_composite<true>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
+            if (kind == kRecCross) Bc = block_composite<true>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
+        } else {
+            block_sums(tot.a0, inA, inB, tid, sc, A, Bc);
+        }
     }
-    if (!inA && !inB) {
+    if (kind == kRecCross && !inA && !inB) {
 #pragma unroll
         for (int q = 0; q < IT; q++) rec_out->win[(tid - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;
     }
     if (tid == 0) {
-        rec_out->kind = kRecCross;
+        rec_out->kind = kind;
         rec_out->E = E;
         rec_out->A = A;
-        rec_out->B = Bc;
+        if (kind == kRecCross) rec_out->B = Bc;
     }
 }
 
 template <int LG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
                const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
                const int4 *__restrict__ chunk_desc, unsigned long long *chunk_sum, ChunkRec *__restrict__ rec, int L) {
