@@ -261,9 +261,10 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__rest
 // sum only through its binade (the ulp) and its parity.  The binade at the start of every chunk is predictable from
 // plain (unordered) chunk sums, so ALL chunks of ALL long rows are composed in parallel, and the sequential part
 // shrinks to one O(1) step per chunk:
-//   k_scan_compose  per (chunk, label): unordered fp32 sum of the chunk's products, published to the chunks behind it;
-//                   predicted start sum -> binade E; composite (a0, a1) of the chunk under that binade and the range
-//                   of start values for which no prefix leaves the binade (parallel)
+//   k_scan_compose  per (chunk, label), one WARP per task: unordered fp32 sum of the chunk's products, published to the
+//                   chunks behind it; predicted start sum -> binade E; composite (a0, a1) of the chunk under that
+//                   binade and the range of start values for which no prefix leaves the binade (parallel); the row
+//                   heads (start value +0) are summed for real
 //   k_scan_walk     per (row, label): walks the chunk records; a record applies iff the true running sum is in
 //                   the predicted binade and inside the record's safe range -- then s <- (m + a_parity) * ulp,
 //                   exactly what the entry-by-entry additions would give.  Otherwise (the chunk that contains a
@@ -274,13 +275,13 @@ __device__ float row_sum_exact(const int2 *__restrict__ ent, const float *__rest
 //   kRecExact  s_exact = the exact running sum at the END of the chunk (row heads: the start value 0 is known)
 //   kRecPlain  composite A covers the whole chunk under binade E
 //   kRecCross  the running sum is predicted to cross from binade E to E+1 inside the chunk: composite A covers the
-//              threads before the crossing window (binade E), win[] holds the kWinEntries products of the window
-//              (added for real by the walk), composite B covers the threads behind it (binade E+1)
+//              entries before the crossing window (binade E), win[] holds the products of the window (32 entries,
+//              added for real by the walk), composite B covers the entries behind it (binade E+1)
 //   kRecZero   every product of the chunk is +-0: the chunk leaves any running sum unchanged (a row start is +0 and a
 //              running sum never becomes -0, so adding +-0 is the identity) -- typical for a label whose marginal
 //              hit the fast_exp cut-off on all points of a vertex
 enum { kRecNone = 0, kRecExact = 1, kRecPlain = 2, kRecCross = 3, kRecZero = 4 };
-constexpr int kWinThreads = 4;                     // threads of the compose team covered by the crossing window
+constexpr int kWinThreads = 4;                     // lanes (of 8 entries each) covered by the crossing window
 struct Composite {
     int a0, a1;              // total increment in ulps for an even / odd start mantissa
     int lo0, hi0, lo1, hi1;  // extreme prefix increments for an even / odd start
@@ -298,7 +299,7 @@ static_assert(sizeof(ChunkRec) == kChunkRecBytes, "engine.cuh: kChunkRecBytes mu
 
 // chunk descriptor (csr.cu: k_long_chunks): {first entry, one past the last entry, index of the row's first chunk,
 // index of the row in the long list}
-constexpr int kScanIT = kScanChunk / 256;  // entries per thread of a 256-thread team
+constexpr int kScanIT = kScanChunk / 256;  // entries per lane and round (a warp walks a chunk in rounds of 256 entries)
 
 // labels handled per (chunk, label-group) task: the float2 of a point serves both labels of the SLAM CRF
 static inline int scan_labels(int L) { return L >= 2 ? 2 : 1; }
@@ -313,112 +314,6 @@ __device__ __forceinline__ void gather_labels(const float *__restrict__ in, int 
 #pragma unroll
         for (int j = 0; j < LG; j++) x[j] = (valid && lb + j < L) ? __ldg(in + (size_t)pt * L + lb + j) : 0.0f;
     }
-}
-
-// Unordered fp32 sums of the chunks (predictions of where the running sum of a row stands at a chunk start) are exchanged
-// between the CTAs of ONE k_scan_compose launch: every task publishes the sum of its chunk as {call tag, sum} in one 64-bit
-// word before it looks at anybody else's, and polls the words of the chunks in front of it in its row.  Tickets are handed
-// out in chunk order and a task publishes before it waits, so a waiting CTA only ever waits for CTAs that are running.
-// The tag (counts[8] + 1, bumped by k_scan_walk behind every compose launch) tells this call's words from stale ones; a
-// stale or wrapped tag could only spoil a prediction, never a result (k_scan_walk verifies every record it applies).
-__device__ __forceinline__ void publish_sum(unsigned long long *p, unsigned tag, float sum) {
-    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(sum);
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ float poll_sum(const unsigned long long *p, unsigned tag) {
-    unsigned long long w;
-    for (;;) {
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-        if ((unsigned)(w >> 32) == tag) break;
-        __nanosleep(64);
-    }
-    return __uint_as_float((unsigned)w);
-}
-
-// block-wide composite of the per-thread composites of the threads in [t_lo, t_hi) (others contribute the identity):
-// returns, in every thread, the composite of the whole range and its safe start range.  256 threads.
-struct ComposeShared {
-    ScanPair wtot[8];
-    int bnd[8][4];
-};
-// MONO: every product of the chunk is >= 0 (block-uniform; the CRF's case -- barycentric weights and marginals are
-// non-negative), so prefixes only grow: the extreme prefix increments are 0 and the total, no range tracking needed.
-template <bool MONO>
-__device__ __forceinline__ Composite block_composite(ScanPair tot, int hi0, int lo0, int hi1, int lo1, bool active,
-                                                     int tid, ComposeShared &sh) {
-    const int lane = tid & 31, wid = tid >> 5;
-    if (!active) {
-        tot.a0 = tot.a1 = 0;
-        hi0 = lo0 = hi1 = lo1 = 0;
-    }
-    ScanPair inc = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        ScanPair lft;
-        lft.a0 = __shfl_up_sync(0xffffffffu, inc.a0, o);
-        lft.a1 = __shfl_up_sync(0xffffffffu, inc.a1, o);
-        if (lane >= o) inc = scan_combine(lft, inc);
-    }
-    ScanPair exc;
-    exc.a0 = __shfl_up_sync(0xffffffffu, inc.a0, 1);
-    exc.a1 = __shfl_up_sync(0xffffffffu, inc.a1, 1);
-    if (lane == 0) exc.a0 = exc.a1 = 0;
-    __syncthreads();  // previous use of sh is over
-    if (lane == 31) sh.wtot[wid] = inc;
-    __syncthreads();
-    ScanPair w = sh.wtot[lane < 8 ? lane : 0];
-    if (lane >= 8) w.a0 = w.a1 = 0;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        ScanPair lft;
-        lft.a0 = __shfl_up_sync(0xffffffffu, w.a0, o);
-        lft.a1 = __shfl_up_sync(0xffffffffu, w.a1, o);
-        if (lane >= o) w = scan_combine(lft, w);
-    }
-    ScanPair wp;
-    wp.a0 = __shfl_sync(0xffffffffu, w.a0, wid > 0 ? wid - 1 : 0);
-    wp.a1 = __shfl_sync(0xffffffffu, w.a1, wid > 0 ? wid - 1 : 0);
-    if (wid > 0) exc = scan_combine(wp, exc);
-    Composite c;
-    c.a0 = __shfl_sync(0xffffffffu, w.a0, 7);
-    c.a1 = __shfl_sync(0xffffffffu, w.a1, 7);
-    if (MONO) {
-        c.lo0 = c.lo1 = 0;
-        c.hi0 = c.a0;
-        c.hi1 = c.a1;
-        return c;
-    }
-    // safe range: for a start of parity p this thread begins at offset exc.a_p with parity (p + exc.a_p) & 1
-    int b_lo0 = exc.a0 + ((exc.a0 & 1) ? lo1 : lo0), b_hi0 = exc.a0 + ((exc.a0 & 1) ? hi1 : hi0);
-    int b_lo1 = exc.a1 + ((exc.a1 & 1) ? lo0 : lo1), b_hi1 = exc.a1 + ((exc.a1 & 1) ? hi0 : hi1);
-    if (!active) {  // identity threads must not widen the range with offsets of ranges they do not belong to
-        b_lo0 = b_lo1 = INT_MAX;
-        b_hi0 = b_hi1 = INT_MIN;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        b_lo0 = min(b_lo0, __shfl_xor_sync(0xffffffffu, b_lo0, o));
-        b_hi0 = max(b_hi0, __shfl_xor_sync(0xffffffffu, b_hi0, o));
-        b_lo1 = min(b_lo1, __shfl_xor_sync(0xffffffffu, b_lo1, o));
-        b_hi1 = max(b_hi1, __shfl_xor_sync(0xffffffffu, b_hi1, o));
-    }
-    if (lane == 0) {
-        sh.bnd[wid][0] = b_lo0;
-        sh.bnd[wid][1] = b_hi0;
-        sh.bnd[wid][2] = b_lo1;
-        sh.bnd[wid][3] = b_hi1;
-    }
-    __syncthreads();
-    c.lo0 = c.lo1 = 0;  // the start itself is a prefix
-    c.hi0 = c.hi1 = 0;
-#pragma unroll
-    for (int w8 = 0; w8 < 8; w8++) {
-        c.lo0 = min(c.lo0, sh.bnd[w8][0]);
-        c.hi0 = max(c.hi0, sh.bnd[w8][1]);
-        c.lo1 = min(c.lo1, sh.bnd[w8][2]);
-        c.hi1 = max(c.hi1, sh.bnd[w8][3]);
-    }
-    return c;
 }
 
 // per-thread composite of the products c[0..IT) under the binade with ulp 1/inv_u (same arithmetic as row_sum_exact)
@@ -461,223 +356,365 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
     }
 }
 
-struct ComposeScratch {
-    float red[8];
-    float wpre[8];
-    int wneg[8];  // warp w holds a negative product
-    int wsum[2][8];
-    ComposeShared cs;
-    int tcross;
-};
-
-// Sums of the thread totals over the threads with inA / inB (block-wide, both at once): the composite of a chunk without
-// ties and without negative products is just the sum of its increments (a0 == a1, prefixes grow from 0 to the total).
-__device__ __forceinline__ void block_sums(int v, bool inA, bool inB, int tid, ComposeScratch &sc, Composite &A, Composite &B) {
-    const int lane = tid & 31, wid = tid >> 5;
-    const int sa = __reduce_add_sync(0xffffffffu, inA ? v : 0), sb = __reduce_add_sync(0xffffffffu, inB ? v : 0);
-    if (lane == 0) {
-        sc.wsum[0][wid] = sa;
-        sc.wsum[1][wid] = sb;
+// ---- composites: one warp owns a (chunk, label group) task and walks the chunk in rounds of 256 entries (lane-contiguous,
+// 8 entries per lane and round); nothing needs a CTA barrier.  (Round 1 and most of round 2 ran one CTA per chunk with
+// block-wide scans: the same instruction count, but barrier-coupled; this form is 1.5 % faster per step beside the other
+// stream's kernels.)
+//   phase 1 (tickets counts[9]): unordered sum + "has a negative product" / "all products are +-0" flags of every chunk,
+//            published as ONE 64-bit word {call tag, flags, sum} (st.relaxed.gpu); all-zero chunks get their kRecZero
+//            record right here
+//   heads   (static, first CTAs): the first chunk of every long row, summed for real
+//   phase 2 (tickets counts[3]): composites; the prediction polls (ld.relaxed.gpu) the words of the chunks in front
+// Tickets are taken by running warps only and a word is published without waiting for anything, so a polling warp only
+// ever waits for warps that are running -- no residency assumption.  The tag (bumped by k_scan_walk behind every
+// compose launch) tells this call's words from older ones.
+constexpr unsigned kPubNeg = 2u, kPubZero = 1u;
+__device__ __forceinline__ void publish_word(unsigned long long *p, unsigned tag, unsigned flags, float sum) {
+    const unsigned long long w = ((unsigned long long)((tag << 2) | flags) << 32) | (unsigned long long)__float_as_uint(sum);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ float poll_word(const unsigned long long *p, unsigned tag, unsigned &flags) {
+    unsigned long long w;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+        if ((unsigned)(w >> 34) == tag) break;
+        __nanosleep(64);
     }
-    __syncthreads();
-    int ta = 0, tb = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        ta += sc.wsum[0][w];
-        tb += sc.wsum[1][w];
-    }
-    A.a0 = A.a1 = A.hi0 = A.hi1 = ta;
-    A.lo0 = A.lo1 = 0;
-    B.a0 = B.a1 = B.hi0 = B.hi1 = tb;
-    B.lo0 = B.lo1 = 0;
+    flags = (unsigned)(w >> 32) & 3u;
+    return __uint_as_float((unsigned)w);
 }
 
-// composite record of one (chunk, label): cq = this thread's products (thread t owns entries [t*IT, (t+1)*IT) of the
-// chunk), n_valid of them inside the chunk.  Called by all 256 threads (barriers inside).  Everything up to the choice of
-// the binade is a PREDICTION (fp32 sums in tree order are plenty: the margins below are 1e-4 and 2e-5, and a record
-// that was built on a wrong prediction is rejected by k_scan_walk).
-template <int IT>
-__device__ __forceinline__ void compose_one(const float (&cq)[IT], int n_valid, const int4 g, int c, int l, int L,
-                                            const unsigned long long *chunk_sum, unsigned tag,
-                                            ChunkRec *__restrict__ rec_out, int tid, ComposeScratch &sc) {
-    const int lane = tid & 31, wid = tid >> 5;
-    // predicted running sum at the start of the chunk = sum of the previous chunks of the row (published by their tasks)
-    float part = 0.0f;
-    for (int j = g.z + tid; j < c; j += 256) part += poll_sum(chunk_sum + (size_t)j * L + l, tag);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncthreads();  // the previous use of the scratch is over
-    if (lane == 0) sc.red[wid] = part;
-    if (tid == 0) sc.tcross = 256;
-    // thread-local sums of the products (a prediction of where the sum crosses the binade)
-    float lsum = 0.0f;
-    bool my_zero = true, my_neg = false;
-#pragma unroll
-    for (int q = 0; q < IT; q++) {
-        if (q < n_valid) lsum += cq[q];
-        my_zero = my_zero && (q >= n_valid || cq[q] == 0.0f);
-        my_neg = my_neg || (q < n_valid && !(cq[q] >= 0.0f));  // NaN counts as negative: full tracking
+// composite of the lanes with `active` of one round (uniform result): total increments for an even / odd start and the
+// extreme prefix increments.  tie_any (uniform): some lane met a round-half-even tie, i.e. a0 != a1 somewhere.
+template <bool MONO>
+__device__ __forceinline__ Composite warp_round_composite(ScanPair tot, int hi0, int lo0, int hi1, int lo1, bool active,
+                                                          bool tie_any, int lane) {
+    Composite c;
+    if (!active) {
+        tot.a0 = tot.a1 = 0;
+        hi0 = lo0 = hi1 = lo1 = 0;
     }
-    const bool warp_neg = __any_sync(0xffffffffu, my_neg);
-    float incl = lsum;  // inclusive prefix of the thread sums over the warp
+    if (MONO && !tie_any) {  // plain sum of the increments
+        const int sm = __reduce_add_sync(0xffffffffu, tot.a0);
+        c.a0 = c.a1 = c.hi0 = c.hi1 = sm;
+        c.lo0 = c.lo1 = 0;
+        return c;
+    }
+    ScanPair inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        ScanPair lft;
+        lft.a0 = __shfl_up_sync(0xffffffffu, inc.a0, o);
+        lft.a1 = __shfl_up_sync(0xffffffffu, inc.a1, o);
+        if (lane >= o) inc = scan_combine(lft, inc);
+    }
+    c.a0 = __shfl_sync(0xffffffffu, inc.a0, 31);
+    c.a1 = __shfl_sync(0xffffffffu, inc.a1, 31);
+    if (MONO) {
+        c.lo0 = c.lo1 = 0;
+        c.hi0 = c.a0;
+        c.hi1 = c.a1;
+        return c;
+    }
+    ScanPair exc;
+    exc.a0 = __shfl_up_sync(0xffffffffu, inc.a0, 1);
+    exc.a1 = __shfl_up_sync(0xffffffffu, inc.a1, 1);
+    if (lane == 0) exc.a0 = exc.a1 = 0;
+    // for a start of parity p this lane begins at offset exc.a_p with parity (p + exc.a_p) & 1
+    int b_lo0 = exc.a0 + ((exc.a0 & 1) ? lo1 : lo0), b_hi0 = exc.a0 + ((exc.a0 & 1) ? hi1 : hi0);
+    int b_lo1 = exc.a1 + ((exc.a1 & 1) ? lo0 : lo1), b_hi1 = exc.a1 + ((exc.a1 & 1) ? hi0 : hi1);
+    if (!active) {  // identity lanes must not widen the range with offsets of ranges they do not belong to
+        b_lo0 = b_lo1 = 0;
+        b_hi0 = b_hi1 = 0;
+    }
+    c.lo0 = min(0, __reduce_min_sync(0xffffffffu, b_lo0));
+    c.hi0 = max(0, __reduce_max_sync(0xffffffffu, b_hi0));
+    c.lo1 = min(0, __reduce_min_sync(0xffffffffu, b_lo1));
+    c.hi1 = max(0, __reduce_max_sync(0xffffffffu, b_hi1));
+    return c;
+}
+
+// R <- R followed by C (both uniform)
+__device__ __forceinline__ void composite_append(Composite &R, const Composite &C) {
+    const int o0 = R.a0, o1 = R.a1;
+    R.lo0 = min(R.lo0, o0 + ((o0 & 1) ? C.lo1 : C.lo0));
+    R.hi0 = max(R.hi0, o0 + ((o0 & 1) ? C.hi1 : C.hi0));
+    R.lo1 = min(R.lo1, o1 + ((o1 & 1) ? C.lo0 : C.lo1));
+    R.hi1 = max(R.hi1, o1 + ((o1 & 1) ? C.hi0 : C.hi1));
+    R.a0 = o0 + ((o0 & 1) ? C.a1 : C.a0);
+    R.a1 = o1 + ((o1 & 1) ? C.a0 : C.a1);
+}
+
+// state of one label of a phase-2 task (uniform across the warp)
+struct LabelTask {
+    int kind, E;
+    bool mono, crossed;
+    float top, inv_u, P;  // 2^(E+1), 1/ulp of binade E, predicted running sum in front of the current round
+    Composite A, B;
+};
+
+template <bool MONO>
+__device__ __forceinline__ void label_round(LabelTask &T, const float (&cq)[kScanIT], int n_valid, int r, int lane,
+                                            ChunkRec *__restrict__ rec_out) {
+    constexpr int IT = kScanIT;
+    // predicted running sum behind this lane's entries of the round
+    float lsum = 0.0f;
+#pragma unroll
+    for (int q = 0; q < IT; q++)
+        if (q < n_valid) lsum += cq[q];
+    float incl = lsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const float y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
     }
-    if (lane == 31) {
-        sc.wpre[wid] = incl;
-        sc.wneg[wid] = warp_neg;
-    }
-    if (__syncthreads_and(my_zero)) {  // (uniform) every product is +-0: the chunk is the identity
-        if (tid == 0) rec_out->kind = kRecZero;
-        return;
-    }
-    float sp = 0.0f, wbase = 0.0f, total = 0.0f;
-    int any_neg = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        sp += sc.red[w];
-        if (w < wid) wbase += sc.wpre[w];
-        total += sc.wpre[w];
-        any_neg |= sc.wneg[w];
-    }
-    const float p_end_thread = sp + wbase + incl;  // predicted running sum behind this thread's entries
-    total += sp;                                   // predicted running sum at the end of the chunk
-    const int E = ((__float_as_int(sp) >> 23) & 0xff) - 127;
-    const bool regular = (sp > 0.0f) && E >= -100 && E <= 100;
-    const float top = __int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
-    int kind = kRecNone;
-    if (regular) {
-        if (total < top * (1.0f - 1e-4f)) kind = kRecPlain;
-        else if (total < 2.0f * top * (1.0f - 1e-4f)) kind = kRecCross;
-    }
-    if (kind == kRecNone) {  // (uniform)
-        if (tid == 0) rec_out->kind = kRecNone;
-        return;
-    }
-    const float inv_u = __int_as_float((23 - E + 127) << 23);
-    int tw = 0;
-    bool inA = true, inB = false;
-    if (kind == kRecCross) {  // (uniform)
-        // crossing: the first thread behind whose entries the predicted sum reaches 2^(E+1) (with a small safety
-        // margin: the true fp32 running sum differs from the prediction by rounding noise only)
-        if (p_end_thread >= top * (1.0f - 2e-5f)) atomicMin(&sc.tcross, tid);
-        __syncthreads();
-        tw = max(0, min(sc.tcross - 1, 256 - kWinThreads));  // window = threads [tw, tw + kWinThreads)
-        inA = tid < tw;
-        inB = tid >= tw + kWinThreads;
+    const float p_end = T.P + incl;
+    T.P += __shfl_sync(0xffffffffu, incl, 31);
+    bool inA = !T.crossed, inB = T.crossed;
+    int tw = -1;
+    if (T.kind == kRecCross && !T.crossed) {  // (uniform)
+        // the crossing: the first lane behind whose entries the predicted sum reaches 2^(E+1) (with a small safety margin:
+        // the true fp32 running sum differs from the prediction by rounding noise only); the window starts one lane
+        // earlier.  A chunk that never gets there keeps its window on the last four lanes of the last round.
+        const unsigned hit = __ballot_sync(0xffffffffu, p_end >= T.top * (1.0f - 2e-5f));
+        if (hit || r == kScanChunk / 256 - 1) {
+            tw = hit ? __ffs(hit) - 2 : 32 - kWinThreads;
+            tw = max(0, min(tw, 32 - kWinThreads));
+            inA = lane < tw;
+            inB = lane >= tw + kWinThreads;
+            T.crossed = true;
+        }
     }
     ScanPair tot;
     int hi0, lo0, hi1, lo1;
     bool tie;
-    Composite A, Bc;
-    if (any_neg) {  // (uniform)
-        thread_composite<IT, false>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1, tie);
-        A = block_composite<false>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
-        if (kind == kRecCross) Bc = block_composite<false>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
-    } else {
-        thread_composite<IT, true>(cq, n_valid, inB ? __fmul_rn(inv_u, 0.5f) : inv_u, tot, hi0, lo0, hi1, lo1, tie);
-        if (__syncthreads_or(tie)) {  // (uniform) round-half-even somewhere in the chunk: parity-dependent composites
-            A = block_composite<true>(tot, hi0, lo0, hi1, lo1, inA, tid, sc.cs);
-            if (kind == kRecCross) Bc = block_composite<true>(tot, hi0, lo0, hi1, lo1, inB, tid, sc.cs);
-        } else {
-            block_sums(tot.a0, inA, inB, tid, sc, A, Bc);
-        }
-    }
-    if (kind == kRecCross && !inA && !inB) {
+    thread_composite<IT, MONO>(cq, n_valid, inB ? __fmul_rn(T.inv_u, 0.5f) : T.inv_u, tot, hi0, lo0, hi1, lo1, tie);
+    const bool tie_any = __any_sync(0xffffffffu, tie);
+    if (tw >= 0) {  // (uniform) the crossing round: lanes before the window -> A, behind it -> B, the window itself is stored
+        composite_append(T.A, warp_round_composite<MONO>(tot, hi0, lo0, hi1, lo1, inA, tie_any, lane));
+        composite_append(T.B, warp_round_composite<MONO>(tot, hi0, lo0, hi1, lo1, inB, tie_any, lane));
+        if (!inA && !inB) {
 #pragma unroll
-        for (int q = 0; q < IT; q++) rec_out->win[(tid - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;
-    }
-    if (tid == 0) {
-        rec_out->kind = kind;
-        rec_out->E = E;
-        rec_out->A = A;
-        if (kind == kRecCross) rec_out->B = Bc;
+            for (int q = 0; q < IT; q++) rec_out->win[(lane - tw) * IT + q] = q < n_valid ? cq[q] : 0.0f;
+        }
+    } else if (inB) {  // (uniform)
+        composite_append(T.B, warp_round_composite<MONO>(tot, hi0, lo0, hi1, lo1, true, tie_any, lane));
+    } else {
+        composite_append(T.A, warp_round_composite<MONO>(tot, hi0, lo0, hi1, lo1, true, tie_any, lane));
     }
 }
 
 template <int LG>
 __global__ void __launch_bounds__(256, 3)
 k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-               const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
-               const int4 *__restrict__ chunk_desc, unsigned long long *chunk_sum, ChunkRec *__restrict__ rec, int L) {
-    constexpr int IT = kScanIT;
-    __shared__ ComposeScratch s_sc;
-    __shared__ ScanShared<1> sh1[8];
-    __shared__ float s_w[8][LG];
-    __shared__ int s_ticket;
+                 const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
+                 const int4 *__restrict__ chunk_desc, unsigned long long *chunk_sum, ChunkRec *__restrict__ rec, int L) {
+    constexpr int IT = kScanIT, NR = kScanChunk / 256;
+    __shared__ float s_head[8][256 * LG];
     const int ngrp = (L + LG - 1) / LG;
     const long long n = (long long)counts[1] * ngrp;
     const int nlong = counts[0];
-    const unsigned tag = (unsigned)counts[8] + 1u;
+    const unsigned tag = ((unsigned)counts[8] & 0x1fffffffu) + 1u;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // Row heads: the start value (0) is known, so the exact sum of a row's first chunk is computed right here,
-    // in parallel with everything else, one head per WARP (warp-level re-scans are cheap, and binade crossings are
-    // dense at a row start).  The first CTAs of the grid take the heads, 8 per CTA; they are resident from the start
-    // of the launch, so the long head tasks overlap with all the short composite tasks.
-    {
-        const long long nheads = (long long)nlong * L;
-        for (long long hk = (long long)blockIdx.x * 8 + wid; hk < nheads; hk += (long long)gridDim.x * 8) {
-            const int i = (int)(hk / L), l = (int)(hk % L);
-            const int v = __ldg(list + i);
-            const int e0 = __ldg(row_ptr + v), e1 = min(e0 + kScanChunk, __ldg(row_ptr + v + 1));
-            const float s = row_sum_exact<1, IT>(ent, in, e0, e1, L, l, lane, sh1[wid], 0.0f);
-            if (lane == 0) {
-                const size_t k = (size_t)__ldg(long_chunk0 + i) * L + l;
-                rec[k].kind = kRecExact;
-                rec[k].s_exact = s;
-            }
-        }
-    }
-    // all other chunks: dynamic tickets (counts[3], zeroed by the lattice build and by k_scan_walk) keep the CTAs that
-    // did heads from lagging
+    // ---- phase 1
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(counts + 3, 1);
-        __syncthreads();
-        const long long k = s_ticket;
+        long long k = 0;
+        if (lane == 0) k = atomicAdd(counts + 9, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n) break;
         const int c = (int)(k / ngrp), lb = (int)(k % ngrp) * LG;
         const int4 g = __ldg(chunk_desc + c);
-        // entries of this chunk (thread-contiguous: thread t owns entries [t*IT, (t+1)*IT) of the chunk)
-        int2 t[IT];
-        float x[IT][LG];
-#pragma unroll
-        for (int q = 0; q < IT; q++) {
-            const int e = g.x + tid * IT + q;
-            t[q] = e < g.y ? __ldg(ent + e) : make_int2(0, 0);
-        }
-#pragma unroll
-        for (int q = 0; q < IT; q++) gather_labels<LG>(in, t[q].x, L, lb, g.x + tid * IT + q < g.y, x[q]);
-        const int n_valid = max(0, min(IT, g.y - (g.x + tid * IT)));
-        {   // this chunk's unordered sums, published before the composites wait for the chunks in front
-            float acc[LG];
-#pragma unroll
-            for (int j = 0; j < LG; j++) {
-                acc[j] = 0.0f;
-#pragma unroll
-                for (int q = 0; q < IT; q++) acc[j] += __int_as_float(t[q].y) * x[q][j];  // (out-of-range entries are 0 * 0)
-#pragma unroll
-                for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-                if (lane == 0) s_w[wid][j] = acc[j];
-            }
-            __syncthreads();
-            if (tid < LG && lb + tid < L) {
-                float tot = 0.0f;
-#pragma unroll
-                for (int w = 0; w < 8; w++) tot += s_w[w][tid];
-                publish_sum(chunk_sum + (size_t)c * L + lb + tid, tag, tot);
-            }
-        }
-        if (c == g.z) continue;  // a row head: its exact sum is computed above, only the prediction was missing
+        float acc[LG];
+        bool zero[LG], neg[LG];
 #pragma unroll
         for (int j = 0; j < LG; j++) {
-            if (lb + j < L) {  // (uniform)
-                float cq[IT];
+            acc[j] = 0.0f;
+            zero[j] = true;
+            neg[j] = false;
+        }
+        for (int e = g.x + lane; e < g.y; e += 32 * 8) {  // eight entries per lane in flight (the loop is latency-bound)
+            int2 t[8];
+            float x[8][LG];
 #pragma unroll
-                for (int q = 0; q < IT; q++) cq[q] = __fmul_rn(__int_as_float(t[q].y), x[q][j]);
-                compose_one<IT>(cq, n_valid, g, c, lb + j, L, chunk_sum, tag, rec + (size_t)c * L + lb + j, tid, s_sc);
+            for (int q = 0; q < 8; q++) t[q] = e + 32 * q < g.y ? __ldg(ent + e + 32 * q) : make_int2(0, 0);
+#pragma unroll
+            for (int q = 0; q < 8; q++) gather_labels<LG>(in, t[q].x, L, lb, e + 32 * q < g.y, x[q]);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (e + 32 * q < g.y) {
+#pragma unroll
+                    for (int j = 0; j < LG; j++) {
+                        const float pr = __fmul_rn(__int_as_float(t[q].y), x[q][j]);
+                        acc[j] += pr;
+                        zero[j] = zero[j] && pr == 0.0f;
+                        neg[j] = neg[j] || !(pr >= 0.0f);  // NaN counts as negative: full tracking
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < LG; j++) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            const bool z = __all_sync(0xffffffffu, zero[j]), ng = __any_sync(0xffffffffu, neg[j]);
+            if (lane == 0 && lb + j < L) {
+                // every product is +-0: the chunk is the identity (a row head keeps its exact record)
+                if (z && c != g.z) rec[(size_t)c * L + lb + j].kind = kRecZero;
+                publish_word(chunk_sum + (size_t)c * L + lb + j, tag, (z ? kPubZero : 0u) | (ng ? kPubNeg : 0u), acc[j]);
+            }
+        }
+    }
+    // ---- row heads: the start value (+0) is known, so the first chunk of a row is summed for real, front to back, by ONE
+    // lane per label: the warp stages the products of a round (256 entries, coalesced) in shared memory, the lane adds
+    // them in order -- 4 cycles per entry, 2048 entries in about 5 microseconds.  (A parallel exact scan is slower here:
+    // binade crossings are dense at a row start, and every crossing restarts the scan.)  The first CTAs of the grid take
+    // the heads, 8 per CTA.
+    {
+        const long long nheads = (long long)nlong * ngrp;
+        for (long long hk = (long long)blockIdx.x * 8 + wid; hk < nheads; hk += (long long)gridDim.x * 8) {
+            const int i = (int)(hk / ngrp), lb = (int)(hk % ngrp) * LG;
+            const int v = __ldg(list + i);
+            const int e0 = __ldg(row_ptr + v), e1 = min(e0 + kScanChunk, __ldg(row_ptr + v + 1));
+            float *stage = s_head[wid];
+            float sum = 0.0f;
+            int2 tn[IT];
+            float xn[IT][LG];
+#pragma unroll
+            for (int q = 0; q < IT; q++) {
+                const int e = e0 + lane * IT + q;
+                tn[q] = e < e1 ? __ldg(ent + e) : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < IT; q++) gather_labels<LG>(in, tn[q].x, L, lb, e0 + lane * IT + q < e1, xn[q]);
+            for (int r = 0; r < NR && e0 + r * 256 < e1; r++) {
+#pragma unroll
+                for (int q = 0; q < IT; q++)
+#pragma unroll
+                    for (int j = 0; j < LG; j++) stage[(lane * IT + q) * LG + j] = __fmul_rn(__int_as_float(tn[q].y), xn[q][j]);
+                if (r + 1 < NR) {
+#pragma unroll
+                    for (int q = 0; q < IT; q++) {
+                        const int e = e0 + (r + 1) * 256 + lane * IT + q;
+                        tn[q] = e < e1 ? __ldg(ent + e) : make_int2(0, 0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < IT; q++) gather_labels<LG>(in, tn[q].x, L, lb, e0 + (r + 1) * 256 + lane * IT + q < e1, xn[q]);
+                }
+                __syncwarp();
+                const int cnt = min(256, e1 - (e0 + r * 256));
+                if (lane < LG) {
+                    int i2 = 0;
+                    for (; i2 + 8 <= cnt; i2 += 8) {  // eight operands in flight, then the ordered chain
+                        float y[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) y[q] = stage[(i2 + q) * LG + lane];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) sum = __fadd_rn(sum, y[q]);
+                    }
+                    for (; i2 < cnt; i2++) sum = __fadd_rn(sum, stage[i2 * LG + lane]);
+                }
+                __syncwarp();
+            }
+            if (lane < LG && lb + lane < L) {
+                const size_t k = (size_t)__ldg(long_chunk0 + i) * L + lb + lane;
+                rec[k].kind = kRecExact;
+                rec[k].s_exact = sum;
+            }
+        }
+    }
+    // ---- phase 2
+    for (;;) {
+        long long k = 0;
+        if (lane == 0) k = atomicAdd(counts + 3, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n) break;
+        const int c = (int)(k / ngrp), lb = (int)(k % ngrp) * LG;
+        const int4 g = __ldg(chunk_desc + c);
+        if (c == g.z) continue;  // a row head
+        LabelTask T[LG];
+        bool any_active = false;
+#pragma unroll
+        for (int j = 0; j < LG; j++) {
+            T[j].kind = -1;  // no record to write
+            if (lb + j >= L) continue;
+            unsigned fl, fdummy;
+            const float own = poll_word(chunk_sum + (size_t)c * L + lb + j, tag, fl);
+            float sp = 0.0f;
+            for (int jj = g.z + lane; jj < c; jj += 32) sp += poll_word(chunk_sum + (size_t)jj * L + lb + j, tag, fdummy);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            if (fl & kPubZero) continue;  // recorded in phase 1
+            const float total = sp + own;  // predicted running sum at the end of the chunk
+            const int E = ((__float_as_int(sp) >> 23) & 0xff) - 127;
+            const bool regular = (sp > 0.0f) && E >= -100 && E <= 100;
+            const float top = __int_as_float((E + 1 + 127) << 23);  // 2^(E+1)
+            int kind = kRecNone;
+            if (regular) {
+                if (total < top * (1.0f - 1e-4f)) kind = kRecPlain;
+                else if (total < 2.0f * top * (1.0f - 1e-4f)) kind = kRecCross;
+            }
+            T[j].kind = kind;
+            T[j].E = E;
+            T[j].mono = !(fl & kPubNeg);
+            T[j].crossed = false;
+            T[j].top = top;
+            T[j].inv_u = __int_as_float((23 - E + 127) << 23);
+            T[j].P = sp;
+            T[j].A.a0 = T[j].A.a1 = T[j].A.lo0 = T[j].A.hi0 = T[j].A.lo1 = T[j].A.hi1 = 0;
+            T[j].B = T[j].A;
+            if (kind == kRecNone) {
+                if (lane == 0) rec[(size_t)c * L + lb + j].kind = kRecNone;
+            } else {
+                any_active = true;
+            }
+        }
+        if (!any_active) continue;  // (uniform)
+        // rounds of 256 entries, lane-contiguous; the loads of the next round are in flight while this one is composed
+        int2 tn[IT];
+        float xn[IT][LG];
+#pragma unroll
+        for (int q = 0; q < IT; q++) {
+            const int e = g.x + lane * IT + q;
+            tn[q] = e < g.y ? __ldg(ent + e) : make_int2(0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < IT; q++) gather_labels<LG>(in, tn[q].x, L, lb, g.x + lane * IT + q < g.y, xn[q]);
+        for (int r = 0; r < NR; r++) {
+            const int e0 = g.x + r * 256 + lane * IT;
+            const int n_valid = max(0, min(IT, g.y - e0));
+            float cq[LG][IT];
+#pragma unroll
+            for (int j = 0; j < LG; j++)
+#pragma unroll
+                for (int q = 0; q < IT; q++) cq[j][q] = __fmul_rn(__int_as_float(tn[q].y), xn[q][j]);
+            if (r + 1 < NR) {
+#pragma unroll
+                for (int q = 0; q < IT; q++) {
+                    const int e = e0 + 256 + q;
+                    tn[q] = e < g.y ? __ldg(ent + e) : make_int2(0, 0);
+                }
+#pragma unroll
+                for (int q = 0; q < IT; q++) gather_labels<LG>(in, tn[q].x, L, lb, e0 + 256 + q < g.y, xn[q]);
+            }
+#pragma unroll
+            for (int j = 0; j < LG; j++) {
+                if (T[j].kind == kRecPlain || T[j].kind == kRecCross) {  // (uniform)
+                    ChunkRec *ro = rec + (size_t)c * L + lb + j;
+                    if (T[j].mono) label_round<true>(T[j], cq[j], n_valid, r, lane, ro);
+                    else label_round<false>(T[j], cq[j], n_valid, r, lane, ro);
+                }
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < LG; j++) {
+                if (T[j].kind == kRecPlain || T[j].kind == kRecCross) {
+                    ChunkRec *ro = rec + (size_t)c * L + lb + j;
+                    ro->kind = T[j].kind;
+                    ro->E = T[j].E;
+                    ro->A = T[j].A;
+                    if (T[j].kind == kRecCross) ro->B = T[j].B;
+                }
             }
         }
     }
@@ -708,6 +745,7 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
     const int tid = threadIdx.x;
     if (blockIdx.x == 0 && tid == 0) {  // the compose launch in front is over: reset its tickets, retire its tag
         counts[3] = 0;
+        counts[9] = 0;
         counts[8] = counts[8] + 1;
     }
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
@@ -1446,12 +1484,10 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
         const int gk = (int)(maxc < kNumSMs * 3 ? maxc : kNumSMs * 3);  // compose: persistent, one resident wave
         const int gr = (int)(maxr < kNumSMs * 8 ? maxr : kNumSMs * 8);
         const int4 *desc = (const int4 *)ls->chunk_desc;
-        if (scan_labels(L) == 1) {
+        {
             LCCRF_KERNEL(ctx, "k_scan_compose");
-            k_scan_compose<1><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
-        } else {
-            LCCRF_KERNEL(ctx, "k_scan_compose");
-            k_scan_compose<2><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
+            if (scan_labels(L) == 1) k_scan_compose<1><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
+            else k_scan_compose<2><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
         }
         { LCCRF_KERNEL(ctx, "k_scan_walk");
           k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, L); }
