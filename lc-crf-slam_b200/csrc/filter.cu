@@ -366,8 +366,8 @@ __device__ __forceinline__ void thread_composite(const float *c, int n_valid, fl
 //   heads   (static, first CTAs): the first chunk of every long row, summed for real
 //   phase 2 (tickets counts[3]): composites; the prediction polls (ld.relaxed.gpu) the words of the chunks in front
 // Tickets are taken by running warps only and a word is published without waiting for anything, so a polling warp only
-// ever waits for warps that are running -- no residency assumption.  The tag (bumped by k_scan_walk behind every
-// compose launch) tells this call's words from older ones.
+// ever waits for warps that are running -- no residency assumption.  k_scan_walk clears the words it has walked and
+// bumps the tag behind every compose launch, so a word is 0 or belongs to the launch that is running.
 constexpr unsigned kPubNeg = 2u, kPubZero = 1u;
 __device__ __forceinline__ void publish_word(unsigned long long *p, unsigned tag, unsigned flags, float sum) {
     const unsigned long long w = ((unsigned long long)((tag << 2) | flags) << 32) | (unsigned long long)__float_as_uint(sum);
@@ -737,7 +737,7 @@ __device__ __forceinline__ bool apply_composite(float &s, int E, const Composite
 __global__ void __launch_bounds__(256)
 k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
             float *__restrict__ val, const int *__restrict__ list, int *counts,
-            const int *__restrict__ long_chunk0, const ChunkRec *__restrict__ rec, int L) {
+            const int *__restrict__ long_chunk0, const ChunkRec *__restrict__ rec, unsigned long long *chunk_sum, int L) {
     __shared__ ScanShared<8> sh;
     __shared__ ChunkRec s_rec[kWalkBatch];
     const long long n = (long long)counts[0] * L;
@@ -765,6 +765,9 @@ k_scan_walk(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const
                     const int j = w / W, o = w - j * W;
                     dst[w] = __ldg(src + ((size_t)(c0 + cb + j) * L + l) * W + o);
                 }
+                // the published word of every walked (chunk, label) is cleared for the next compose launch: a word is
+                // either 0 or carries the tag of the launch that is running, whatever the tag counter does
+                if (tid < nb) chunk_sum[(size_t)(c0 + cb + tid) * L + l] = 0ull;
             }
             __syncthreads();
             for (int j = 0; j < nb; j++) {
@@ -1490,7 +1493,7 @@ int filter_splat_blur(Ctx *ctx, const Batch &b, LatticeSet *ls, const float *in_
             else k_scan_compose<2><<<gk, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, ls->row_list_long, ls->row_counts, ls->long_chunk0, desc, ls->chunk_sum, (ChunkRec *)ls->chunk_rec, L);
         }
         { LCCRF_KERNEL(ctx, "k_scan_walk");
-          k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, L); }
+          k_scan_walk<<<gr, 256, 0, st>>>(ls->row_ptr, ls->csr_ent, in_dev, src, ls->row_list_long, ls->row_counts, ls->long_chunk0, (const ChunkRec *)ls->chunk_rec, ls->chunk_sum, L); }
     }
     if (split) {
         LCCRF_CUDA(cudaEventRecord(ctx->ev_sub_join[ctx->branch], ctx->sub_stream[ctx->branch]));
