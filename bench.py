@@ -100,7 +100,9 @@ def workload_config(workload: str, batch: int, splat: str) -> dict:
     cfg = {"workload": desc, "l2_policy": l2, "splat_mode": SPLAT_MODES[splat]}
     if workload == "c5":
         cfg.update({"sequences": C5_SEQUENCES, "frames_per_batch": batch, "problems_per_step": C5_SEQUENCES * batch,
-                    "sharding": "sequences round-robin over ranks (lc-crf-slam_b200/shard.py), no collective; strong scaling"})
+                    "sharding": "sequences round-robin over ranks (lc-crf-slam_b200/shard.py), no collective; strong scaling",
+                    "concurrency": "GPU arm: one context (stream, workspaces, map) per sequence, one host thread per sequence in "
+                                   "the end-to-end loop; reference arm: one host thread per frame CRF"})
     elif workload == "c4":
         cfg.update({"problems_per_step": batch,
                     "sharding": "ONE job of independent problems cut into contiguous ranges of balanced size over the ranks "
@@ -573,7 +575,10 @@ def run_gpu_arm_replay(args):
     sequence the host sends the frames' visible point ids + keypoints and one map delta (new keyframes with their
     keypoint rows and observations, culled observations, bad points, all poses, all positions).
       e2e    the pipelined loop (lccrf_frames_submit_visible / wait), host clock vs CUDA events, whichever is longer
-      value  the last frame batch of every sequence, K times, against the final map with its inputs resident"""
+      value  the last frame batch of every sequence, K times, against the final map with its inputs resident
+    Every sequence has its own context (stream, workspaces, map) and, in the pipelined loop, its own host thread -- as
+    the reference runs one tracking thread per sequence: the small kernels of a 64-frame batch do not fill a B200, and
+    the ~120 launches of a sequence-step are issued beside those of the other sequences."""
     import torch
     pkg = importlib.import_module("lc-crf-slam_b200")
     shard_mod = importlib.import_module("lc-crf-slam_b200.shard")
@@ -590,9 +595,6 @@ def run_gpu_arm_replay(args):
     desc, dbatch, _, _ = WORKLOADS["c5"]
     FB = args.batch or dbatch
     W, K = max(args.warmup, 3), args.steps
-    stream = torch.cuda.Stream()
-    ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
-    ctx.set_option("ordered_splat", 1 if args.splat == "ordered" else 0)
     prm = pkg.SlamParams.make()
     keep = []
 
@@ -615,6 +617,9 @@ def run_gpu_arm_replay(args):
         built = list(ex.map(build, local))
     S = []
     for s, (gen, kfs, xyz, ptr, ref, steps) in zip(local, built):
+        sq_stream = torch.cuda.Stream()
+        ctx = pkg.Context(local_rank, stream=sq_stream.cuda_stream)
+        ctx.set_option("ordered_splat", 1 if args.splat == "ordered" else 0)
         mp = pkg.Map(ctx, gen.stride)
         mp.apply(kf_pose=kfs["pose"], kf_intr=kfs["intr"], kf_bounds=kfs["bounds"], kf_keypoints=kfs["kp"], xyz=xyz)
         mp.set_observations(ptr, ref)
@@ -622,57 +627,73 @@ def run_gpu_arm_replay(args):
         NTs = int(sum(gen.sizes))
         pin_steps = [(keep_pinned(i), keep_pinned(k), pkg.MapDelta.make(pin=keep_pinned, **d)) for i, k, d in steps]
         outs = [(keep_pinned(np.zeros(NTs, np.int16)), keep_pinned(np.zeros((NTs, 2), np.float32))) for _ in (0, 1)]
-        S.append(dict(seq=s, gen=gen, mp=mp, F=F, steps=pin_steps, outs=outs, NT=NTs))
+        S.append(dict(seq=s, gen=gen, mp=mp, F=F, steps=pin_steps, outs=outs, NT=NTs, ctx=ctx, stream=sq_stream))
     del built
+    stream = S[0]["stream"] if S else torch.cuda.Stream()
+    pool = ThreadPoolExecutor(max_workers=max(1, len(S)))
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(i0, i1):
+    def seq_steps(st, i0, i1):
         for i in range(i0, i1):
-            for st in S:
-                ids, kp, delta = st["steps"][i]
-                st["F"].wait(i & 1)
-                st["F"].submit_visible(i & 1, st["mp"], ids, kp, st["outs"][i & 1][0], st["outs"][i & 1][1], delta=delta)
+            ids, kp, delta = st["steps"][i]
+            st["F"].wait(i & 1)
+            st["F"].submit_visible(i & 1, st["mp"], ids, kp, st["outs"][i & 1][0], st["outs"][i & 1][1], delta=delta)
+        st["F"].wait(0)
+        st["F"].wait(1)
+
+    def run_steps(i0, i1):  # one host thread per sequence (the C calls release the GIL)
+        if len(S) == 1:
+            seq_steps(S[0], i0, i1)
+        else:
+            list(pool.map(lambda st: seq_steps(st, i0, i1), S))
+
+    def all_launches():
+        return sum(st["ctx"].kernel_launches for st in S)
+
+    def elapsed_all(start):  # ms from `start` to the end of the work enqueued so far on every sequence's stream
+        ends = []
         for st in S:
-            st["F"].wait(0)
-            st["F"].wait(1)
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(st["stream"])
+            ends.append(e)
+        torch.cuda.synchronize()
+        return max(start.elapsed_time(e) for e in ends)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     with torch.cuda.stream(stream):
         run_steps(0, W)
-        l0 = ctx.kernel_launches
+        l0 = all_launches()
         barrier()
         t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)  # (the device is idle behind the barrier: a common start for every sequence's stream)
         t_sub = time.perf_counter()
         run_steps(W, W + K)
         t_sub = 1e3 * (time.perf_counter() - t_sub)   # host time inside the submit / wait calls of the timed steps
-        e1.record(stream)
+        ms_e2e_ev = elapsed_all(e0)
         barrier()
-        ms_e2e_ev, ms_e2e_wall = e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)
+        ms_e2e_wall = 1e3 * (time.perf_counter() - t0)
         ms_e2e = max(ms_e2e_ev, ms_e2e_wall)
-        launches = ctx.kernel_launches - l0
+        launches = all_launches() - l0
         last = [(st["outs"][(W + K - 1) & 1][0].copy(), st["outs"][(W + K - 1) & 1][1].copy()) for st in S]
         # device-resident: the LAST frame batch of every sequence K times against the final map (earlier batches name
         # points that have been culled since), inputs uploaded outside the timed region
-        ms = 0.0
         for st in S:
             ids, kp, _ = st["steps"][W + K - 1]
             st["F"].set_visible(st["mp"], ids, kp)
             st["F"].run()  # (first use after the pipelined loop: graph of slot 0)
             st["F"].run()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(K):
-                st["F"].run()
-            b.record(stream)
-            torch.cuda.synchronize()
-            ms += a.elapsed_time(b)
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(K):
+            for st in S:
+                st["F"].run()  # graph replays on the sequences' own streams, side by side
+        ms = elapsed_all(a)
         clocks = sampler.stop() if sampler else None
         # the last step once more against the final map: the pipelined loop delivered exactly these results
         for st, (m_, p_) in zip(S, last):
@@ -729,7 +750,7 @@ def run_gpu_arm_replay(args):
     nnz = int(round((ab["unary"] - st["NT"] * 24 - st["gen"].n_kf * 80) / 12.0))
     if not args.no_profile:
         with torch.cuda.stream(stream):
-            roofline, shares, kernel_ms = profile_kernels(ctx, st["F"], st["NT"], nnz, st["gen"].n_kf, prm.iters, peak, peak_src)
+            roofline, shares, kernel_ms = profile_kernels(st["ctx"], st["F"], st["NT"], nnz, st["gen"].n_kf, prm.iters, peak, peak_src)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
