@@ -556,6 +556,34 @@ def test_frames_from_map_snapshot_c3_small(pkg, ctx, oracle):
     F.close()
 
 
+def test_launch_structure_options_do_not_change_a_bit(pkg, ctx):
+    """graphs / concurrent / split_splat / fused only change HOW the launch sequence runs (graph replay, the two pairwise
+    kernels on two branches, the short-row splat beside the long-row scan kernels, the fused point pass): marginals and MAP
+    of a C3-shaped batch (long rows in the appearance lattice) must be bit-identical in every combination."""
+    snaps = [synth.map_snapshot(30000, 64, seed=40 + i) for i in range(2)]
+    cat = pkg.concat_frames(snaps)
+    ref = None
+    try:
+        for graphs, concurrent, split, fused in [(1, 1, 1, 1), (0, 1, 1, 1), (1, 0, 1, 1), (1, 1, 0, 1), (0, 0, 0, 0), (1, 1, 1, 0)]:
+            for k, v in (("graphs", graphs), ("concurrent", concurrent), ("split_splat", split), ("fused", fused)):
+                ctx.set_option(k, v)
+            F = pkg.Frames(ctx, [s.n for s in snaps])
+            F.set_map_inputs(cat["xyz"], cat["obs_ptr"], cat["obs_kf"], cat["obs_uv"], cat["kf_pose"], cat["kf_intr"],
+                             cat["kf_bounds"], cat["kp2d"], cat["kf_ptr"])
+            for _ in range(3):  # plain launches, capture, replay
+                F.run()
+            mp, pr = F.get_outputs()
+            F.close()
+            if ref is None:
+                ref = (mp.copy(), pr.copy())
+                assert 0 < mp.sum() < mp.size
+            else:
+                assert np.array_equal(mp, ref[0]) and np.array_equal(bits(pr), bits(ref[1])), (graphs, concurrent, split, fused)
+    finally:
+        for k in ("graphs", "concurrent", "split_splat", "fused"):
+            ctx.set_option(k, 1)
+
+
 def test_frames_rejects_points_without_observations(pkg, ctx):
     snap = synth.map_snapshot(64, 4, seed=1)
     ptr = snap.obs_ptr.copy()
