@@ -507,8 +507,8 @@ __device__ __forceinline__ void label_round(LabelTask &T, const float (&cq)[kSca
 template <int LG>
 __global__ void __launch_bounds__(256, 3)
 k_scan_compose(const int *__restrict__ row_ptr, const int2 *__restrict__ ent, const float *__restrict__ in,
-                 const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
-                 const int4 *__restrict__ chunk_desc, unsigned long long *chunk_sum, ChunkRec *__restrict__ rec, int L) {
+               const int *__restrict__ list, int *counts, const int *__restrict__ long_chunk0,
+               const int4 *__restrict__ chunk_desc, unsigned long long *chunk_sum, ChunkRec *__restrict__ rec, int L) {
     constexpr int IT = kScanIT, NR = kScanChunk / 256;
     __shared__ float s_head[8][256 * LG];
     const int ngrp = (L + LG - 1) / LG;
